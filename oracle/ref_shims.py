@@ -1,0 +1,163 @@
+"""ORACLE SUPPORT (test infrastructure): import the UNMODIFIED reference modules from
+/root/reference with in-memory shims for the five packages the image lacks (SURVEY.md
+section 8c).  None of the shims changes arithmetic.  /root/reference exists only in the
+build container, so this module is used solely by `tests/golden/make_golden.py` and by
+tests that are skipped when the reference tree is absent (e.g. on the GPU box).
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+from torch import nn
+
+REF_ROOT = "/root/reference/Unet_research"
+REF_CODE = os.path.join(REF_ROOT, "unet_code")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(REF_CODE)
+
+
+def _install_shims():
+    if not hasattr(np, "product"):
+        np.product = np.prod                      # utils_modules.py:5 (removed in numpy 2)
+
+    if "dropblock" not in sys.modules:
+        m = types.ModuleType("dropblock")
+
+        class LinearScheduler(nn.Module):
+            """dropblock==0.3.0 scheduler restated (PARITY UNPINNED, see unet_oracle)."""
+
+            def __init__(self, dropblock, start_value, stop_value, nr_steps):
+                super().__init__()
+                self.dropblock = dropblock
+                self.i = 0
+                self.drop_values = np.linspace(start=start_value, stop=stop_value, num=int(nr_steps))
+
+            def forward(self, x):
+                return self.dropblock(x)
+
+            def step(self):
+                if self.i < len(self.drop_values):
+                    self.dropblock.drop_prob = self.drop_values[self.i]
+                self.i += 1
+
+        m.LinearScheduler = LinearScheduler
+        sys.modules["dropblock"] = m
+
+    if "fairscale" not in sys.modules:
+        fs = types.ModuleType("fairscale")
+        fsnn = types.ModuleType("fairscale.nn")
+        fsnn.checkpoint_wrapper = lambda mod, *a, **k: mod      # identity: values unchanged
+        fs.nn = fsnn
+        sys.modules["fairscale"] = fs
+        sys.modules["fairscale.nn"] = fsnn
+
+    if "pytorch_lightning" not in sys.modules:
+        pl = types.ModuleType("pytorch_lightning")
+
+        class LightningModule(nn.Module):
+            def log(self, *a, **k):
+                pass
+
+            @classmethod
+            def load_from_checkpoint(cls, path, **kw):
+                obj = cls(**kw)
+                obj.load_state_dict(torch.load(path, map_location="cpu")["state_dict"])
+                return obj
+
+        class Trainer:
+            def __init__(self, *a, **k):
+                pass
+
+            @staticmethod
+            def add_argparse_args(p):
+                return p
+
+            @classmethod
+            def from_argparse_args(cls, *a, **k):
+                return cls()
+
+        def seed_everything(seed, workers=False):
+            import random
+            random.seed(seed)
+            np.random.seed(seed)
+            torch.manual_seed(seed)
+            return seed
+
+        pl.LightningModule = LightningModule
+        pl.Trainer = Trainer
+        pl.seed_everything = seed_everything
+        cb = types.ModuleType("pytorch_lightning.callbacks")
+        cb.ModelCheckpoint = cb.EarlyStopping = cb.LearningRateMonitor = lambda *a, **k: None
+        pl.callbacks = cb
+        sys.modules["pytorch_lightning"] = pl
+        sys.modules["pytorch_lightning.callbacks"] = cb
+
+    class _Fake(types.ModuleType):
+        """Attribute sink: plotting / sklearn entry points the oracle never calls."""
+
+        def __getattr__(self, item):
+            if item.startswith("__"):
+                raise AttributeError(item)
+            return lambda *a, **k: None
+
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.colors",
+                 "pandas", "sklearn", "sklearn.metrics"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                sys.modules[name] = _Fake(name)
+
+
+def load_reference():
+    """Returns a namespace with the reference's own classes: UNet, DropBlock2D,
+    Dropblock2d_ichan, LinearScheduler, BaseUNetTraining, DropBlockEval, set_dropblock_on,
+    RotationEval, UNetTraining."""
+    if not reference_available():
+        raise RuntimeError("reference tree not present at " + REF_CODE)
+    _install_shims()
+    if REF_CODE not in sys.path:
+        sys.path.insert(0, REF_CODE)
+    cwd = os.getcwd()
+    os.chdir(REF_ROOT)          # scripts do sys.path.append(os.getcwd() + '/unet_code')
+    try:
+        from utils import utils_unet, utils_modules, utils_training  # type: ignore
+
+        def load_script(name, rel):
+            spec = importlib.util.spec_from_file_location(name, os.path.join(REF_CODE, rel))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            return mod
+
+        db = load_script("ref_dropblock_uncertainty", "uncertainty_tests/Dropblock_Uncertainty.py")
+        rot = load_script("ref_rotational_uncertainty", "uncertainty_tests/Rotational_Uncertainty.py")
+        tr = load_script("ref_training", "base_model_tests/training.py")
+    finally:
+        os.chdir(cwd)
+    ns = types.SimpleNamespace(
+        UNet=utils_unet.UNet, DropBlock2D=utils_modules.DropBlock2D,
+        Dropblock2d_ichan=utils_modules.Dropblock2d_ichan, LinearScheduler=utils_modules.LinearScheduler,
+        BaseUNetTraining=utils_training.BaseUNetTraining, DropBlockEval=db.DropBlockEval,
+        set_dropblock_on=db.set_dropblock_on, RotationEval=rot.RotationEval, UNetTraining=tr.UNetTraining)
+    return ns
+
+
+def build_reference_unet(ref, init_channels=1, filters=64, dropblock=None, drop_prob=0.15, block_size=7,
+                         use_scheduler=False, num_groups=32, **sched):
+    """The canonical configuration of R/base_model_tests/training.py:171-192."""
+    unet = ref.UNet(init_channels=init_channels, filters=filters, output_channels=1, model_depth=4,
+                    pool_mode="max", up_mode="upconv", connection="cat", same_padding=True,
+                    conv_layers_per_block=2, checkpointing=True)
+    unet.set_activation_function(nn.ReLU())
+    if dropblock is not None:
+        unet.set_dropblock(dropblock, block_size=block_size, drop_prob=drop_prob, use_scheduler=use_scheduler, **sched)
+    unet.set_normalization(nn.GroupNorm, params={"num_groups": num_groups, "num_channels": "fill"})
+    unet.create_model()
+    return unet
