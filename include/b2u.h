@@ -1,0 +1,194 @@
+/* b2u.h -- C ABI of libb2u.so, the B200 (sm_100a) kernels behind the U-Net / MC-DropBlock hot path.
+ *
+ * The reference (JohnDLee/Unet-Research) is pure Python: it has no FFI layer, its "operators" are
+ * the torch.nn calls inside `UNet.forward` (unet_code/utils/utils_unet.py:408-449) and
+ * `DropBlock2D.forward` (unet_code/utils/utils_modules.py:36-66).  Each entry point below replaces
+ * the library op(s) named in its comment; the Python host (`unet_research_b200/`) binds them with
+ * ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - every pointer is a NON-OWNING DEVICE pointer into a caller-allocated buffer unless it is a
+ *    `const b2u_*_desc*` (host POD struct) or says "host";
+ *  - `stream` is a cudaStream_t passed as void*; all launches are asynchronous, allocate nothing,
+ *    never synchronise, and are CUDA-graph capturable;
+ *  - return 0 on success, B2U_ERR_* otherwise; `b2u_last_error()` returns a thread-local message;
+ *    nothing throws or exits across the ABI;
+ *  - activations are NHWC, `dtype` B2U_BF16 (bf16 storage, tcgen05 kind::f16) or B2U_F32 (fp32
+ *    storage, tcgen05 kind::tf32); GroupNorm statistics, coefficients and accumulators are fp32/fp64.
+ */
+#ifndef B2U_H_
+#define B2U_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2U_VERSION 1
+
+#define B2U_OK 0
+#define B2U_ERR_ARG 1
+#define B2U_ERR_CUDA 2
+#define B2U_ERR_UNSUPPORTED 3
+
+#define B2U_BF16 0
+#define B2U_F32 1
+
+const char* b2u_last_error(void);
+int b2u_version(void);
+/* SM count and max threads per SM of the current device (needed to reproduce torch.rand's launch
+ * geometry, ATen/native/cuda/DistributionTemplates.h:50-62). */
+int b2u_device_info(int* sm_count, int* max_threads_per_sm);
+
+/* ------------------------------------------------------------------ weight packing (once per model)
+ * nn.Conv2d weight [Cout,Cin,3,3] fp32 -> [9][Cout][Cin] (K-major per tap) in `dtype`.
+ * transpose_flip != 0 packs the data-gradient operand instead: [9][Cin][Cout] with taps rotated 180. */
+int b2u_pack_conv3x3_weight(const float* w, void* packed, int cout, int cin, int dtype, int transpose_flip,
+                            void* stream);
+/* nn.ConvTranspose2d weight [Cin,Cout,2,2] fp32 -> [4][Cout][Cin] (tap = 2*i+j) in `dtype`. */
+int b2u_pack_convT2x2_weight(const float* w, void* packed, int cin, int cout, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ tensor-core convolutions
+ * Implicit-GEMM 3x3 / stride 1 / zero "same" padding / no bias  (replaces nn.Conv2d at
+ * utils_unet.py:166-171,188-193,216-229,244-249,329-342,355-360) and the 2x2 stride-2 transposed
+ * convolution (nn.ConvTranspose2d, utils_unet.py:311-315) as TMA-fed tcgen05 GEMMs.
+ * Output is the RAW convolution result; per-(image, channel-subgroup) sum / sum-of-squares partials of
+ * the fp32 accumulators are written for the GroupNorm that follows (utils_unet.py:177 etc.). */
+typedef struct {
+  int32_t n, h, w;          /* input batch / height / width (pixels)                               */
+  int32_t cin, cout;        /* channels; cin % (128/sizeof(elt)) == 0, cout % 64 == 0              */
+  int32_t dtype;            /* B2U_BF16 | B2U_F32                                                  */
+  int32_t num_groups;       /* GroupNorm groups of the FOLLOWING norm; 0 = no statistics           */
+  int32_t x_cstride;        /* channel count of the tensor x lives in (>= cin; concat buffers)     */
+  int32_t reserved[4];
+} b2u_conv_desc;
+
+/* rows of the partial-statistics buffer per image and sub-group size:
+ * partials is float[n][rows][cout / sgs][2]. */
+int b2u_conv3x3_stat_layout(const b2u_conv_desc* d, int* rows_per_image, int* subgroup_size);
+int b2u_convT2x2_stat_layout(const b2u_conv_desc* d, int* rows_per_image, int* subgroup_size);
+/* x: [n,h,w,x_cstride]; wpacked: [9][cout][cin]; y: [n,h,w,cout]; partials may be NULL iff num_groups==0 */
+int b2u_conv3x3_fwd(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d,
+                    void* stream);
+/* x: [n,h,w,x_cstride]; wpacked: [4][cout][cin]; y: [n,2h,2w,cout] */
+int b2u_convT2x2_fwd(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d,
+                     void* stream);
+
+/* First layer (Cin = 1 or 3, K = 9*Cin is not a tensor-core job): reads the fp32 NCHW network input
+ * [n,cin,h0,w0] directly, applies UNet.autopad (utils_unet.py:451-458) by treating everything outside
+ * h0 x w0 as zero, writes raw NHWC [n,h,w,cout] + GroupNorm partials float[n][rows][cout/sgs][2]. */
+int b2u_conv_first_stat_layout(int h, int w, int cout, int num_groups, int* rows_per_image, int* subgroup_size);
+int b2u_conv_first_fwd(const float* x_nchw, const float* wgt /*[cout,cin,3,3] fp32*/, void* y, float* partials,
+                       int n, int cin, int h0, int w0, int h, int w, int cout, int num_groups, int dtype,
+                       void* stream);
+
+/* ------------------------------------------------------------------ GroupNorm (nn.GroupNorm(32, C), training.py:191)
+ * Reduce the partials of one tensor to per-(image, channel) affine coefficients
+ *   a = gamma * rstd * s,  b = (beta - mean * gamma * rstd) * s
+ * where s = numel_per_call / keep_count is the DropBlock rescale of the site that follows the norm
+ * (utils_modules.py:64; s > 0 so relu(s*z) = s*relu(z)); keep_counts == NULL means s = 1.
+ * coef: float2[n][c].  count = elements per (image, group) = (c/num_groups) * H * W. */
+int b2u_gn_finalize(const float* partials, int rows_per_image, int subgroup_size, const float* gamma,
+                    const float* beta, float* coef, int n, int c, int num_groups, double count, float eps,
+                    const unsigned long long* keep_counts, int images_per_call, double numel_per_call,
+                    void* stream);
+
+/* Fused normalise-affine [+ DropBlock mask] [+ ReLU] [+ second mask and rescale]: the elementwise tail
+ * of a conv unit (GroupNorm -> DropBlock -> ReLU, utils_unet.py:177-182) and, with mask2, the DropBlock
+ * applied to the concatenated tensor (utils_unet.py:382-383) folded into the producer's store.
+ *   v   = a*x + b;  v = mask1 ? v : 0;  v = relu ? max(v,0) : v;  out = mask2 ? v * s2 : 0
+ * Masks are bit-packed NHWC keep-masks (1 = keep), uint32[n][h][w][channels/32]. */
+typedef struct {
+  int32_t n, h, w, c;             /* logical tensor                                                 */
+  int32_t dtype;
+  int32_t relu;
+  int32_t out_cstride, out_coffset; /* output tensor channel count and first channel written        */
+  int32_t mask2_cstride, mask2_coffset; /* channel count / offset of the mask2 tensor (concat site)  */
+  int32_t images_per_call2;       /* images sharing one keep count of site 2                        */
+  int32_t reserved[3];
+  double numel_per_call2;         /* numel of one DropBlock call of site 2                          */
+} b2u_apply_desc;
+int b2u_gn_apply(const void* x, const float* coef, const uint32_t* mask1, const uint32_t* mask2,
+                 const unsigned long long* keep_counts2, void* out, const b2u_apply_desc* d, void* stream);
+
+/* Tail of an encoder block: the same fused apply, PLUS the 2x2/stride-2 max-pool of the activated tensor
+ * (nn.MaxPool2d, utils_unet.py:265-266) written raw with GroupNorm partials for the norm that follows the
+ * pool (utils_unet.py:282), PLUS the skip tensor written (with the concat-site mask2) into channels
+ * [out_coffset, out_coffset+c) of the decoder's concat buffer (replaces x.clone() :420 and torch.cat :382).
+ * pooled: [n,h/2,w/2,c]; pool_partials: float[n][rows][c/sgs][2]; argmax (optional, training): uint8
+ * [n,h/2,w/2,c] holding the window index 0..3 (row-major, first maximum wins as in ATen). */
+int b2u_pool_stat_layout(int h, int w, int c, int num_groups, int* rows_per_image, int* subgroup_size);
+int b2u_gn_apply_pool(const void* x, const float* coef, const uint32_t* mask1, const uint32_t* mask2,
+                      const unsigned long long* keep_counts2, void* skip_out, void* pooled, float* pool_partials,
+                      uint8_t* argmax, int pool_num_groups, const b2u_apply_desc* d, void* stream);
+
+/* ------------------------------------------------------------------ output head
+ * GroupNorm-affine + DropBlock mask + ReLU of the last conv unit, the 1x1 conv 64->1 (utils_unet.py:397-402),
+ * sigmoid (:404), crop to h0 x w0 (:440), clamp(0,1) (:443), NaN->0 (:444); then either
+ *   out != NULL : out[n][h0][w0] fp32                         (UNet.forward result), and / or
+ *   acc != NULL : Monte-Carlo accumulation of v = result * fov (Dropblock_Uncertainty.py:64-67):
+ *                 acc[0][pix] += sum_n v, acc[1][pix] += sum_n v*v (fp64), and the sample with global
+ *                 index (*iter_base + n) < return_num is stored to samples[idx][h0][w0].
+ * logits (optional): pre-sigmoid values [n][h0][w0] fp32 for parity checks. */
+typedef struct {
+  int32_t n, h, w, c;             /* padded tensor [n,h,w,c], c % 8 == 0, c <= 512                  */
+  int32_t h0, w0;                 /* un-padded output size                                           */
+  int32_t dtype;
+  int32_t return_num;
+  int32_t fov_per_image;          /* 0: one fov [h0][w0] shared by all images, 1: fov[n][h0][w0]    */
+  int32_t reserved[3];
+} b2u_head_desc;
+int b2u_head_fwd(const void* x, const float* coef, const uint32_t* mask1, const float* w_head, float* out,
+                 float* logits, const float* fov, double* acc, float* samples, const long long* iter_base,
+                 const b2u_head_desc* d, void* stream);
+/* mean = S1/T, std = sqrt(max((S2 - S1*S1/T)/(T-1), 0)) (unbiased, torch.std default) */
+int b2u_mc_finalize(const double* acc, float* mean, float* std, long long npix, long long t, void* stream);
+/* acc[0] += v, acc[1] += v*v for v = x[i] * fov (rotation ensemble accumulation of already-final samples) */
+int b2u_mc_accumulate(const float* x, const float* fov, double* acc, float* samples, const long long* iter_base,
+                      int n, long long npix, int return_num, void* stream);
+int b2u_advance_counter(long long* counter, long long delta, void* stream);
+
+/* ------------------------------------------------------------------ DropBlock masks (DropBlock2D.forward,
+ * utils_modules.py:46-58).  Two phases, both for a TABLE of calls so one launch covers all 22 sites of
+ * several Monte-Carlo iterations:
+ *  centers: bit p of call k = (torch.rand(...)[p] < gamma_k), reproducing torch's CUDA Philox stream for
+ *           (seed, offset_k) bit-exactly (Philox4x32-10; element order of
+ *           distribution_elementwise_grid_stride_kernel; raw-word thresholds instead of float compares);
+ *  dilate : zero-pad(bs/2) + bs x bs stride-1 max-pool + (1 - .) as a bitwise OR-smear, transposed to the
+ *           NHWC keep-mask layout, and the keep count (block_mask.sum()) per call.                     */
+typedef struct {
+  uint64_t philox_offset;     /* generator offset of this torch.rand call (multiple of 4)            */
+  uint64_t center_word_off;   /* first uint32 word of this call's centre bitmap                       */
+  uint64_t mask_word_off;     /* first uint32 word of this call's NHWC keep-mask                      */
+  uint32_t numel;             /* n_img * c * (h-bs+1) * (w-bs+1)                                      */
+  uint32_t grid;              /* torch's grid.x for this numel (host computes min(SMs*8, ceil(numel/256))) */
+  uint32_t thresh_lo;         /* centre = word < thresh_lo || word >= thresh_hi                       */
+  uint32_t thresh_hi;
+  int32_t n_img, c, h, w;     /* tensor this call masks                                               */
+  int32_t block_size;         /* odd, <= 31                                                           */
+  int32_t count_index;        /* slot of keep_counts this call adds to                                */
+  int32_t reserved[2];
+} b2u_dropblock_call;
+/* table: device array of n_calls descriptors; seed: host value; offset_base: device scalar added to every
+ * philox_offset (lets a captured CUDA graph advance the stream between replays); may be NULL. */
+int b2u_dropblock_centers(const b2u_dropblock_call* table, int n_calls, uint64_t seed,
+                          const unsigned long long* offset_base, uint32_t* center_bits, void* stream);
+int b2u_dropblock_dilate(const b2u_dropblock_call* table, int n_calls, const b2u_dropblock_call* host_table,
+                         const uint32_t* center_bits, uint32_t* mask_bits, unsigned long long* keep_counts,
+                         void* stream);
+/* centre bitmap from caller-supplied uniforms (parity mode: feed the oracle's captured torch.rand values) */
+int b2u_dropblock_centers_from_uniform(const float* u, uint32_t* center_bits, long long numel, float gamma,
+                                       void* stream);
+
+/* ------------------------------------------------------------------ rotation (torchvision TF.rotate, BILINEAR,
+ * fill 0, as called at Rotational_Uncertainty.py:54,58): affine grid in fp32, grid_sample(bilinear, zeros,
+ * align_corners=False) of the image and of a ones channel, result img*m.  x,out: [n][c][h][w] fp32;
+ * angles_deg: host array of n angles (counter-clockwise degrees, as passed to TF.rotate). */
+int b2u_rotate_bilinear(const float* x, float* out, int n, int c, int h, int w, const double* angles_deg,
+                        int x_batch_stride_is_zero, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2U_H_ */

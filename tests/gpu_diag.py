@@ -1,0 +1,433 @@
+"""GPU bring-up diagnostics (run on the B200 box through gpurun):
+
+    python tests/gpu_diag.py            # every section, each in its own subprocess (a trapped kernel
+                                        # kills only its section), summary in gpurun_out/diag.log
+    python tests/gpu_diag.py conv       # one section in-process
+
+Not a pytest file: it prints error magnitudes instead of asserting, to get the most out of one GPU call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+import time
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+SECTIONS = ["info", "conv", "convt", "first", "gn", "pool", "head", "dropblock", "rotate", "forward", "mc", "rot_ens", "tf32"]
+
+
+def rel(a, b):
+    import torch
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30)), float((a - b).abs().max())
+
+
+def sec_info():
+    import torch
+    from unet_research_b200 import _lib
+    from unet_research_b200.engine import device_rand_geometry
+    _lib.load()
+    print("device", torch.cuda.get_device_name(0), "sms/maxthreads", device_rand_geometry())
+    print("torch", torch.__version__, "cuda", torch.version.cuda)
+
+
+def _conv_case(n, h, w, cin, cout, dtype, conv_t=False, block_n=0, stages=0):
+    import torch
+    import torch.nn.functional as F
+    from unet_research_b200 import _lib
+    from unet_research_b200._lib import ConvDesc, call, ptr, stream_ptr
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(cin * 1000 + cout + h)
+    tdt = torch.float32 if dtype == _lib.F32 else torch.bfloat16
+    x = torch.randn(n, cin, h, w, generator=g).to(dev)
+    if conv_t:
+        wt = (torch.randn(cin, cout, 2, 2, generator=g) / (cin ** 0.5)).to(dev)
+    else:
+        wt = (torch.randn(cout, cin, 3, 3, generator=g) / ((9 * cin) ** 0.5)).to(dev)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().to(tdt)
+    G = 32
+    d = ConvDesc()
+    d.n, d.h, d.w, d.cin, d.cout, d.dtype, d.num_groups, d.x_cstride = n, h, w, cin, cout, dtype, G, cin
+    d.reserved[0], d.reserved[1] = block_n, stages
+    rows, sgs = C.c_int(0), C.c_int(0)
+    call("b2u_convT2x2_stat_layout" if conv_t else "b2u_conv3x3_stat_layout", C.byref(d), C.byref(rows), C.byref(sgs))
+    oh, ow = (2 * h, 2 * w) if conv_t else (h, w)
+    y = torch.full((n, oh, ow, cout), float("nan"), dtype=tdt, device=dev)
+    parts = torch.full((n, rows.value, cout // sgs.value, 2), float("nan"), dtype=torch.float32, device=dev)
+    if conv_t:
+        packed = torch.empty(4, cout, cin, dtype=tdt, device=dev)
+        call("b2u_pack_convT2x2_weight", ptr(wt), ptr(packed), cin, cout, dtype, stream_ptr())
+    else:
+        packed = torch.empty(9, cout, cin, dtype=tdt, device=dev)
+        call("b2u_pack_conv3x3_weight", ptr(wt), ptr(packed), cout, cin, dtype, 0, stream_ptr())
+    call("b2u_convT2x2_fwd" if conv_t else "b2u_conv3x3_fwd", ptr(x_nhwc), ptr(packed), ptr(y), ptr(parts), C.byref(d), stream_ptr())
+    torch.cuda.synchronize()
+    # reference on the SAME rounded operands, fp32 math (TF32 off)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    xr = x_nhwc.float().permute(0, 3, 1, 2).double()
+    wr = wt.to(tdt).float().double() if dtype == _lib.BF16 else wt.double()
+    ref = (F.conv_transpose2d(xr, wr, stride=2) if conv_t else F.conv2d(xr, wr, padding=1)).float()
+    got = y.float().permute(0, 3, 1, 2)
+    r, mx = rel(got, ref)
+    # statistics: per (image, group) sums
+    gs = cout // G
+    ps = parts.double().sum(1).view(n, G, -1, 2).sum(2)          # [n, G, 2]
+    rs = ref.double().view(n, G, gs * oh * ow)
+    s_ref = torch.stack([rs.sum(-1), (rs * rs).sum(-1)], -1)
+    sr, _ = rel(ps, s_ref)
+    nan = int(torch.isnan(got).sum())
+    print(f"  {'convT' if conv_t else 'conv3'} n{n} {h}x{w} {cin}->{cout} dt{dtype} bn{block_n} st{stages}: rel {r:.3e} max {mx:.3e} stats_rel {sr:.3e} nan {nan} rows {rows.value} sgs {sgs.value}")
+    return r
+
+
+def sec_conv():
+    from unet_research_b200 import _lib
+    _conv_case(1, 16, 16, 64, 64, _lib.BF16)
+    _conv_case(2, 24, 40, 64, 64, _lib.BF16)
+    _conv_case(1, 37, 36, 128, 128, _lib.BF16)
+    _conv_case(2, 20, 24, 128, 256, _lib.BF16)
+    _conv_case(1, 74, 72, 512, 512, _lib.BF16)
+    _conv_case(1, 37, 36, 1024, 1024, _lib.BF16)
+    _conv_case(1, 16, 16, 128, 64, _lib.BF16)
+    _conv_case(1, 33, 47, 64, 128, _lib.BF16, block_n=64)
+    _conv_case(1, 32, 32, 256, 256, _lib.BF16, block_n=128, stages=2)
+    _conv_case(1, 592, 576, 64, 64, _lib.BF16)
+
+
+def sec_convt():
+    from unet_research_b200 import _lib
+    _conv_case(1, 16, 16, 128, 64, _lib.BF16, conv_t=True)
+    _conv_case(2, 37, 36, 1024, 512, _lib.BF16, conv_t=True)
+    _conv_case(1, 20, 24, 256, 128, _lib.BF16, conv_t=True)
+
+
+def sec_tf32():
+    from unet_research_b200 import _lib
+    _conv_case(1, 16, 16, 64, 64, _lib.F32)
+    _conv_case(2, 24, 40, 128, 256, _lib.F32)
+    _conv_case(1, 16, 16, 128, 64, _lib.F32, conv_t=True)
+    _forward_case(120, 116, 1, "tf32")
+
+
+def sec_first():
+    import torch
+    import torch.nn.functional as F
+    from unet_research_b200 import _lib
+    from unet_research_b200._lib import call, ptr, stream_ptr
+    dev = torch.device("cuda")
+    for cin, (h0, w0), (h, w) in ((1, (120, 116), (128, 128)), (3, (64, 80), (64, 80)), (1, (584, 565), (592, 576))):
+        g = torch.Generator().manual_seed(5)
+        x = torch.rand(2, cin, h0, w0, generator=g).to(dev)
+        wt = torch.randn(64, cin, 3, 3, generator=g).to(dev)
+        rows, sgs = C.c_int(0), C.c_int(0)
+        call("b2u_conv_first_stat_layout", h, w, 64, 32, C.byref(rows), C.byref(sgs))
+        y = torch.empty(2, h, w, 64, dtype=torch.bfloat16, device=dev)
+        parts = torch.empty(2, rows.value, 64 // sgs.value, 2, dtype=torch.float32, device=dev)
+        call("b2u_conv_first_fwd", ptr(x), ptr(wt), ptr(y), ptr(parts), 2, cin, h0, w0, h, w, 64, 32, _lib.BF16, stream_ptr())
+        torch.cuda.synchronize()
+        ref = F.conv2d(F.pad(x, (0, w - w0, 0, h - h0)).double(), wt.double(), padding=1).float()
+        r, mx = rel(y.float().permute(0, 3, 1, 2), ref)
+        ps = parts.double().sum(1).view(2, 32, -1, 2).sum(2)
+        rs = ref.double().view(2, 32, -1)
+        sr, _ = rel(ps, torch.stack([rs.sum(-1), (rs * rs).sum(-1)], -1))
+        print(f"  first cin{cin} {h0}x{w0}->{h}x{w}: rel {r:.3e} max {mx:.3e} stats_rel {sr:.3e}")
+
+
+def sec_gn():
+    import torch
+    import torch.nn.functional as F
+    from unet_research_b200 import _lib
+    from unet_research_b200._lib import ApplyDesc, call, ptr, stream_ptr
+    dev = torch.device("cuda")
+    for c, h, w in ((64, 32, 48), (256, 20, 24), (1024, 8, 8)):
+        n, G = 2, 32
+        g = torch.Generator().manual_seed(c)
+        x = (torch.randn(n, c, h, w, generator=g) * 2 + 0.5).to(dev)
+        gamma = (1 + 0.1 * torch.randn(c, generator=g)).to(dev)
+        beta = (0.1 * torch.randn(c, generator=g)).to(dev)
+        x_nhwc = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        xr = x_nhwc.float().permute(0, 3, 1, 2)
+        # partials: one row per image built with torch (the conv epilogue is tested in `conv`)
+        gs = c // G
+        sgs = min(gs, 32)
+        v = xr.double().reshape(n, c // sgs, sgs * h * w)
+        parts = torch.stack([v.sum(-1), (v * v).sum(-1)], -1).float().view(n, 1, c // sgs, 2).contiguous()
+        coef = torch.empty(n, c, 2, dtype=torch.float32, device=dev)
+        call("b2u_gn_finalize", ptr(parts), 1, sgs, ptr(gamma), ptr(beta), ptr(coef), n, c, G, float(gs * h * w), 1e-5, None, 1, 0.0, stream_ptr())
+        a = ApplyDesc()
+        a.n, a.h, a.w, a.c, a.dtype, a.relu, a.out_cstride, a.out_coffset = n, h, w, c, _lib.BF16, 1, c, 0
+        a.images_per_call2 = 1
+        out = torch.empty_like(x_nhwc)
+        call("b2u_gn_apply", ptr(x_nhwc), ptr(coef), None, None, None, ptr(out), C.byref(a), stream_ptr())
+        torch.cuda.synchronize()
+        ref = F.relu(F.group_norm(xr, G, gamma, beta, 1e-5))
+        r, mx = rel(out.float().permute(0, 3, 1, 2), ref)
+        print(f"  gn+relu c{c} {h}x{w}: rel {r:.3e} max {mx:.3e}")
+
+
+def sec_pool():
+    import torch
+    import torch.nn.functional as F
+    from unet_research_b200 import _lib
+    from unet_research_b200._lib import ApplyDesc, call, ptr, stream_ptr
+    dev = torch.device("cuda")
+    for c, h, w in ((64, 32, 48), (512, 12, 8)):
+        n, G = 2, 32
+        g = torch.Generator().manual_seed(c + 1)
+        x = torch.randn(n, c, h, w, generator=g).to(dev)
+        x_nhwc = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        xr = x_nhwc.float().permute(0, 3, 1, 2)
+        coef = torch.empty(n, c, 2, dtype=torch.float32, device=dev)
+        coef[..., 0] = 1.5
+        coef[..., 1] = -0.25
+        rows, sgs = C.c_int(0), C.c_int(0)
+        call("b2u_pool_stat_layout", h, w, c, G, C.byref(rows), C.byref(sgs))
+        cat = torch.zeros(n, h, w, 2 * c, dtype=torch.bfloat16, device=dev)
+        pooled = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device=dev)
+        parts = torch.empty(n, rows.value, c // sgs.value, 2, dtype=torch.float32, device=dev)
+        arg = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device=dev)
+        a = ApplyDesc()
+        a.n, a.h, a.w, a.c, a.dtype, a.relu, a.out_cstride, a.out_coffset = n, h, w, c, _lib.BF16, 1, 2 * c, c
+        a.images_per_call2 = 1
+        call("b2u_gn_apply_pool", ptr(x_nhwc), ptr(coef), None, None, None, ptr(cat), ptr(pooled), ptr(parts), ptr(arg), G, C.byref(a), stream_ptr())
+        torch.cuda.synchronize()
+        act = F.relu(xr * 1.5 - 0.25)
+        pr, idx = F.max_pool2d(act, 2, 2, return_indices=True)
+        r1, _ = rel(cat[..., c:].float().permute(0, 3, 1, 2), act)
+        r2, _ = rel(pooled.float().permute(0, 3, 1, 2), pr)
+        # window index from flat index
+        iy, ix = idx // w, idx % w
+        win = ((iy % 2) * 2 + (ix % 2)).to(torch.uint8)
+        argmatch = float((arg.permute(0, 3, 1, 2) == win).float().mean())
+        ps = parts.double().sum(1).view(n, G, -1, 2).sum(2)
+        rs = pooled.float().permute(0, 3, 1, 2).double().reshape(n, G, -1)
+        sr, _ = rel(ps, torch.stack([rs.sum(-1), (rs * rs).sum(-1)], -1))
+        print(f"  apply_pool c{c}: skip rel {r1:.3e} pooled rel {r2:.3e} argmax match {argmatch:.6f} stats_rel {sr:.3e} first-half-untouched {float(cat[..., :c].abs().max()):.1f}")
+
+
+def sec_head():
+    import torch
+    from unet_research_b200 import _lib
+    from unet_research_b200._lib import HeadDesc, call, ptr, stream_ptr
+    dev = torch.device("cuda")
+    n, c, h, w, h0, w0 = 3, 64, 32, 48, 29, 45
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(n, h, w, c, generator=g).to(dev).to(torch.bfloat16)
+    coef = torch.stack([1 + 0.1 * torch.randn(n, c, generator=g), 0.1 * torch.randn(n, c, generator=g)], -1).to(dev).contiguous()
+    wh = (torch.randn(c, generator=g) / 8).to(dev)
+    fov = (torch.rand(h0, w0, generator=g) > 0.3).float().to(dev)
+    out = torch.empty(n, 1, h0, w0, device=dev)
+    logits = torch.empty(n, 1, h0, w0, device=dev)
+    acc = torch.zeros(2, h0, w0, dtype=torch.float64, device=dev)
+    samples = torch.zeros(2, h0, w0, device=dev)
+    it = torch.zeros(1, dtype=torch.int64, device=dev)
+    hd = HeadDesc()
+    hd.n, hd.h, hd.w, hd.c, hd.h0, hd.w0, hd.dtype, hd.return_num = n, h, w, c, h0, w0, _lib.BF16, 2
+    call("b2u_head_fwd", ptr(x), ptr(coef), None, ptr(wh), ptr(out), ptr(logits), ptr(fov), ptr(acc), ptr(samples), ptr(it), C.byref(hd), stream_ptr())
+    torch.cuda.synchronize()
+    z = torch.relu(x.float() * coef[:, None, None, :, 0] + coef[:, None, None, :, 1])
+    lg = (z * wh).sum(-1)[:, :h0, :w0]
+    y = torch.sigmoid(lg)
+    r1, m1 = rel(logits[:, 0], lg)
+    r2, m2 = rel(out[:, 0], y)
+    v = y * fov
+    r3, _ = rel(acc[0], v.double().sum(0))
+    r4, _ = rel(acc[1], (v.double() ** 2).sum(0))
+    r5, _ = rel(samples, v[:2])
+    print(f"  head: logits rel {r1:.3e} max {m1:.3e}; out rel {r2:.3e}; acc rel {r3:.3e} {r4:.3e}; samples rel {r5:.3e}")
+
+
+def sec_dropblock():
+    import torch
+    from oracle import unet_oracle as O
+    from unet_research_b200.modules import DropBlock2D
+    dev = torch.device("cuda")
+    # (a) does torch compare `rand < gamma` in fp32?  (b) bit-exact masks vs the oracle using torch.rand on this GPU
+    for shape in ((1, 64, 128, 128), (2, 32, 37, 36), (1, 64, 592, 576), (1, 1024, 37, 36), (3, 96, 9, 50)):
+        x = torch.randn(*shape, device=dev)
+        torch.manual_seed(1234)
+        _ = torch.rand(7, device=dev)                 # move the offset off zero
+        rec = []
+        ref = O.dropblock2d(x, 0.15, 7, True, record=rec)
+        off_ref = torch.cuda.default_generators[0].get_offset()
+        torch.manual_seed(1234)
+        _ = torch.rand(7, device=dev)
+        db = DropBlock2D(0.15, 7)
+        db.train()
+        m, keep = db.block_mask(x)
+        off_got = torch.cuda.default_generators[0].get_offset()
+        mism = int((m != rec[0]).sum())
+        torch.manual_seed(1234)
+        _ = torch.rand(7, device=dev)
+        got = db(x)
+        r, mx = rel(got, ref)
+        print(f"  dropblock {shape}: mask mismatches {mism} / {m.numel()}  keep {int(keep)} vs {int(rec[0].sum())}  offset {off_got} vs {off_ref}  out rel {r:.2e}")
+
+
+def sec_rotate():
+    import torch
+    from oracle import unet_oracle as O
+    from unet_research_b200._lib import call, ptr, stream_ptr
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(1, 1, 584, 565, generator=g).to(dev)
+    angs = [1.0, 45.0, 90.0, 179.0, 359.0, -33.0]
+    out = torch.empty(len(angs), 1, 584, 565, device=dev)
+    arr = (C.c_double * len(angs))(*angs)
+    call("b2u_rotate_bilinear", ptr(x), ptr(out), len(angs), 1, 584, 565, arr, 1, stream_ptr())
+    torch.cuda.synchronize()
+    for i, a in enumerate(angs):
+        ref = O.rotate_bilinear(x, a)
+        r, mx = rel(out[i:i + 1], ref)
+        print(f"  rotate {a}: rel {r:.3e} max {mx:.3e}")
+
+
+def _build_model(dev, dropblock=False, compute="bf16", init_channels=1):
+    import torch
+    from torch import nn
+    import unet_research_b200 as U
+    from unet_research_b200 import synthetic
+    m = U.UNet(init_channels=init_channels, filters=64, output_channels=1, model_depth=4)
+    m.set_activation_function(nn.ReLU())
+    if dropblock:
+        m.set_dropblock(U.DropBlock2D, block_size=7, drop_prob=0.15, use_scheduler=False)
+    m.set_normalization(nn.GroupNorm, params={"num_groups": 32, "num_channels": "fill"})
+    m.create_model()
+    sd = synthetic.make_state_dict(init_channels=init_channels, seed=1234)
+    m.load_state_dict(sd)
+    m.compute_dtype = compute
+    m.to(dev)
+    m.eval()
+    return m, {k: v.to(dev) for k, v in sd.items()}
+
+
+def _forward_case(h, w, n, compute):
+    import torch
+    from oracle import unet_oracle as O
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m, sd = _build_model(dev, compute=compute)
+    x = synthetic.make_image(h, w, seed=1234, batch=n).to(dev)
+    with torch.no_grad():
+        eng = m._get_engine(dev)
+        ws = eng.workspace(n, h, w)
+        out = eng.forward(x, ws, None, want_logits=True).clone()
+        lg = ws.logits.clone()
+        torch.cuda.synchronize()
+        taps = {}
+        ref = O.unet_forward(sd, x, taps=taps)
+        ref_lg = taps["logits"][:, :, :h, :w]
+    r, mx = rel(out, ref)
+    rl, ml = rel(lg, ref_lg)
+    print(f"  forward {compute} n{n} {h}x{w}: out rel {r:.3e} max {mx:.3e}; logits rel {rl:.3e} max {ml:.3e} (|logit| max {float(ref_lg.abs().max()):.2f})")
+    # per-layer raw conv outputs
+    B = ws.buf
+    names = {"d0.c1.conv": "d0.raw1", "d0.c2.conv": "d0.raw2", "d1.c1.conv": "d1.raw1", "d3.c2.conv": "d3.raw2",
+             "b.c1.conv": "b.raw1", "b.c2.conv": "b.raw2", "u0.up": "u0.rawT", "u0.c1.conv": "u0.raw1", "u3.c1.conv": "u3.raw1",
+             "u3.c2.conv": "u3.raw2", "d0.pool": "d0.praw"}
+    for tname, bname in names.items():
+        rr, _ = rel(B[bname].float().permute(0, 3, 1, 2), taps[tname])
+        print(f"     {tname:12s} rel {rr:.3e}")
+
+
+def sec_forward():
+    _forward_case(120, 116, 1, "bf16")
+    _forward_case(120, 116, 3, "bf16")
+    _forward_case(584, 565, 1, "bf16")
+    # module API + golden vector from the unmodified reference
+    import numpy as np
+    import torch
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    m, _ = _build_model(dev)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "unet_eval_120x116.npz"))
+    with torch.no_grad():
+        y = m(synthetic.make_image(120, 116, seed=1234).to(dev))
+    r, mx = rel(y.cpu(), torch.from_numpy(g["output"]))
+    print(f"  module forward vs reference golden: rel {r:.3e} max {mx:.3e}")
+
+
+def sec_mc():
+    import torch
+    from oracle import unet_oracle as O
+    import unet_research_b200 as U
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    h, w = 120, 116
+    m, sd = _build_model(dev, dropblock=True)
+    x = synthetic.make_image(h, w, seed=1234).to(dev)
+    fov = synthetic.make_fov_mask(h, w).to(dev)
+    T = 6
+    for graph in (False, True):
+        ev = U.DropBlockEval(m, num_iterations=T, return_num=4, iter_batch=2, use_cuda_graph=graph)
+        torch.manual_seed(77)
+        _, (mean, std, tens) = ev.predict_step((x, None, fov), 0)
+        off_got = torch.cuda.default_generators[0].get_offset()
+        torch.cuda.synchronize()
+        torch.manual_seed(77)
+        rmean, rstd, rtens = O.mc_dropblock(sd, x, fov, T, 4, 0.15, 7)
+        off_ref = torch.cuda.default_generators[0].get_offset()
+        print(f"  mc graph={graph}: mean rel {rel(mean, rmean)[0]:.3e} std rel {rel(std, rstd)[0]:.3e} samples rel {rel(tens, rtens)[0]:.3e} "
+              f"max|std-ref| {rel(std, rstd)[1]:.3e} (std max {float(rstd.max()):.3f}) offset {off_got} vs {off_ref}")
+        for i in range(4):
+            print(f"     sample {i}: rel {rel(tens[i], rtens[i])[0]:.3e}")
+
+
+def sec_rot_ens():
+    import torch
+    from oracle import unet_oracle as O
+    import unet_research_b200 as U
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    h, w = 120, 116
+    m, sd = _build_model(dev)
+    x = synthetic.make_image(h, w, seed=1234).to(dev)
+    fov = synthetic.make_fov_mask(h, w).to(dev)
+    ev = U.RotationEval(m, num_iterations=5, return_num=3, angle_batch=2)
+    _, (mean, std, tens) = ev.predict_step((x, None, fov), 0)
+    rmean, rstd, rtens = O.rotation_ensemble(sd, x, fov, 5, 3)
+    print(f"  rotation ensemble: mean rel {rel(mean, rmean)[0]:.3e} std rel {rel(std, rstd)[0]:.3e} max|d| {rel(std, rstd)[1]:.3e} samples rel {rel(tens, rtens)[0]:.3e}")
+
+
+def main():
+    if len(sys.argv) > 1:
+        name = sys.argv[1]
+        print(f"== {name}", flush=True)
+        t = time.time()
+        try:
+            globals()["sec_" + name]()
+            print(f"== {name} done in {time.time() - t:.1f}s", flush=True)
+        except Exception:
+            traceback.print_exc()
+            print(f"== {name} FAILED", flush=True)
+            sys.exit(1)
+        return
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    log = open(os.path.join(ROOT, "gpurun_out", "diag.log"), "w")
+    for name in SECTIONS:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), name], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                               text=True, timeout=600)
+            out = r.stdout
+        except subprocess.TimeoutExpired as e:
+            out = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+            out += f"\n== {name} TIMEOUT\n"
+        print(out, flush=True)
+        log.write(out)
+        log.flush()
+
+
+if __name__ == "__main__":
+    main()

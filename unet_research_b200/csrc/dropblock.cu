@@ -1,0 +1,228 @@
+// DropBlock mask construction (DropBlock2D.forward, reference utils_modules.py:46-58) as two
+// integer kernels over a table of calls:
+//
+//  centers : reproduces `torch.rand(N,C,H-bs+1,W-bs+1, device='cuda') < gamma` bit-exactly for a given
+//            (seed, philox offset): Philox4x32-10 keyed by the seed, counter = (offset/4 + trip, 0, idx, 0),
+//            thread idx's trip-t draw supplies elements idx + Tn*(4t+ii), ii = 0..3, Tn = 256*grid
+//            (ATen/native/cuda/DistributionTemplates.h:65-90).  One warp evaluates 32 consecutive idx,
+//            compares the raw 32-bit words against host-computed thresholds (equivalent to the fp32
+//            compare incl. the 1.0 -> 0.0 wrap) and writes four ballot words of a flat bitmap.
+//  dilate  : block_mask = 1 - maxpool_{bs x bs, stride 1, pad bs/2}(zero_pad_{bs/2}(centre)) becomes
+//            drop(h,w) = OR_{i,j<bs} centre[h-i][w-j]: a horizontal bit-smear, a vertical OR over a sliding
+//            window of bs rows, a 32x32 bit transpose (channel-major -> NHWC pixel-major) with warp ballots
+//            and a popcount for block_mask.sum().
+#include "b2u_common.cuh"
+
+namespace b2u {
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0;
+    const uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// grid = (blocks, n_calls).  Each warp-iteration: 32 consecutive thread indices of torch's launch, one trip.
+__global__ void __launch_bounds__(256) dropblock_centers_kernel(const b2u_dropblock_call* __restrict__ table, uint64_t seed,
+                                         const unsigned long long* __restrict__ offset_base,
+                                         uint32_t* __restrict__ center_bits) {
+  const b2u_dropblock_call c = table[blockIdx.y];
+  const uint32_t tn = c.grid * 256u;
+  const uint64_t trips = (static_cast<uint64_t>(c.numel) - 1) / (static_cast<uint64_t>(tn) * 4) + 1;
+  const uint32_t warps_per_trip = tn / 32;
+  const uint64_t total_warp_items = trips * warps_per_trip;
+  const uint64_t off = c.philox_offset + (offset_base ? *offset_base : 0ull);
+  const uint64_t ctr_base = off >> 2;                      // curand skipahead: offset counts 32-bit words
+  const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  const int lane = threadIdx.x & 31;
+  uint32_t* out = center_bits + c.center_word_off;
+  const uint64_t warp_global = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t warp_stride = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (uint64_t item = warp_global; item < total_warp_items; item += warp_stride) {
+    const uint64_t trip = item / warps_per_trip;
+    const uint32_t idx0 = static_cast<uint32_t>(item - trip * warps_per_trip) * 32u;
+    const uint64_t ctr = ctr_base + trip;
+    uint32_t r[4];
+    philox4x32_10(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), idx0 + lane, 0u, k0, k1, r);
+    uint32_t words[4];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) words[ii] = __ballot_sync(0xffffffffu, r[ii] < c.thresh_lo || r[ii] >= c.thresh_hi);
+    if (lane < 4) {
+      const uint64_t p0 = trip * 4ull * tn + static_cast<uint64_t>(lane) * tn + idx0;   // first element of this word
+      if (p0 < c.numel) {
+        const uint32_t wsel = lane == 0 ? words[0] : lane == 1 ? words[1] : lane == 2 ? words[2] : words[3];
+        out[p0 >> 5] = wsel;
+      }
+    }
+  }
+}
+
+__global__ void dropblock_centers_from_uniform_kernel(const float* __restrict__ u, uint32_t* __restrict__ bits,
+                                                      long long numel, float gamma) {
+  const long long nwords = (numel + 31) / 32;
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long warp_stride = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long wd = warp_global; wd < nwords; wd += warp_stride) {
+    const long long i = wd * 32 + lane;
+    const bool b = i < numel && u[i] < gamma;
+    const uint32_t word = __ballot_sync(0xffffffffu, b);
+    if (lane == 0) bits[wd] = word;
+  }
+}
+
+// 32 bits of a centre row: bit k = centre[x = xa + k] (0 outside [0, wc)); row starts at bit `rowbit`
+// of the flat bitmap.
+__device__ __forceinline__ uint32_t row_bits(const uint32_t* __restrict__ bits, uint64_t rowbit, int xa, int wc) {
+  if (xa <= -32 || xa >= wc) return 0u;
+  int shift_in = 0;
+  if (xa < 0) {
+    shift_in = -xa;
+    xa = 0;
+  }
+  const uint64_t q = rowbit + static_cast<uint64_t>(xa);
+  const uint64_t wi = q >> 5;
+  const uint32_t sh = static_cast<uint32_t>(q & 31);
+  uint32_t v = __funnelshift_r(__ldg(bits + wi), __ldg(bits + wi + 1), sh);
+  const int cnt = wc - xa;                                  // valid bits from xa
+  if (cnt < 32) v &= (1u << cnt) - 1u;
+  return shift_in ? (v << shift_in) : v;
+}
+
+// One warp: 32 channels (lane = channel) x 32 pixels of one image row band.
+// grid = (bands * wwords, c/32 * n_img, n_calls).
+template <int RING>
+__global__ void __launch_bounds__(128) dropblock_dilate_kernel(const b2u_dropblock_call* __restrict__ table,
+                                        const uint32_t* __restrict__ center_bits, uint32_t* __restrict__ mask_bits,
+                                        unsigned long long* __restrict__ keep_counts, int band_rows) {
+  const b2u_dropblock_call c = table[blockIdx.z];
+  const int cgs = c.c >> 5;
+  const int wwords = (c.w + 31) >> 5;
+  const int bands = (c.h + band_rows - 1) / band_rows;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + warp_in_block;       // (band, wword)
+  const int plane_grp = blockIdx.y;                                     // (img, channel group)
+  if (item >= bands * wwords || plane_grp >= cgs * c.n_img) return;     // uniform per warp
+  const int band = item / wwords, wj = item - band * wwords;
+  const int img = plane_grp / cgs, cg = plane_grp - img * cgs;
+  const int bs = c.block_size;
+  const int hc = c.h - bs + 1, wc = c.w - bs + 1;
+  const int ch = cg * 32 + lane;
+  const uint32_t* cb = center_bits + c.center_word_off;
+  const uint64_t plane_bit = (static_cast<uint64_t>(img) * c.c + ch) * static_cast<uint64_t>(hc) * wc;
+  const int w0 = wj * 32;
+  const int h_begin = band * band_rows;
+  const int h_end = min(h_begin + band_rows, c.h);
+  const uint32_t valid_w = (c.w - w0 >= 32) ? 0xffffffffu : ((1u << (c.w - w0)) - 1u);
+  uint32_t* mout = mask_bits + c.mask_word_off;
+
+  // smeared centre rows in a register ring of bs <= RING entries
+  uint32_t ring[RING];
+#pragma unroll
+  for (int i = 0; i < RING; ++i) ring[i] = 0u;
+  unsigned long long keep = 0;
+  // rows h-bs+1 .. h contribute to output row h; prime the window with rows h_begin-bs+1 .. h_begin-1
+  for (int r = h_begin - bs + 1; r < h_end; ++r) {
+    uint32_t sm = 0u;
+    if (r >= 0 && r < hc) {
+      const uint64_t rowbit = plane_bit + static_cast<uint64_t>(r) * wc;
+      const uint32_t lo = row_bits(cb, rowbit, w0 - 32, wc);
+      const uint32_t hi = row_bits(cb, rowbit, w0, wc);
+      uint64_t v = (static_cast<uint64_t>(hi) << 32) | lo;
+      // OR of shifts 0..bs-1 by doubling
+      int have = 1;
+      while (have < bs) {
+        const int add = min(have, bs - have);
+        v |= v << add;
+        have += add;
+      }
+      sm = static_cast<uint32_t>(v >> 32);
+    }
+    // ring slot = r mod bs (r may be negative)
+    const int slot = ((r % bs) + bs) % bs;
+#pragma unroll
+    for (int i = 0; i < RING; ++i)
+      if (i == slot) ring[i] = sm;
+    if (r < h_begin) continue;
+    uint32_t drop = 0u;
+#pragma unroll
+    for (int i = 0; i < RING; ++i) drop |= ring[i];
+    const uint32_t keepw = ~drop & valid_w;
+    keep += __popc(keepw);
+    // 32x32 bit transpose: lane k ends with the word of pixel w0+k (bit j = channel cg*32+j)
+    uint32_t mine = 0u;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const uint32_t wk = __ballot_sync(0xffffffffu, (keepw >> k) & 1u);
+      if (lane == k) mine = wk;
+    }
+    if (w0 + lane < c.w) {
+      mout[((static_cast<uint64_t>(img) * c.h + r) * c.w + (w0 + lane)) * cgs + cg] = mine;
+    }
+  }
+  // integer count: atomics are order-independent, the result is deterministic
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+  if (lane == 0 && keep) atomicAdd(keep_counts + c.count_index, keep);
+}
+
+}  // namespace b2u
+
+using namespace b2u;
+
+extern "C" int b2u_dropblock_centers(const b2u_dropblock_call* table, int n_calls, uint64_t seed,
+                                     const unsigned long long* offset_base, uint32_t* center_bits, void* stream) {
+  B2U_REQUIRE(table && center_bits && n_calls > 0, "bad arguments");
+  dim3 grid(b2u_num_sms() * 2, n_calls);
+  dropblock_centers_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, seed, offset_base, center_bits);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_dropblock_dilate(const b2u_dropblock_call* table, int n_calls, const b2u_dropblock_call* host_table,
+                                    const uint32_t* center_bits, uint32_t* mask_bits, unsigned long long* keep_counts,
+                                    void* stream) {
+  B2U_REQUIRE(table && host_table && center_bits && mask_bits && keep_counts && n_calls > 0, "bad arguments");
+  // the grid must cover the largest call of the table; smaller calls exit early
+  const int band_rows = 37;
+  int max_items = 0, max_planes = 0, max_bs = 0;
+  for (int i = 0; i < n_calls; ++i) {
+    const b2u_dropblock_call& c = host_table[i];
+    B2U_REQUIRE(c.block_size >= 1 && c.block_size <= 31 && (c.block_size & 1), "block_size must be odd and <= 31 (got %d)", c.block_size);
+    B2U_REQUIRE(c.c % 32 == 0 && c.c > 0, "channels must be a multiple of 32 (got %d)", c.c);
+    B2U_REQUIRE(c.h >= c.block_size && c.w >= c.block_size, "feature map %dx%d smaller than block_size %d", c.h, c.w, c.block_size);
+    const int items = ((c.h + band_rows - 1) / band_rows) * ((c.w + 31) / 32);
+    const int planes = (c.c / 32) * c.n_img;
+    if (items > max_items) max_items = items;
+    if (planes > max_planes) max_planes = planes;
+    if (c.block_size > max_bs) max_bs = c.block_size;
+  }
+  B2U_REQUIRE(max_planes <= 65535, "too many channel groups x images (%d)", max_planes);
+  dim3 grid((max_items + 3) / 4, max_planes, n_calls);
+  if (max_bs <= 7)
+    dropblock_dilate_kernel<7><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, center_bits, mask_bits, keep_counts, band_rows);
+  else
+    dropblock_dilate_kernel<31><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, center_bits, mask_bits, keep_counts, band_rows);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_dropblock_centers_from_uniform(const float* u, uint32_t* center_bits, long long numel, float gamma,
+                                                  void* stream) {
+  B2U_REQUIRE(u && center_bits && numel > 0, "bad arguments");
+  long long warps = (numel + 31) / 32;
+  long long blocks = (warps + 7) / 8;
+  if (blocks > b2u_num_sms() * 8) blocks = b2u_num_sms() * 8;
+  dropblock_centers_from_uniform_kernel<<<static_cast<int>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(u, center_bits, numel, gamma);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}

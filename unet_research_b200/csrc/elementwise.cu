@@ -1,0 +1,666 @@
+// HBM-bound kernels of the U-Net path: first-layer direct conv, GroupNorm finalise, fused
+// normalise/DropBlock-mask/ReLU apply (+ 2x2 max-pool, + concat-buffer store), output head with
+// Monte-Carlo accumulation, rotation.  All NHWC, 8 channels (16 B bf16 / 32 B fp32) per thread,
+// fp32 math, deterministic reductions (no floating-point atomics).
+#include "b2u_common.cuh"
+
+#include <math.h>
+
+namespace b2u {
+
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+template <typename T> __device__ __forceinline__ void round_for_storage(float (&f)[8]) {}
+template <> __device__ __forceinline__ void round_for_storage<float>(float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = round_tf32(f[i]);     // the consumer is a kind::tf32 MMA
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic block reduction of per-thread 8-channel (sum, sumsq) accumulators into one row of
+// the GroupNorm partial buffer.  Thread t owns channel vector cv = t % cvs and pixel slot t / cvs.
+// smem: float[blockDim.x * 16] + float[c * 2].
+__device__ void block_stats_to_partials(const float (&s)[8], const float (&q)[8], int c, int sgs,
+                                        float* __restrict__ smem, float* __restrict__ out_row) {
+  const int cvs = c >> 3;
+  const int t = threadIdx.x;
+  const int slots = blockDim.x / cvs;
+  float* mine = smem + t * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mine[i] = s[i];
+    mine[8 + i] = q[i];
+  }
+  __syncthreads();
+  float* chan = smem + blockDim.x * 16;            // [c][2]
+  for (int o = t; o < c * 2; o += blockDim.x) {
+    const int ch = o >> 1, st = o & 1;
+    const int cv = ch >> 3, ci = ch & 7;
+    float acc = 0.f;
+    for (int sl = 0; sl < slots; ++sl) acc += smem[(sl * cvs + cv) * 16 + st * 8 + ci];
+    chan[o] = acc;
+  }
+  __syncthreads();
+  const int nsg = c / sgs;
+  for (int o = t; o < nsg * 2; o += blockDim.x) {
+    const int sg = o >> 1, st = o & 1;
+    float acc = 0.f;
+    for (int i = 0; i < sgs; ++i) acc += chan[(sg * sgs + i) * 2 + st];
+    out_row[o] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// First layer: direct 3x3 conv, Cin in {1,3}, fp32 NCHW input read with autopad semantics.
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ wgt, T* __restrict__ y,
+                                  float* __restrict__ partials, int h0, int w0, int h, int w, int cout, int sgs) {
+  extern __shared__ float sm[];
+  float* wsm = sm;                                  // [cout][CIN*9]
+  float* red = sm + cout * CIN * 9;
+  for (int i = threadIdx.x; i < cout * CIN * 9; i += blockDim.x) wsm[i] = wgt[i];
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int cvs = cout >> 3;
+  const int cv = threadIdx.x % cvs;
+  const int slot = threadIdx.x / cvs;
+  const int slots = blockDim.x / cvs;
+  const float* xn = x + static_cast<size_t>(n) * CIN * h0 * w0;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  const int npix = h * w;
+  for (int pix = blockIdx.x * slots + slot; pix < npix; pix += gridDim.x * slots) {
+    const int ph = pix / w, pw = pix - ph * w;
+    float in[CIN * 9];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int yy = ph + r - 1, xx = pw + c - 1;
+          in[ci * 9 + r * 3 + c] = (yy >= 0 && yy < h0 && xx >= 0 && xx < w0) ? __ldg(xn + (static_cast<size_t>(ci) * h0 + yy) * w0 + xx) : 0.f;
+        }
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float* wk = wsm + (cv * 8 + k) * CIN * 9;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < CIN * 9; ++j) acc = fmaf(in[j], wk[j], acc);
+      o[k] = acc;
+      s[k] += acc;
+      q[k] += acc * acc;
+    }
+    Vec8<T> v;
+    v.from_float(o);
+    v.store(y + (static_cast<size_t>(n) * npix + pix) * cout + cv * 8);
+  }
+  if (partials) {
+    block_stats_to_partials(s, q, cout, sgs, red,
+                            partials + (static_cast<size_t>(n) * gridDim.x + blockIdx.x) * (cout / sgs) * 2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void gn_finalize_kernel(const float* __restrict__ partials, int rows, int sgs, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float2* __restrict__ coef, int c, int num_groups,
+                                   double count, float eps, const unsigned long long* __restrict__ keep,
+                                   int images_per_call, double numel_per_call) {
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int gsize = c / num_groups;
+  const int nsg_total = c / sgs;
+  const int sg_per_group = gsize / sgs;              // >= 1 (sgs = min(gsize, 32))
+  const float* base = partials + static_cast<size_t>(n) * rows * nsg_total * 2;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < rows * sg_per_group; i += blockDim.x) {
+    const int r = i / sg_per_group, k = i - r * sg_per_group;
+    const float* p = base + (static_cast<size_t>(r) * nsg_total + g * sg_per_group + k) * 2;
+    s += static_cast<double>(p[0]);
+    q += static_cast<double>(p[1]);
+  }
+  __shared__ double sh[2][128];
+  sh[0][threadIdx.x] = s;
+  sh[1][threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  const double mean = sh[0][0] / count;
+  double var = sh[1][0] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  float scale = 1.f;
+  if (keep) scale = static_cast<float>(numel_per_call / static_cast<double>(keep[n / images_per_call]));
+  for (int i = threadIdx.x; i < gsize; i += blockDim.x) {
+    const int ch = g * gsize + i;
+    const float a = gamma[ch] * rstd;
+    const float b = beta[ch] - static_cast<float>(mean) * a;
+    coef[static_cast<size_t>(n) * c + ch] = make_float2(a * scale, b * scale);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct ApplyParams {
+  int n, h, w, c;
+  int relu;
+  int out_cstride, out_coffset;
+  int mask2_cstride, mask2_coffset;
+  int images_per_call2;
+  double numel_per_call2;
+};
+
+__device__ __forceinline__ void apply8(float (&f)[8], const float2* __restrict__ cf, uint32_t m1, bool relu) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float2 ab = __ldg(cf + i);
+    float v = fmaf(f[i], ab.x, ab.y);
+    v = ((m1 >> i) & 1u) ? v : 0.f;
+    f[i] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, const float2* __restrict__ coef, const uint8_t* __restrict__ mask1,
+                                const uint8_t* __restrict__ mask2, const unsigned long long* __restrict__ keep2,
+                                T* __restrict__ out, ApplyParams p) {
+  const int cvs = p.c >> 3;
+  const long hw = static_cast<long>(p.h) * p.w;
+  const long total = static_cast<long>(p.n) * hw * cvs;
+  for (long v = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; v < total; v += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long pix = v / cvs;
+    const int cv = static_cast<int>(v - pix * cvs);
+    const int n = static_cast<int>(pix / hw);
+    Vec8<T> vec;
+    vec.load(x + pix * p.c + cv * 8);
+    float f[8];
+    vec.to_float(f);
+    const uint32_t m1 = mask1 ? mask1[pix * cvs + cv] : 0xFFu;
+    apply8(f, coef + static_cast<size_t>(n) * p.c + cv * 8, m1, p.relu != 0);
+    if (mask2) {
+      const uint32_t m2 = mask2[pix * (p.mask2_cstride >> 3) + (p.mask2_coffset >> 3) + cv];
+      const float s2 = static_cast<float>(p.numel_per_call2 / static_cast<double>(keep2[n / p.images_per_call2]));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = ((m2 >> i) & 1u) ? f[i] * s2 : 0.f;
+    }
+    round_for_storage<T>(f);
+    vec.from_float(f);
+    vec.store(out + pix * p.out_cstride + p.out_coffset + cv * 8);
+  }
+}
+
+// Encoder tail: apply + skip store (with concat mask) + 2x2 max-pool + pooled GroupNorm partials.
+template <typename T>
+__global__ void __launch_bounds__(256) gn_apply_pool_kernel(const T* __restrict__ x, const float2* __restrict__ coef, const uint8_t* __restrict__ mask1,
+                                     const uint8_t* __restrict__ mask2, const unsigned long long* __restrict__ keep2,
+                                     T* __restrict__ skip_out, T* __restrict__ pooled, float* __restrict__ pool_partials,
+                                     uint8_t* __restrict__ argmax, int pool_sgs, ApplyParams p) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.y;
+  const int cvs = p.c >> 3;
+  const int cv = threadIdx.x % cvs;
+  const int slot = threadIdx.x / cvs;
+  const int slots = blockDim.x / cvs;
+  const int ph = p.h >> 1, pw = p.w >> 1;
+  const int npool = ph * pw;
+  const float2* cf = coef + static_cast<size_t>(n) * p.c + cv * 8;
+  float s2 = 1.f;
+  if (mask2) s2 = static_cast<float>(p.numel_per_call2 / static_cast<double>(keep2[n / p.images_per_call2]));
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  for (int pp = blockIdx.x * slots + slot; pp < npool; pp += gridDim.x * slots) {
+    const int py = pp / pw, px = pp - py * pw;
+    float best[8];
+    uint32_t arg[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long pix = (static_cast<long>(n) * p.h + (2 * py + (k >> 1))) * p.w + (2 * px + (k & 1));
+      Vec8<T> vec;
+      vec.load(x + pix * p.c + cv * 8);
+      float f[8];
+      vec.to_float(f);
+      const uint32_t m1 = mask1 ? mask1[pix * cvs + cv] : 0xFFu;
+      apply8(f, cf, m1, p.relu != 0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        // ATen max_pool2d: first maximum in row-major window order wins (val > maxval || isnan(val))
+        if (k == 0 || f[i] > best[i] || f[i] != f[i]) {
+          best[i] = f[i];
+          arg[i] = k;
+        }
+      }
+      if (skip_out) {
+        float g[8];
+        if (mask2) {
+          const uint32_t m2 = mask2[pix * (p.mask2_cstride >> 3) + (p.mask2_coffset >> 3) + cv];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = ((m2 >> i) & 1u) ? f[i] * s2 : 0.f;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = f[i];
+        }
+        round_for_storage<T>(g);
+        Vec8<T> o;
+        o.from_float(g);
+        o.store(skip_out + pix * p.out_cstride + p.out_coffset + cv * 8);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i] += best[i];
+      q[i] += best[i] * best[i];
+    }
+    const long po = (static_cast<long>(n) * npool + pp) * p.c + cv * 8;
+    Vec8<T> o;
+    o.from_float(best);
+    o.store(pooled + po);
+    if (argmax) {
+      uint2 a;
+      a.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+      a.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+      *reinterpret_cast<uint2*>(argmax + po) = a;
+    }
+  }
+  if (pool_partials) {
+    block_stats_to_partials(s, q, p.c, pool_sgs, sm,
+                            pool_partials + (static_cast<size_t>(n) * gridDim.x + blockIdx.x) * (p.c / pool_sgs) * 2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Output head.  LPP = c/8 lanes cooperate on one pixel (c <= 256); each lane owns 8 channels.
+template <typename T>
+__global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x, const float2* __restrict__ coef, const uint8_t* __restrict__ mask1,
+                            const float* __restrict__ w_head, float* __restrict__ out, float* __restrict__ logits,
+                            const float* __restrict__ fov, double* __restrict__ acc, float* __restrict__ samples,
+                            const long long* __restrict__ iter_base, b2u_head_desc d) {
+  const int lpp = d.c >> 3;
+  const int lane_in = threadIdx.x % lpp;
+  const long group = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) / lpp;
+  const long ngroups = (static_cast<long>(gridDim.x) * blockDim.x) / lpp;
+  const long npix0 = static_cast<long>(d.h0) * d.w0;
+  float wh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) wh[i] = __ldg(w_head + lane_in * 8 + i);
+  const long long base_iter = iter_base ? *iter_base : 0;
+  // every lane of a warp runs the same trip count (shuffles below need the full warp)
+  const long trips = (npix0 + ngroups - 1) / ngroups;
+  for (long tr = 0; tr < trips; ++tr) {
+    const long op = tr * ngroups + group;
+    const bool active = op < npix0;
+    const long opc = active ? op : 0;
+    const int oh = static_cast<int>(opc / d.w0), ow = static_cast<int>(opc - static_cast<long>(oh) * d.w0);
+    double s1 = 0.0, s2 = 0.0;
+    for (int n = 0; n < d.n; ++n) {
+      const long pix = (static_cast<long>(n) * d.h + oh) * d.w + ow;
+      Vec8<T> vec;
+      vec.load(x + pix * d.c + lane_in * 8);
+      float f[8];
+      vec.to_float(f);
+      const uint32_t m1 = mask1 ? mask1[pix * lpp + lane_in] : 0xFFu;
+      apply8(f, coef + static_cast<size_t>(n) * d.c + lane_in * 8, m1, true);
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dot = fmaf(f[i], wh[i], dot);
+      for (int o = lpp >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (active && lane_in == 0) {
+        float yv = 1.f / (1.f + expf(-dot));
+        yv = fminf(fmaxf(yv, 0.f), 1.f);
+        if (yv != yv) yv = 0.f;
+        if (logits) logits[static_cast<long>(n) * npix0 + op] = dot;
+        if (out) out[static_cast<long>(n) * npix0 + op] = yv;
+        if (acc) {
+          const float fv = fov ? fov[(d.fov_per_image ? static_cast<long>(n) * npix0 : 0) + op] : 1.f;
+          const float v = yv * fv;
+          s1 += static_cast<double>(v);
+          s2 += static_cast<double>(v) * static_cast<double>(v);
+          const long long it = base_iter + n;
+          if (samples && it < d.return_num) samples[it * npix0 + op] = v;
+        }
+      }
+    }
+    if (acc && active && lane_in == 0) {
+      acc[op] += s1;
+      acc[npix0 + op] += s2;
+    }
+  }
+}
+
+__global__ void mc_finalize_kernel(const double* __restrict__ acc, float* __restrict__ mean, float* __restrict__ stdv,
+                                   long long npix, long long t) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < npix;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const double s1 = acc[i], s2 = acc[npix + i];
+    const double m = s1 / static_cast<double>(t);
+    double var = (s2 - s1 * s1 / static_cast<double>(t)) / static_cast<double>(t - 1);
+    if (var < 0.0) var = 0.0;
+    mean[i] = static_cast<float>(m);
+    stdv[i] = static_cast<float>(sqrt(var));
+  }
+}
+
+__global__ void mc_accumulate_kernel(const float* __restrict__ x, const float* __restrict__ fov, double* __restrict__ acc,
+                                     float* __restrict__ samples, const long long* __restrict__ iter_base, int n,
+                                     long long npix, int return_num) {
+  const long long base_iter = iter_base ? *iter_base : 0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < npix;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float fv = fov ? fov[i] : 1.f;
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < n; ++k) {
+      const float v = x[static_cast<long long>(k) * npix + i] * fv;
+      s1 += static_cast<double>(v);
+      s2 += static_cast<double>(v) * static_cast<double>(v);
+      const long long it = base_iter + k;
+      if (samples && it < return_num) samples[it * npix + i] = v;
+    }
+    acc[i] += s1;
+    acc[npix + i] += s2;
+  }
+}
+
+__global__ void advance_counter_kernel(long long* c, long long delta) { *c += delta; }
+
+// ---------------------------------------------------------------------------------------------
+// torchvision TF.rotate(BILINEAR, fill=0) restated in one gather kernel (see include/b2u.h).
+struct RotParams {
+  float t00, t01, t02, t10, t11, t12;   // rescaled theta^T columns: gx = x*t00 + y*t01 + t02, gy = x*t10 + y*t11 + t12
+};
+__device__ __forceinline__ float linspace_val(float start, float end, int steps, int i) {
+  // ATen linspace (RangeFactories.cu): symmetric evaluation around the midpoint
+  if (steps == 1) return start;
+  const float step = (end - start) / static_cast<float>(steps - 1);
+  const int half = steps / 2;
+  return i < half ? start + step * i : end - step * (steps - i - 1);
+}
+constexpr int kMaxAnglesPerLaunch = 64;
+struct RotBatch {
+  RotParams r[kMaxAnglesPerLaunch];
+};
+__global__ void rotate_kernel(const float* __restrict__ x, float* __restrict__ out, int n, int c, int h, int w,
+                              const RotBatch rp, long x_batch_stride) {
+  const long total = static_cast<long>(n) * h * w;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int ow = static_cast<int>(i % w);
+    const int oh = static_cast<int>((i / w) % h);
+    const int img = static_cast<int>(i / (static_cast<long>(w) * h));
+    const RotParams r = rp.r[img];
+    const float bx = linspace_val(-w * 0.5f + 0.5f, w * 0.5f + 0.5f - 1.f, w, ow);
+    const float by = linspace_val(-h * 0.5f + 0.5f, h * 0.5f + 0.5f - 1.f, h, oh);
+    const float gx = bx * r.t00 + by * r.t01 + r.t02;
+    const float gy = bx * r.t10 + by * r.t11 + r.t12;
+    // grid_sample, align_corners=False: unnormalise, bilinear, zero padding
+    const float ix = ((gx + 1.f) * w - 1.f) * 0.5f;
+    const float iy = ((gy + 1.f) * h - 1.f) * 0.5f;
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+    const float ax = ix - fx, ay = iy - fy;
+    const float wnw = (1.f - ax) * (1.f - ay), wne = ax * (1.f - ay), wsw = (1.f - ax) * ay, wse = ax * ay;
+    const bool inx0 = x0 >= 0 && x0 < w, inx1 = x0 + 1 >= 0 && x0 + 1 < w;
+    const bool iny0 = y0 >= 0 && y0 < h, iny1 = y0 + 1 >= 0 && y0 + 1 < h;
+    float m = 0.f;
+    if (inx0 && iny0) m += wnw;
+    if (inx1 && iny0) m += wne;
+    if (inx0 && iny1) m += wsw;
+    if (inx1 && iny1) m += wse;
+    for (int ch = 0; ch < c; ++ch) {
+      const float* src = x + img * x_batch_stride + static_cast<long>(ch) * h * w;
+      float v = 0.f;
+      if (inx0 && iny0) v += src[static_cast<long>(y0) * w + x0] * wnw;
+      if (inx1 && iny0) v += src[static_cast<long>(y0) * w + x0 + 1] * wne;
+      if (inx0 && iny1) v += src[static_cast<long>(y0 + 1) * w + x0] * wsw;
+      if (inx1 && iny1) v += src[static_cast<long>(y0 + 1) * w + x0 + 1] * wse;
+      out[(static_cast<long>(img) * c + ch) * h * w + static_cast<long>(oh) * w + ow] = v * m;
+    }
+  }
+}
+
+static int grid_for(long work_items, int threads) {
+  long blocks = (work_items + threads - 1) / threads;
+  long cap = static_cast<long>(b2u_num_sms()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+static int stat_sgs(int c, int num_groups) {
+  int gs = c / num_groups;
+  return gs < 32 ? gs : 32;
+}
+
+static int blocks_per_image_for(long items, int per_block) {
+  long b = (items + per_block - 1) / per_block;
+  long cap = static_cast<long>(b2u_num_sms()) * 4;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+static int pick_threads(int cvs) {
+  // blockDim must be a multiple of the channel-vector count so each thread keeps one cv
+  int t = 256;
+  if (cvs > 256) return 0;
+  t = (256 / cvs) * cvs;
+  return t;
+}
+
+}  // namespace b2u
+
+using namespace b2u;
+
+extern "C" int b2u_conv_first_stat_layout(int h, int w, int cout, int num_groups, int* rows_per_image,
+                                          int* subgroup_size) {
+  B2U_REQUIRE(h > 0 && w > 0 && cout > 0 && cout % 8 == 0 && cout <= 256, "bad shape h=%d w=%d cout=%d", h, w, cout);
+  B2U_REQUIRE(num_groups > 0 && cout % num_groups == 0, "cout %d not divisible by groups %d", cout, num_groups);
+  const int threads = pick_threads(cout / 8);
+  if (rows_per_image) *rows_per_image = blocks_per_image_for(static_cast<long>(h) * w, threads / (cout / 8));
+  if (subgroup_size) *subgroup_size = stat_sgs(cout, num_groups);
+  return B2U_OK;
+}
+
+extern "C" int b2u_conv_first_fwd(const float* x_nchw, const float* w, void* y, float* partials, int n, int cin,
+                                  int h0, int w0, int h, int wd, int cout, int num_groups, int dtype, void* stream) {
+  B2U_REQUIRE(x_nchw && w && y, "null pointer");
+  B2U_REQUIRE(cin == 1 || cin == 3, "first-layer kernel supports cin 1 or 3, got %d", cin);
+  B2U_REQUIRE(n > 0 && h0 > 0 && w0 > 0 && h >= h0 && wd >= w0, "bad sizes");
+  int rows = 0, sgs = 0;
+  int rc = b2u_conv_first_stat_layout(h, wd, cout, num_groups > 0 ? num_groups : 1, &rows, &sgs);
+  if (rc) return rc;
+  const int threads = pick_threads(cout / 8);
+  const size_t smem = (static_cast<size_t>(cout) * cin * 9 + threads * 16 + cout * 2) * sizeof(float);
+  dim3 grid(rows, n);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* parts = num_groups > 0 ? partials : nullptr;
+  B2U_REQUIRE(num_groups == 0 || partials, "partials required");
+#define B2U_LAUNCH_FIRST(T, CIN)                                                                                  \
+  do {                                                                                                            \
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(conv_first_kernel<T, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+    conv_first_kernel<T, CIN><<<grid, threads, smem, st>>>(x_nchw, w, static_cast<T*>(y), parts, h0, w0, h, wd, cout, sgs); \
+  } while (0)
+  if (dtype == B2U_F32) {
+    if (cin == 1) B2U_LAUNCH_FIRST(float, 1); else B2U_LAUNCH_FIRST(float, 3);
+  } else {
+    if (cin == 1) B2U_LAUNCH_FIRST(__nv_bfloat16, 1); else B2U_LAUNCH_FIRST(__nv_bfloat16, 3);
+  }
+#undef B2U_LAUNCH_FIRST
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_gn_finalize(const float* partials, int rows_per_image, int subgroup_size, const float* gamma,
+                               const float* beta, float* coef, int n, int c, int num_groups, double count, float eps,
+                               const unsigned long long* keep_counts, int images_per_call, double numel_per_call,
+                               void* stream) {
+  B2U_REQUIRE(partials && gamma && beta && coef, "null pointer");
+  B2U_REQUIRE(n > 0 && c > 0 && num_groups > 0 && c % num_groups == 0, "bad n/c/groups");
+  B2U_REQUIRE(subgroup_size > 0 && (c / num_groups) % subgroup_size == 0, "subgroup size %d does not divide group size %d",
+              subgroup_size, c / num_groups);
+  B2U_REQUIRE(!keep_counts || images_per_call > 0, "images_per_call must be positive");
+  dim3 grid(num_groups, n);
+  gn_finalize_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      partials, rows_per_image, subgroup_size, gamma, beta, reinterpret_cast<float2*>(coef), c, num_groups, count, eps,
+      keep_counts, images_per_call > 0 ? images_per_call : 1, numel_per_call);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+static int fill_apply(const b2u_apply_desc* d, ApplyParams* p) {
+  B2U_REQUIRE(d, "null descriptor");
+  B2U_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->c % 8 == 0, "bad tensor shape");
+  B2U_REQUIRE(d->out_cstride >= d->c && d->out_cstride % 8 == 0 && d->out_coffset % 8 == 0, "bad output channel layout");
+  p->n = d->n; p->h = d->h; p->w = d->w; p->c = d->c; p->relu = d->relu;
+  p->out_cstride = d->out_cstride; p->out_coffset = d->out_coffset;
+  p->mask2_cstride = d->mask2_cstride; p->mask2_coffset = d->mask2_coffset;
+  p->images_per_call2 = d->images_per_call2 > 0 ? d->images_per_call2 : 1;
+  p->numel_per_call2 = d->numel_per_call2;
+  return B2U_OK;
+}
+
+extern "C" int b2u_gn_apply(const void* x, const float* coef, const uint32_t* mask1, const uint32_t* mask2,
+                            const unsigned long long* keep_counts2, void* out, const b2u_apply_desc* d, void* stream) {
+  ApplyParams p;
+  int rc = fill_apply(d, &p);
+  if (rc) return rc;
+  B2U_REQUIRE(x && coef && out, "null pointer");
+  B2U_REQUIRE(!mask2 || (keep_counts2 && d->mask2_cstride % 8 == 0 && d->mask2_coffset % 8 == 0), "mask2 needs keep counts and 8-aligned channel layout");
+  const long total = static_cast<long>(d->n) * d->h * d->w * (d->c / 8);
+  const int grid = grid_for(total, 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (d->dtype == B2U_F32)
+    gn_apply_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), reinterpret_cast<const float2*>(coef),
+                                                 reinterpret_cast<const uint8_t*>(mask1), reinterpret_cast<const uint8_t*>(mask2),
+                                                 keep_counts2, static_cast<float*>(out), p);
+  else
+    gn_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), reinterpret_cast<const float2*>(coef),
+                                                         reinterpret_cast<const uint8_t*>(mask1), reinterpret_cast<const uint8_t*>(mask2),
+                                                         keep_counts2, static_cast<__nv_bfloat16*>(out), p);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_pool_stat_layout(int h, int w, int c, int num_groups, int* rows_per_image, int* subgroup_size) {
+  B2U_REQUIRE(h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "pool needs even h,w (got %d,%d)", h, w);
+  B2U_REQUIRE(c > 0 && c % 8 == 0 && c / 8 <= 256, "bad channel count %d", c);
+  B2U_REQUIRE(num_groups > 0 && c % num_groups == 0, "c %d not divisible by groups %d", c, num_groups);
+  const int threads = pick_threads(c / 8);
+  if (rows_per_image) *rows_per_image = blocks_per_image_for(static_cast<long>(h / 2) * (w / 2), threads / (c / 8));
+  if (subgroup_size) *subgroup_size = stat_sgs(c, num_groups);
+  return B2U_OK;
+}
+
+extern "C" int b2u_gn_apply_pool(const void* x, const float* coef, const uint32_t* mask1, const uint32_t* mask2,
+                                 const unsigned long long* keep_counts2, void* skip_out, void* pooled,
+                                 float* pool_partials, uint8_t* argmax, int pool_num_groups, const b2u_apply_desc* d,
+                                 void* stream) {
+  ApplyParams p;
+  int rc = fill_apply(d, &p);
+  if (rc) return rc;
+  B2U_REQUIRE(x && coef && pooled, "null pointer");
+  B2U_REQUIRE(!mask2 || keep_counts2, "mask2 needs keep counts");
+  int rows = 0, sgs = 1;
+  rc = b2u_pool_stat_layout(d->h, d->w, d->c, pool_num_groups > 0 ? pool_num_groups : 1, &rows, &sgs);
+  if (rc) return rc;
+  B2U_REQUIRE(pool_num_groups == 0 || pool_partials, "pool partials required");
+  const int threads = pick_threads(d->c / 8);
+  const size_t smem = (static_cast<size_t>(threads) * 16 + d->c * 2) * sizeof(float);
+  dim3 grid(rows, d->n);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* parts = pool_num_groups > 0 ? pool_partials : nullptr;
+  if (d->dtype == B2U_F32)
+    gn_apply_pool_kernel<float><<<grid, threads, smem, st>>>(
+        static_cast<const float*>(x), reinterpret_cast<const float2*>(coef), reinterpret_cast<const uint8_t*>(mask1),
+        reinterpret_cast<const uint8_t*>(mask2), keep_counts2, static_cast<float*>(skip_out), static_cast<float*>(pooled),
+        parts, argmax, sgs, p);
+  else
+    gn_apply_pool_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(
+        static_cast<const __nv_bfloat16*>(x), reinterpret_cast<const float2*>(coef), reinterpret_cast<const uint8_t*>(mask1),
+        reinterpret_cast<const uint8_t*>(mask2), keep_counts2, static_cast<__nv_bfloat16*>(skip_out),
+        static_cast<__nv_bfloat16*>(pooled), parts, argmax, sgs, p);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_head_fwd(const void* x, const float* coef, const uint32_t* mask1, const float* w_head, float* out,
+                            float* logits, const float* fov, double* acc, float* samples, const long long* iter_base,
+                            const b2u_head_desc* d, void* stream) {
+  B2U_REQUIRE(d && x && coef && w_head, "null pointer");
+  B2U_REQUIRE(d->c % 8 == 0 && d->c >= 8 && d->c <= 256 && ((d->c / 8) & (d->c / 8 - 1)) == 0,
+              "head supports c in {8,16,32,64,128,256}, got %d", d->c);
+  B2U_REQUIRE(d->h0 > 0 && d->w0 > 0 && d->h0 <= d->h && d->w0 <= d->w && d->n > 0, "bad sizes");
+  B2U_REQUIRE(out || acc, "nothing to write: out and acc are both NULL");
+  const long groups = static_cast<long>(d->h0) * d->w0;
+  const int grid = grid_for(groups * (d->c / 8), 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (d->dtype == B2U_F32)
+    head_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), reinterpret_cast<const float2*>(coef),
+                                             reinterpret_cast<const uint8_t*>(mask1), w_head, out, logits, fov, acc, samples,
+                                             iter_base, *d);
+  else
+    head_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), reinterpret_cast<const float2*>(coef),
+                                                     reinterpret_cast<const uint8_t*>(mask1), w_head, out, logits, fov, acc,
+                                                     samples, iter_base, *d);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_mc_finalize(const double* acc, float* mean, float* stdv, long long npix, long long t, void* stream) {
+  B2U_REQUIRE(acc && mean && stdv && npix > 0 && t > 0, "bad arguments");
+  mc_finalize_kernel<<<grid_for(npix, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(acc, mean, stdv, npix, t);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_mc_accumulate(const float* x, const float* fov, double* acc, float* samples,
+                                 const long long* iter_base, int n, long long npix, int return_num, void* stream) {
+  B2U_REQUIRE(x && acc && n > 0 && npix > 0, "bad arguments");
+  mc_accumulate_kernel<<<grid_for(npix, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, fov, acc, samples, iter_base, n,
+                                                                                              npix, return_num);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_advance_counter(long long* counter, long long delta, void* stream) {
+  B2U_REQUIRE(counter, "null counter");
+  advance_counter_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(counter, delta);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_rotate_bilinear(const float* x, float* out, int n, int c, int h, int w, const double* angles_deg,
+                                   int x_batch_stride_is_zero, void* stream) {
+  B2U_REQUIRE(x && out && angles_deg && n > 0 && c > 0 && h > 0 && w > 0, "bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long img_stride = static_cast<long>(c) * h * w;
+  // theta per torchvision functional.py:1006-1063 with angle -> -angle (functional.py:1130), evaluated in double,
+  // cast to fp32, then rescaled by [0.5 w, 0.5 h] in fp32 (_functional_tensor.py:598).  The per-angle
+  // coefficients travel by value as a kernel parameter: no allocation, CUDA-graph capturable.
+  for (int base = 0; base < n; base += kMaxAnglesPerLaunch) {
+    const int nb = n - base < kMaxAnglesPerLaunch ? n - base : kMaxAnglesPerLaunch;
+    RotBatch rb;
+    for (int i = 0; i < nb; ++i) {
+      const double rot = -angles_deg[base + i] * 3.14159265358979323846 / 180.0;   // math.radians(-angle)
+      const double a = cos(rot), b = -sin(rot), cc = sin(rot), dd = cos(rot);
+      const float m0 = static_cast<float>(dd), m1 = static_cast<float>(-b), m2 = 0.f;
+      const float m3 = static_cast<float>(-cc), m4 = static_cast<float>(a), m5 = 0.f;
+      const float sx = 0.5f * w, sy = 0.5f * h;
+      // rescaled_theta = theta^T / [sx, sy]: column 0 (gx) divides by sx, column 1 (gy) by sy
+      rb.r[i].t00 = m0 / sx; rb.r[i].t01 = m1 / sx; rb.r[i].t02 = m2 / sx;
+      rb.r[i].t10 = m3 / sy; rb.r[i].t11 = m4 / sy; rb.r[i].t12 = m5 / sy;
+    }
+    const long total = static_cast<long>(nb) * h * w;
+    rotate_kernel<<<grid_for(total, 256), 256, 0, st>>>(x + (x_batch_stride_is_zero ? 0 : base * img_stride),
+                                                       out + base * img_stride, nb, c, h, w, rb,
+                                                       x_batch_stride_is_zero ? 0 : img_stride);
+    B2U_LAUNCH_CHECK();
+  }
+  return B2U_OK;
+}

@@ -1,0 +1,467 @@
+"""Host-side runtime of the U-Net forward: packed weights, HBM workspaces and the kernel schedule.
+
+One `UNetEngine` serves one set of weights; `Workspace` objects (one per (batch, H0, W0)) own every
+activation / statistics / mask buffer, so a forward launches kernels only -- no allocation, no host
+synchronisation -- and can be captured in a CUDA graph.  The schedule mirrors `UNet.forward`
+(reference utils_unet.py:408-449):
+
+  conv (tcgen05 implicit GEMM, raw output + GroupNorm partials)
+    -> gn_finalize (per-(image, channel) affine, DropBlock rescale folded in)
+    -> gn_apply (normalise + DropBlock mask + ReLU [+ 2x2 max-pool + skip store into the concat buffer])
+
+Data layout in HBM: activations NHWC (bf16, or fp32 in TF32 mode); the decoder's concat buffer
+[N,H,W,2C] is written in halves by its two producers (up-conv apply -> channels [0,C), encoder
+apply_pool -> channels [C,2C)), so `torch.cat` and `x.clone()` never run.  DropBlock keep-masks are
+bit-packed NHWC (uint32 [N,H,W,C/32]).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ApplyDesc, ConvDesc, DropblockCall, HeadDesc, call, ptr, stream_ptr
+
+GN_EPS = 1e-5
+
+
+def _torch_dtype(dtype: int):
+    return torch.float32 if dtype == _lib.F32 else torch.bfloat16
+
+
+def device_rand_geometry() -> Tuple[int, int]:
+    sms, mt = C.c_int(0), C.c_int(0)
+    call("b2u_device_info", C.byref(sms), C.byref(mt))
+    return sms.value, mt.value
+
+
+# ----------------------------------------------------------------------------- DropBlock host logic
+def dropblock_gamma(drop_prob: float, block_size: int, h: int, w: int) -> float:
+    """gamma of reference utils_modules.py:81-82."""
+    return drop_prob * h * w / ((block_size ** 2) * (h - block_size + 1) * (w - block_size + 1))
+
+
+def _uniform_f32(x: np.ndarray) -> np.ndarray:
+    xf = x.astype(np.float32)
+    return xf * np.float32(2.0 ** -32) + np.float32(2.0 ** -33)
+
+
+def philox_thresholds(gamma: float) -> Tuple[int, int]:
+    """Raw-word equivalents of `curand_uniform(word) < float32(gamma)` including torch's 1.0 -> 0.0
+    wrap: centre = word < lo or word >= hi.  Found by bisection on the exact fp32 arithmetic."""
+    g = np.float32(gamma)
+    lo, hi = 0, 1 << 32
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if _uniform_f32(np.array([mid], dtype=np.uint32))[0] < g:
+            lo = mid + 1
+        else:
+            hi = mid
+    a, b = 0, (1 << 32) - 1
+    while a < b:
+        mid = (a + b) // 2
+        if _uniform_f32(np.array([mid], dtype=np.uint32))[0] == np.float32(1.0):
+            b = mid
+        else:
+            a = mid + 1
+    wrap = a if g > 0 else (1 << 32) - 1
+    return min(lo, (1 << 32) - 1), min(wrap, (1 << 32) - 1)
+
+
+def rand_grid(numel: int, sms: int, max_threads: int) -> int:
+    return min(sms * (max_threads // 256), (numel + 255) // 256)
+
+
+def rand_offset_increment(numel: int, sms: int, max_threads: int) -> int:
+    tn = 256 * rand_grid(numel, sms, max_threads)
+    return ((numel - 1) // (tn * 4) + 1) * 4
+
+
+def site_shapes(h: int, w: int, filters: int, depth: int) -> List[Tuple[int, int, int]]:
+    """(C, H, W) of the DropBlock sites in the reference's call order (utils_unet.py:417-433)."""
+    sites = []
+    c = filters
+    for lvl in range(depth):
+        sites += [(c, h >> lvl, w >> lvl)] * 2
+        c *= 2
+    sites += [(c, h >> depth, w >> depth)] * 2
+    for u in range(depth):
+        lvl = depth - 1 - u
+        c //= 2
+        sites += [(2 * c, h >> lvl, w >> lvl), (c, h >> lvl, w >> lvl), (c, h >> lvl, w >> lvl)]
+    return sites
+
+
+class MaskPlan:
+    """All DropBlock masks of one forward batch: `n_calls` independent reference forwards of
+    `images_per_call` images each (Monte-Carlo: n_calls = batched iterations, 1 image each; training:
+    one call covering the whole batch).  Holds the call table, bitmaps and keep counters."""
+
+    def __init__(self, n_calls: int, images_per_call: int, h: int, w: int, filters: int, depth: int,
+                 drop_prob: float, block_size: int, device):
+        if block_size % 2 == 0 or block_size > 31:
+            raise NotImplementedError("CUDA DropBlock supports odd block_size <= 31 (reference default 7)")
+        self.n_calls, self.ipc = n_calls, images_per_call
+        self.drop_prob, self.block_size = float(drop_prob), int(block_size)
+        self.sites = site_shapes(h, w, filters, depth)
+        self.n_sites = len(self.sites)
+        sms, mt = device_rand_geometry()
+        n_img = n_calls * images_per_call
+        calls = (DropblockCall * (n_calls * self.n_sites))()
+        center_words = 0
+        mask_words = 0
+        self.mask_site_off = []
+        self.numel_per_call = []
+        site_prefix = []
+        per_iter = 0
+        for (c, hh, ww) in self.sites:
+            if hh < block_size or ww < block_size:
+                raise ValueError(f"feature map {hh}x{ww} smaller than block_size {block_size} "
+                                 "(the reference fails here too: negative dimension)")
+            site_prefix.append(per_iter)
+            per_iter += rand_offset_increment(images_per_call * c * (hh - block_size + 1) * (ww - block_size + 1), sms, mt)
+        self.offset_per_call = per_iter
+        k = 0
+        for s, (c, hh, ww) in enumerate(self.sites):
+            self.mask_site_off.append(mask_words)
+            hc, wc = hh - block_size + 1, ww - block_size + 1
+            numel = images_per_call * c * hc * wc
+            lo, hi = philox_thresholds(dropblock_gamma(drop_prob, block_size, hh, ww))
+            self.numel_per_call.append(float(images_per_call * c * hh * ww))
+            for b in range(n_calls):
+                d = calls[k]
+                k += 1
+                d.philox_offset = b * per_iter + site_prefix[s]
+                d.center_word_off = center_words
+                d.mask_word_off = mask_words + b * images_per_call * hh * ww * (c // 32)
+                d.numel = numel
+                d.grid = rand_grid(numel, sms, mt)
+                d.thresh_lo, d.thresh_hi = lo, hi
+                d.n_img, d.c, d.h, d.w = images_per_call, c, hh, ww
+                d.block_size = block_size
+                d.count_index = s * n_calls + b
+                center_words += (numel + 31) // 32 + 2
+            mask_words += n_img * hh * ww * (c // 32)
+        self.host_table = calls
+        raw = np.frombuffer(bytes(calls), dtype=np.uint8).copy()
+        self.table = torch.from_numpy(raw).to(device)
+        self.center_bits = torch.zeros(center_words + 4, dtype=torch.int32, device=device)
+        self.mask_bits = torch.empty(mask_words, dtype=torch.int32, device=device)
+        self.keep_counts = torch.zeros(self.n_sites * n_calls, dtype=torch.int64, device=device)
+        self.offset_base = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def set_stream_position(self, philox_offset: int):
+        self.offset_base.fill_(int(philox_offset))
+
+    def generate(self, seed: int):
+        """Launch both mask phases for the whole table (reads the stream position from `offset_base`)."""
+        self.keep_counts.zero_()
+        n = self.n_calls * self.n_sites
+        call("b2u_dropblock_centers", ptr(self.table), n, C.c_uint64(seed & (2 ** 64 - 1)), ptr(self.offset_base),
+             ptr(self.center_bits), stream_ptr())
+        call("b2u_dropblock_dilate", ptr(self.table), n, self.host_table, ptr(self.center_bits), ptr(self.mask_bits),
+             ptr(self.keep_counts), stream_ptr())
+
+    def advance(self, n_calls: Optional[int] = None):
+        call("b2u_advance_counter", ptr(self.offset_base), (n_calls or self.n_calls) * self.offset_per_call, stream_ptr())
+
+    def mask_ptr(self, site: int) -> int:
+        return self.mask_bits.data_ptr() + 4 * self.mask_site_off[site]
+
+    def keep_ptr(self, site: int) -> int:
+        return self.keep_counts.data_ptr() + 8 * site * self.n_calls
+
+
+# ----------------------------------------------------------------------------- workspace
+@dataclass
+class _Stat:
+    partials: torch.Tensor
+    rows: int
+    sgs: int
+    coef: torch.Tensor
+
+
+class Workspace:
+    """Every device buffer one forward of a fixed (batch, H0, W0) needs."""
+
+    def __init__(self, eng: "UNetEngine", n: int, h0: int, w0: int):
+        self.n, self.h0, self.w0 = n, h0, w0
+        mult = 2 ** eng.depth
+        self.h = -(-h0 // mult) * mult
+        self.w = -(-w0 // mult) * mult
+        dev, dt = eng.device, _torch_dtype(eng.dtype)
+        self.buf: Dict[str, torch.Tensor] = {}
+        self.stat: Dict[str, _Stat] = {}
+        f, d = eng.filters, eng.depth
+
+        def act(name, hh, ww, c):
+            self.buf[name] = torch.empty(n, hh, ww, c, dtype=dt, device=dev)
+
+        def stat(name, rows, sgs, c):
+            self.stat[name] = _Stat(torch.empty(n, rows, c // sgs, 2, dtype=torch.float32, device=dev), rows, sgs,
+                                    torch.empty(n, c, 2, dtype=torch.float32, device=dev))
+
+        c = f
+        for lvl in range(d):
+            hh, ww = self.h >> lvl, self.w >> lvl
+            cin = eng.init_channels if lvl == 0 else c // 2
+            for j in (1, 2):
+                act(f"d{lvl}.raw{j}", hh, ww, c)
+            act(f"d{lvl}.act1", hh, ww, c)
+            act(f"cat{lvl}", hh, ww, 2 * c)
+            act(f"d{lvl}.praw", hh // 2, ww // 2, c)
+            act(f"d{lvl}.pact", hh // 2, ww // 2, c)
+            if lvl == 0:
+                r, s = eng.first_stat_layout(hh, ww, c)
+            else:
+                r, s = eng.conv_stat_layout(n, hh, ww, cin, c, False)
+            stat(f"d{lvl}.c1", r, s, c)
+            r, s = eng.conv_stat_layout(n, hh, ww, c, c, False)
+            stat(f"d{lvl}.c2", r, s, c)
+            r, s = eng.pool_stat_layout(hh, ww, c)
+            stat(f"d{lvl}.pool", r, s, c)
+            c *= 2
+        hh, ww = self.h >> d, self.w >> d
+        for j in (1, 2):
+            act(f"b.raw{j}", hh, ww, c)
+            act(f"b.act{j}", hh, ww, c)
+        r, s = eng.conv_stat_layout(n, hh, ww, c // 2, c, False)
+        stat("b.c1", r, s, c)
+        r, s = eng.conv_stat_layout(n, hh, ww, c, c, False)
+        stat("b.c2", r, s, c)
+        for u in range(d):
+            lvl = d - 1 - u
+            cin = c
+            c //= 2
+            hh, ww = self.h >> lvl, self.w >> lvl
+            act(f"u{u}.rawT", hh, ww, c)
+            for j in (1, 2):
+                act(f"u{u}.raw{j}", hh, ww, c)
+                act(f"u{u}.act{j}", hh, ww, c)
+            r, s = eng.conv_stat_layout(n, hh // 2, ww // 2, cin, c, True)
+            stat(f"u{u}.up", r, s, c)
+            r, s = eng.conv_stat_layout(n, hh, ww, 2 * c, c, False)
+            stat(f"u{u}.c1", r, s, c)
+            r, s = eng.conv_stat_layout(n, hh, ww, c, c, False)
+            stat(f"u{u}.c2", r, s, c)
+        self.out = torch.empty(n, 1, h0, w0, dtype=torch.float32, device=dev)
+        self.logits: Optional[torch.Tensor] = None
+        self.masks: Optional[MaskPlan] = None
+
+    def nbytes(self) -> int:
+        t = sum(b.numel() * b.element_size() for b in self.buf.values())
+        t += sum(s.partials.numel() * 4 + s.coef.numel() * 4 for s in self.stat.values())
+        return t
+
+
+# ----------------------------------------------------------------------------- engine
+class UNetEngine:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], init_channels: int, filters: int, depth: int,
+                 num_groups: int, dtype: int = _lib.BF16, device=None):
+        _lib.load()
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise _lib.B2uError("UNetEngine needs a CUDA device: there is no CPU path")
+        if filters % 64 != 0:
+            raise NotImplementedError("tensor-core path needs filters to be a multiple of 64")
+        if init_channels not in (1, 3):
+            raise NotImplementedError("first-layer kernel supports init_channels 1 or 3")
+        self.init_channels, self.filters, self.depth, self.num_groups, self.dtype = init_channels, filters, depth, num_groups, dtype
+        self.w: Dict[str, torch.Tensor] = {}
+        self._workspaces: Dict[Tuple[int, int, int], Workspace] = {}
+        self.load_weights(state_dict)
+
+    # ---- weights
+    def load_weights(self, sd: Dict[str, torch.Tensor]):
+        dev, dt = self.device, _torch_dtype(self.dtype)
+        st = stream_ptr()
+        self.w = {}
+        for k, v in sd.items():
+            v32 = v.detach().to(device=dev, dtype=torch.float32).contiguous()
+            if v32.dim() == 4 and k == "down_blocks.0.0.0.weight":
+                self.w[k] = v32                                            # direct first-layer kernel reads fp32
+            elif v32.dim() == 4 and k.startswith("output_conv"):
+                if v32.shape[0] != 1:
+                    raise NotImplementedError("head kernel supports output_channels == 1")
+                self.w[k] = v32.reshape(-1).contiguous()
+            elif v32.dim() == 4 and v32.shape[2] == 3:
+                cout, cin = v32.shape[0], v32.shape[1]
+                packed = torch.empty(9, cout, cin, dtype=dt, device=dev)
+                call("b2u_pack_conv3x3_weight", ptr(v32), ptr(packed), cout, cin, self.dtype, 0, st)
+                self.w[k] = packed
+            elif v32.dim() == 4 and v32.shape[2] == 2:
+                cin, cout = v32.shape[0], v32.shape[1]
+                packed = torch.empty(4, cout, cin, dtype=dt, device=dev)
+                call("b2u_pack_convT2x2_weight", ptr(v32), ptr(packed), cin, cout, self.dtype, st)
+                self.w[k] = packed
+            else:
+                self.w[k] = v32
+        torch.cuda.current_stream().synchronize()      # v32 temporaries die here
+
+    # ---- layout queries
+    def conv_stat_layout(self, n, h, w, cin, cout, conv_t: bool) -> Tuple[int, int]:
+        d = self._conv_desc(n, h, w, cin, cout, cin)
+        rows, sgs = C.c_int(0), C.c_int(0)
+        call("b2u_convT2x2_stat_layout" if conv_t else "b2u_conv3x3_stat_layout", C.byref(d), C.byref(rows), C.byref(sgs))
+        return rows.value, sgs.value
+
+    def first_stat_layout(self, h, w, cout) -> Tuple[int, int]:
+        rows, sgs = C.c_int(0), C.c_int(0)
+        call("b2u_conv_first_stat_layout", h, w, cout, self.num_groups, C.byref(rows), C.byref(sgs))
+        return rows.value, sgs.value
+
+    def pool_stat_layout(self, h, w, c) -> Tuple[int, int]:
+        rows, sgs = C.c_int(0), C.c_int(0)
+        call("b2u_pool_stat_layout", h, w, c, self.num_groups, C.byref(rows), C.byref(sgs))
+        return rows.value, sgs.value
+
+    def _conv_desc(self, n, h, w, cin, cout, x_cstride) -> ConvDesc:
+        d = ConvDesc()
+        d.n, d.h, d.w, d.cin, d.cout = n, h, w, cin, cout
+        d.dtype, d.num_groups, d.x_cstride = self.dtype, self.num_groups, x_cstride
+        return d
+
+    def workspace(self, n: int, h0: int, w0: int) -> Workspace:
+        key = (n, h0, w0)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            ws = Workspace(self, n, h0, w0)
+            self._workspaces[key] = ws
+        return ws
+
+    # ---- kernel wrappers
+    def _conv(self, ws, xname, wkey, yname, sname, n, h, w, cin, cout, conv_t=False):
+        d = self._conv_desc(n, h, w, cin, cout, cin)
+        call("b2u_convT2x2_fwd" if conv_t else "b2u_conv3x3_fwd", ptr(ws.buf[xname]), ptr(self.w[wkey]), ptr(ws.buf[yname]),
+             ptr(ws.stat[sname].partials), C.byref(d), stream_ptr())
+
+    def _finalize(self, ws, sname, gkey, n, c, hw, masks: Optional[MaskPlan], site: Optional[int]):
+        st = ws.stat[sname]
+        count = float((c // self.num_groups) * hw)
+        if masks is not None and site is not None:
+            keep, ipc, numel = masks.keep_ptr(site), masks.ipc, masks.numel_per_call[site]
+        else:
+            keep, ipc, numel = None, 1, 0.0
+        call("b2u_gn_finalize", ptr(st.partials), st.rows, st.sgs, ptr(self.w[gkey + ".weight"]), ptr(self.w[gkey + ".bias"]),
+             ptr(st.coef), n, c, self.num_groups, count, GN_EPS, keep, ipc, numel, stream_ptr())
+
+    def _apply_desc(self, n, h, w, c, relu, out_cstride, out_coffset, masks, site2, m2_cstride=0, m2_coffset=0) -> ApplyDesc:
+        a = ApplyDesc()
+        a.n, a.h, a.w, a.c, a.dtype, a.relu = n, h, w, c, self.dtype, int(relu)
+        a.out_cstride, a.out_coffset = out_cstride, out_coffset
+        a.mask2_cstride, a.mask2_coffset = m2_cstride, m2_coffset
+        if masks is not None and site2 is not None:
+            a.images_per_call2 = masks.ipc
+            a.numel_per_call2 = masks.numel_per_call[site2]
+        else:
+            a.images_per_call2 = 1
+            a.numel_per_call2 = 0.0
+        return a
+
+    # ---- the forward schedule
+    def forward(self, x: torch.Tensor, ws: Workspace, masks: Optional[MaskPlan] = None, *, head_out: bool = True,
+                want_logits: bool = False, mc: Optional[dict] = None, argmax: Optional[Dict[int, torch.Tensor]] = None):
+        """x: fp32 NCHW [n, Cin, h0, w0] on the engine's device (contiguous).  Launches only.
+        mc = {"acc": double[2,h0,w0], "fov": float[h0,w0] | None, "samples": float[R,h0,w0] | None,
+              "iter_base": int64[1], "return_num": R} switches the head to Monte-Carlo accumulation."""
+        n, f, d, G = ws.n, self.filters, self.depth, self.num_groups
+        assert x.shape == (n, self.init_channels, ws.h0, ws.w0) and x.dtype == torch.float32 and x.is_contiguous()
+        st = stream_ptr()
+        B = ws.buf
+        m = masks
+
+        def mptr(site):
+            return m.mask_ptr(site) if m is not None else None
+
+        def kptr(site):
+            return m.keep_ptr(site) if m is not None else None
+
+        c = f
+        for lvl in range(d):
+            hh, ww = ws.h >> lvl, ws.w >> lvl
+            p = f"down_blocks.{lvl}.0"
+            s1, s2, scat = 2 * lvl, 2 * lvl + 1, 2 * d + 2 + 3 * (d - 1 - lvl)
+            # conv 1
+            if lvl == 0:
+                call("b2u_conv_first_fwd", ptr(x), ptr(self.w[p + ".0.weight"]), ptr(B["d0.raw1"]), ptr(ws.stat["d0.c1"].partials),
+                     n, self.init_channels, ws.h0, ws.w0, hh, ww, c, G, self.dtype, st)
+            else:
+                self._conv(ws, f"d{lvl - 1}.pact", p + ".0.weight", f"d{lvl}.raw1", f"d{lvl}.c1", n, hh, ww, c // 2, c)
+            self._finalize(ws, f"d{lvl}.c1", p + ".1", n, c, hh * ww, m, s1)
+            a = self._apply_desc(n, hh, ww, c, True, c, 0, None, None)
+            call("b2u_gn_apply", ptr(B[f"d{lvl}.raw1"]), ptr(ws.stat[f"d{lvl}.c1"].coef), mptr(s1), None, None,
+                 ptr(B[f"d{lvl}.act1"]), C.byref(a), st)
+            # conv 2 + pool + skip store
+            self._conv(ws, f"d{lvl}.act1", p + ".4.weight", f"d{lvl}.raw2", f"d{lvl}.c2", n, hh, ww, c, c)
+            self._finalize(ws, f"d{lvl}.c2", p + ".5", n, c, hh * ww, m, s2)
+            a = self._apply_desc(n, hh, ww, c, True, 2 * c, c, m, scat, 2 * c, c)
+            call("b2u_gn_apply_pool", ptr(B[f"d{lvl}.raw2"]), ptr(ws.stat[f"d{lvl}.c2"].coef), mptr(s2), mptr(scat), kptr(scat),
+                 ptr(B[f"cat{lvl}"]), ptr(B[f"d{lvl}.praw"]), ptr(ws.stat[f"d{lvl}.pool"].partials),
+                 ptr(argmax[lvl]) if argmax is not None else None, G, C.byref(a), st)
+            # GroupNorm after the pool (no ReLU, no DropBlock)
+            self._finalize(ws, f"d{lvl}.pool", f"down_blocks.{lvl}.1.1", n, c, (hh // 2) * (ww // 2), None, None)
+            a = self._apply_desc(n, hh // 2, ww // 2, c, False, c, 0, None, None)
+            call("b2u_gn_apply", ptr(B[f"d{lvl}.praw"]), ptr(ws.stat[f"d{lvl}.pool"].coef), None, None, None,
+                 ptr(B[f"d{lvl}.pact"]), C.byref(a), st)
+            c *= 2
+        # bottleneck
+        hh, ww = ws.h >> d, ws.w >> d
+        prev = f"d{d - 1}.pact"
+        for j, (idx, site) in enumerate(((0, 2 * d), (4, 2 * d + 1)), start=1):
+            cin = c // 2 if j == 1 else c
+            self._conv(ws, prev, f"conn_block.{idx}.weight", f"b.raw{j}", f"b.c{j}", n, hh, ww, cin, c)
+            self._finalize(ws, f"b.c{j}", f"conn_block.{idx + 1}", n, c, hh * ww, m, site)
+            a = self._apply_desc(n, hh, ww, c, True, c, 0, None, None)
+            call("b2u_gn_apply", ptr(B[f"b.raw{j}"]), ptr(ws.stat[f"b.c{j}"].coef), mptr(site), None, None,
+                 ptr(B[f"b.act{j}"]), C.byref(a), st)
+            prev = f"b.act{j}"
+        # decoder
+        for u in range(d):
+            lvl = d - 1 - u
+            cin = c
+            c //= 2
+            hh, ww = ws.h >> lvl, ws.w >> lvl
+            scat, s1, s2 = 2 * d + 2 + 3 * u, 2 * d + 3 + 3 * u, 2 * d + 4 + 3 * u
+            # up-conv -> GroupNorm -> ReLU -> (concat-site DropBlock) -> channels [0, c) of the concat buffer
+            self._conv(ws, prev, f"up_blocks.{u}.0.0.weight", f"u{u}.rawT", f"u{u}.up", n, hh // 2, ww // 2, cin, c, conv_t=True)
+            self._finalize(ws, f"u{u}.up", f"up_blocks.{u}.0.1", n, c, hh * ww, None, None)
+            a = self._apply_desc(n, hh, ww, c, True, 2 * c, 0, m, scat, 2 * c, 0)
+            call("b2u_gn_apply", ptr(B[f"u{u}.rawT"]), ptr(ws.stat[f"u{u}.up"].coef), None, mptr(scat), kptr(scat),
+                 ptr(B[f"cat{lvl}"]), C.byref(a), st)
+            # conv 1 over the concat buffer
+            self._conv(ws, f"cat{lvl}", f"up_blocks.{u}.1.0.weight", f"u{u}.raw1", f"u{u}.c1", n, hh, ww, 2 * c, c)
+            self._finalize(ws, f"u{u}.c1", f"up_blocks.{u}.1.1", n, c, hh * ww, m, s1)
+            a = self._apply_desc(n, hh, ww, c, True, c, 0, None, None)
+            call("b2u_gn_apply", ptr(B[f"u{u}.raw1"]), ptr(ws.stat[f"u{u}.c1"].coef), mptr(s1), None, None,
+                 ptr(B[f"u{u}.act1"]), C.byref(a), st)
+            # conv 2
+            self._conv(ws, f"u{u}.act1", f"up_blocks.{u}.1.4.weight", f"u{u}.raw2", f"u{u}.c2", n, hh, ww, c, c)
+            self._finalize(ws, f"u{u}.c2", f"up_blocks.{u}.1.5", n, c, hh * ww, m, s2)
+            if u < d - 1:
+                a = self._apply_desc(n, hh, ww, c, True, c, 0, None, None)
+                call("b2u_gn_apply", ptr(B[f"u{u}.raw2"]), ptr(ws.stat[f"u{u}.c2"].coef), mptr(s2), None, None,
+                     ptr(B[f"u{u}.act2"]), C.byref(a), st)
+                prev = f"u{u}.act2"
+        # head (GroupNorm-apply + DropBlock + ReLU of the last unit fused in)
+        hd = HeadDesc()
+        hd.n, hd.h, hd.w, hd.c, hd.h0, hd.w0, hd.dtype = n, ws.h, ws.w, f, ws.h0, ws.w0, self.dtype
+        last = d - 1
+        logits = None
+        if want_logits:
+            if ws.logits is None:
+                ws.logits = torch.empty(n, 1, ws.h0, ws.w0, dtype=torch.float32, device=self.device)
+            logits = ws.logits
+        if mc is not None:
+            hd.return_num = int(mc.get("return_num", 0))
+            hd.fov_per_image = 0
+            call("b2u_head_fwd", ptr(B[f"u{last}.raw2"]), ptr(ws.stat[f"u{last}.c2"].coef), mptr(2 * d + 4 + 3 * last),
+                 ptr(self.w["output_conv.0.weight"]), ptr(ws.out) if head_out else None, ptr(logits), ptr(mc.get("fov")),
+                 ptr(mc["acc"]), ptr(mc.get("samples")), ptr(mc.get("iter_base")), C.byref(hd), st)
+        else:
+            call("b2u_head_fwd", ptr(B[f"u{last}.raw2"]), ptr(ws.stat[f"u{last}.c2"].coef), mptr(2 * d + 4 + 3 * last),
+                 ptr(self.w["output_conv.0.weight"]), ptr(ws.out), ptr(logits), None, None, None, None, C.byref(hd), st)
+        return ws.out

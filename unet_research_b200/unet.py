@@ -1,0 +1,214 @@
+"""`UNet` -- drop-in mirror of the reference model class (unet_code/utils/utils_unet.py:12-463).
+
+Same constructor, `set_dropblock` / `set_normalization` / `set_activation_function` / `create_model`
+builder protocol, same module tree (hence the same 75 state-dict keys) and the
+same `forward(x)` contract: any H, W (auto-padded to a multiple of 2**depth, de-padded), DropBlock
+scheduler stepped once per training forward (:410-411), sigmoid -> crop -> clamp -> NaN scrub (:436-444).
+
+The modules in the tree are parameter containers only; `forward` runs the B200 kernel schedule of
+`engine.UNetEngine` through the C ABI.  Configurations outside the reference scripts' canonical one
+(pool 'max', up 'upconv', connection 'cat', same padding, 2 convs per block, GroupNorm, ReLU) raise
+NotImplementedError at `create_model()`; CPU tensors raise -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+from .engine import MaskPlan, UNetEngine
+from .modules import DropBlock2D, LinearScheduler
+
+
+class UNet(nn.Module):
+    def __init__(self, init_channels: int = 3, filters: int = 64, output_channels: int = 1, model_depth: int = 4,
+                 pool_mode: str = 'max', up_mode: str = 'upconv', connection: str = 'cat', same_padding: bool = True,
+                 conv_layers_per_block: int = 2, checkpointing=True):
+        super().__init__()
+        self._kernel_size, self._stride = 3, 1
+        self._pool_kernel, self._pool_stride, self._upsample_factor = 2, 2, 2
+        self.same_padding = same_padding
+        self._init_channels, self._filters, self._output_channels = init_channels, filters, output_channels
+        self._base_filters = filters
+        if connection not in ['add', 'cat', 'none']:
+            raise ValueError('Connection type must be of (add, cat, none)')
+        self._connection = connection
+        self._padding = 'same' if same_padding else 0
+        self._norm = nn.Identity
+        self._bias = True
+        self._norm_params = {}
+        self._norm_keys = []
+        self._dropblock = nn.Identity()
+        if pool_mode not in ['max', 'avg', 'conv']:
+            raise ValueError('Pool Mode must be of (max, avg, conv).')
+        self._pool_mode = pool_mode
+        if up_mode not in ['upsample', 'upconv']:
+            raise ValueError('Up_Mode must be of (upsample, upconv).')
+        self._up_mode = up_mode
+        if conv_layers_per_block <= 1:
+            raise ValueError('Convolutional Layers in each block must be 2 or more.')
+        self._conv_layers_per_block = conv_layers_per_block
+        self._act_fcn = nn.ReLU()
+        self._model_depth = model_depth
+        self._checkpointing = checkpointing       # activation recompute is a memory trick; values are unchanged
+        self.compute_dtype = "bf16"               # "bf16" (tcgen05 kind::f16) or "tf32" (fp32 storage, kind::tf32)
+        self._engine: Optional[UNetEngine] = None
+        self._engine_key = None
+        self._mask_plans = {}
+
+    # ------------------------------------------------------------------ builder protocol (reference :98-160)
+    def set_dropblock(self, dropblock_class, block_size: int = 7, drop_prob: float = .1, use_scheduler: bool = True,
+                      start_drop_prob: float = 0., max_drop_prob: float = .2, dropblock_ls_steps: int = 500):
+        if use_scheduler:
+            self._dropblock = LinearScheduler(dropblock_class(block_size=block_size, drop_prob=drop_prob),
+                                              start_value=start_drop_prob, stop_value=max_drop_prob,
+                                              nr_steps=dropblock_ls_steps)
+        else:
+            self._dropblock = dropblock_class(block_size=block_size, drop_prob=drop_prob)
+
+    def set_normalization(self, normalization_class, params: dict):
+        self._norm = normalization_class
+        self._bias = False
+        self._norm_params = params
+        for key, value in params.items():
+            if value == 'fill':
+                self._norm_keys.append(key)
+
+    def update_norm_params(self):
+        for key in self._norm_keys:
+            self._norm_params[key] = self._filters
+
+    def set_activation_function(self, act_fcn):
+        self._act_fcn = act_fcn
+
+    def _check_supported(self):
+        bad = []
+        if self._pool_mode != 'max':
+            bad.append(f"pool_mode={self._pool_mode!r}")
+        if self._up_mode != 'upconv':
+            bad.append(f"up_mode={self._up_mode!r}")
+        if self._connection != 'cat':
+            bad.append(f"connection={self._connection!r}")
+        if not self.same_padding:
+            bad.append("same_padding=False")
+        if self._conv_layers_per_block != 2:
+            bad.append(f"conv_layers_per_block={self._conv_layers_per_block}")
+        if self._norm is not nn.GroupNorm:
+            bad.append(f"normalization {getattr(self._norm, '__name__', self._norm)} (GroupNorm only)")
+        if not isinstance(self._act_fcn, nn.ReLU):
+            bad.append("activation other than ReLU")
+        if self._output_channels != 1:
+            bad.append(f"output_channels={self._output_channels}")
+        inner = self._dropblock.dropblock if isinstance(self._dropblock, LinearScheduler) else self._dropblock
+        if not isinstance(inner, (nn.Identity, DropBlock2D)):
+            bad.append(f"dropblock class {type(inner).__name__}")
+        if bad:
+            raise NotImplementedError("the B200 path implements the reference scripts' canonical configuration only; "
+                                      "unsupported: " + ", ".join(bad))
+
+    def _conv_unit(self, cin, cout):
+        layers = [nn.Conv2d(cin, cout, self._kernel_size, self._stride, padding=self._padding, bias=self._bias)]
+        self._filters = cout
+        self.update_norm_params()
+        layers += [self._norm(**self._norm_params), self._dropblock, self._act_fcn]
+        return layers
+
+    def create_model(self):
+        self._check_supported()
+        self._filters = self._base_filters
+        self._num_groups = None
+        self.down_blocks = nn.ModuleList()
+        cin = self._init_channels
+        for lvl in range(self._model_depth):
+            cout = self._filters if lvl == 0 else self._filters * 2
+            layers = self._conv_unit(cin, cout) + self._conv_unit(cout, cout)
+            self.update_norm_params()
+            pooling = [nn.MaxPool2d(kernel_size=self._pool_kernel, stride=self._pool_stride), self._norm(**self._norm_params)]
+            self.down_blocks.append(nn.ModuleList([nn.Sequential(*layers), nn.Sequential(*pooling)]))
+            cin = cout
+        f = self._filters
+        self.conn_block = nn.Sequential(*(self._conv_unit(f, 2 * f) + self._conv_unit(2 * f, 2 * f)))
+        self.up_blocks = nn.ModuleList()
+        for _ in range(self._model_depth):
+            f = self._filters
+            up = [nn.ConvTranspose2d(f, f // 2, kernel_size=self._pool_kernel, stride=self._pool_stride, bias=self._bias)]
+            self._filters = f // 2
+            self.update_norm_params()
+            up += [self._norm(**self._norm_params), self._act_fcn]
+            layers = self._conv_unit(f, f // 2) + self._conv_unit(f // 2, f // 2)
+            self.up_blocks.append(nn.ModuleList([nn.Sequential(*up), nn.Sequential(*layers)]))
+        self.output_conv = nn.Sequential(nn.Conv2d(self._filters, self._output_channels, kernel_size=1, stride=self._stride,
+                                                   padding=self._padding, bias=self._bias), nn.Sigmoid())
+        gn = self.down_blocks[0][0][1]
+        self._num_groups = gn.num_groups
+        for m in self.modules():
+            if isinstance(m, nn.GroupNorm) and (m.num_groups != self._num_groups or abs(m.eps - 1e-5) > 0 or not m.affine):
+                raise NotImplementedError("GroupNorm must use one num_groups, eps=1e-5, affine=True")
+
+    # ------------------------------------------------------------------ engine management
+    def _dropblock_state(self):
+        """(active, drop_prob, block_size) of the single shared DropBlock instance (reference :117-134)."""
+        db = self._dropblock
+        if isinstance(db, LinearScheduler):
+            db = db.dropblock
+        if isinstance(db, DropBlock2D) and db.training and db.drop_prob != 0.:
+            return True, float(db.drop_prob), int(db.block_size)
+        return False, 0.0, 7
+
+    def _get_engine(self, device) -> UNetEngine:
+        dtype = _lib.F32 if self.compute_dtype == "tf32" else _lib.BF16
+        params = list(self.parameters())
+        key = (str(device), dtype, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        if self._engine is None or self._engine_key != key:
+            sd = {k: v for k, v in self.state_dict().items()}
+            if self._engine is None or self._engine_key[:2] != key[:2]:
+                self._engine = UNetEngine(sd, self._init_channels, self._base_filters, self._model_depth,
+                                          self._num_groups, dtype, device)
+                self._mask_plans = {}
+            else:
+                self._engine.load_weights(sd)
+            self._engine_key = key
+        return self._engine
+
+    def _mask_plan(self, eng, n_calls, ipc, ws, drop_prob, block_size) -> MaskPlan:
+        key = (n_calls, ipc, ws.h, ws.w, drop_prob, block_size)
+        mp = self._mask_plans.get(key)
+        if mp is None:
+            if len(self._mask_plans) > 4:          # scheduler ramps drop_prob every step: keep the cache small
+                self._mask_plans.clear()
+            mp = MaskPlan(n_calls, ipc, ws.h, ws.w, self._base_filters, self._model_depth, drop_prob, block_size, eng.device)
+            self._mask_plans[key] = mp
+        return mp
+
+    # ------------------------------------------------------------------ forward (reference :408-449)
+    def forward(self, x):
+        if type(self._dropblock) == LinearScheduler and self.training:
+            self._dropblock.step()
+        if not x.is_cuda:
+            raise _lib.B2uError("unet_research_b200.UNet runs on CUDA (B200) only: move the input to the GPU; "
+                                "there is deliberately no CPU fallback")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .training import unet_autograd_forward
+            return unet_autograd_forward(self, x)
+        return self._forward_inference(x)
+
+    def _forward_inference(self, x):
+        eng = self._get_engine(x.device)
+        n, _, h0, w0 = x.shape
+        self._original_size = (h0, w0)
+        ws = eng.workspace(n, h0, w0)
+        xin = x.detach().to(torch.float32).contiguous()
+        active, p, bs = self._dropblock_state()
+        masks = None
+        if active:
+            # one reference forward over the whole batch: every site draws ONE torch.rand of shape [N,C,H-6,W-6]
+            masks = self._mask_plan(eng, 1, n, ws, p, bs)
+            gen = torch.cuda.default_generators[x.device.index if x.device.index is not None else torch.cuda.current_device()]
+            masks.set_stream_position(gen.get_offset())
+            masks.generate(gen.initial_seed())
+            gen.set_offset(gen.get_offset() + masks.offset_per_call)
+        out = eng.forward(xin, ws, masks)
+        return out.clone()
