@@ -189,6 +189,17 @@ __host__ __device__ constexpr uint32_t umma_idesc(int m, int n, int ab_format) {
 }
 
 // ---- misc
+__device__ __forceinline__ float round_tf32(float x) {   // round-to-nearest (ties away) to the 10-bit tf32 mantissa
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// Storage conversion of an MMA operand: bf16 round-to-nearest-even, or fp32 pre-rounded to tf32 (the
+// tensor core would otherwise truncate the low 13 mantissa bits, a biased error twice as large).
+template <typename T> __device__ __forceinline__ T to_operand(float x);
+template <> __device__ __forceinline__ __nv_bfloat16 to_operand<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+template <> __device__ __forceinline__ float to_operand<float>(float x) { return round_tf32(x); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -429,7 +429,7 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, T* __restrict__
     int tap = static_cast<int>(i / (static_cast<long>(cols) * rows));
     int co = tflip ? col : row, ci = tflip ? row : col;
     int src_tap = tflip ? 8 - tap : tap;
-    out[i] = static_cast<T>(w[(static_cast<long>(co) * cin + ci) * 9 + src_tap]);
+    out[i] = to_operand<T>(w[(static_cast<long>(co) * cin + ci) * 9 + src_tap]);
   }
 }
 template <typename T>
@@ -439,7 +439,7 @@ __global__ void pack_convT_kernel(const float* __restrict__ w, T* __restrict__ o
     int ci = static_cast<int>(i % cin);
     int co = static_cast<int>((i / cin) % cout);
     int tap = static_cast<int>(i / (static_cast<long>(cin) * cout));
-    out[i] = static_cast<T>(w[(static_cast<long>(ci) * cout + co) * 4 + tap]);
+    out[i] = to_operand<T>(w[(static_cast<long>(ci) * cout + co) * 4 + tap]);
   }
 }
 

@@ -8,11 +8,6 @@
 
 namespace b2u {
 
-__device__ __forceinline__ float round_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 template <typename T> __device__ __forceinline__ void round_for_storage(float (&f)[8]) {}
 template <> __device__ __forceinline__ void round_for_storage<float>(float (&f)[8]) {
 #pragma unroll
