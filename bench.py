@@ -1,0 +1,370 @@
+"""bench.py -- headline benchmark of the U-Net / MC-DropBlock hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2]): dependent MC-DropBlock uncertainty of ONE synthetic DRIVE-shaped
+584x565 image (autopad 592x576), canonical U-Net (31.04 M parameters, GroupNorm(32), DropBlock2D bs 7
+p 0.15), bf16 tcgen05 convolutions.  A "step" is one batched pass of the hot path: `iter_batch`
+Monte-Carlo iterations (mask build -> forward -> head accumulate -> Philox advance), replayed as a CUDA
+graph.  `value` = forward passes per second over all ranks (weak scaling: every rank runs K steps of
+`iter_batch` iterations on the same image with its own Philox window; no data-path collective inside a
+step -- the single fp64 all-reduce that closes a real run is timed separately and reported).
+
+JSON keys follow the driver contract; see DESIGN.md "Measurement" for how each number is taken.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H0, W0 = 584, 565
+FLOP_PER_FORWARD = 500.46e9          # 2*M*N*K over the 18 conv3x3 + 4 convT + head
+CONV_FLOP_PER_FORWARD = 500.03e9     # the tensor-core convs only (first layer 0.39 G and head 0.04 G excluded)
+METRIC = "MC-DropBlock fwd passes/s at 584x565"
+UNIT = "passes/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops", 1590.0),
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def oracle_mc_forward_timer(steps: int, warmup: int, budget_s: float):
+    """Times the reference algorithm (oracle port, torch fp32 on the host cores, all threads) for the same
+    workload: one MC-DropBlock forward of the 584x565 image per step."""
+    import torch
+    from oracle import unet_oracle as O
+    from unet_research_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synthetic.make_state_dict(seed=1234)
+    x = synthetic.make_image(H0, W0, seed=1234)
+    fov = synthetic.make_fov_mask(H0, W0)
+    db = O.DropBlockCfg(0.15, 7, True)
+    torch.manual_seed(1234)
+
+    def one():
+        with torch.no_grad():
+            return O.unet_forward(sd, x, dropblock=db) * fov
+
+    t0 = time.perf_counter()
+    one()
+    first = time.perf_counter() - t0
+    # bounded sample: keep the whole run inside the budget
+    w = max(0, min(warmup, int(budget_s * 0.2 / max(first, 1e-3)) - 1))
+    k = max(1, min(steps, int(budget_s * 0.8 / max(first, 1e-3))))
+    for _ in range(w):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(k):
+        one()
+    dt = time.perf_counter() - t0
+    return k / dt, k, w + 1, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    val, k, w, cores = oracle_mc_forward_timer(args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": w,
+        "ms_per_step": 1000.0 / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "configs[2]: dependent MC-DropBlock, canonical U-Net, one 584x565 image, DropBlock bs7 p0.15",
+                   "step": "one MC forward pass (CPU, torch fp32, all host threads)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{k} timed MC forward passes of the 584x565 image after {w} warm-up (requested {args.steps}/{args.warmup}; "
+                                   "bounded to ~150 s of CPU work); oracle port of the reference (the Python reference cannot travel to the GPU box)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank, local, world = dist_env()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    import unet_research_b200 as U
+    from unet_research_b200 import _lib, synthetic
+    from unet_research_b200._lib import call, ptr, stream_ptr
+    from unet_research_b200.smoke_test import build_canonical
+
+    peaks = load_peaks()
+    NB = args.iter_batch
+    K, W = args.steps, args.warmup
+    model, _ = build_canonical(dev, dropblock=True, compute="bf16")
+    model.apply(U.set_dropblock_on)
+    x = synthetic.make_image(H0, W0, seed=1234).to(dev)
+    fov2d = synthetic.make_fov_mask(H0, W0).to(dev).reshape(H0, W0).contiguous()
+    eng = model._get_engine(dev)
+    ws = eng.workspace(NB, H0, W0)
+    masks = model._mask_plan(eng, NB, 1, ws, 0.15, 7)
+    acc = torch.zeros(2, H0, W0, dtype=torch.float64, device=dev)
+    samples = torch.zeros(25, H0, W0, dtype=torch.float32, device=dev)
+    iter_base = torch.full((1,), rank * 1_000_000, dtype=torch.int64, device=dev)
+    xb = x.expand(NB, -1, -1, -1).contiguous()
+    mc = {"acc": acc, "fov": fov2d, "samples": samples, "iter_base": iter_base, "return_num": 25}
+    seed = 1234
+    masks.set_stream_position(rank * (1 << 40))          # disjoint Philox windows per rank
+
+    def step():
+        masks.generate(seed)
+        eng.forward(xb, ws, masks, head_out=False, mc=mc)
+        masks.advance(NB)
+        call("b2u_advance_counter", ptr(iter_base), NB, stream_ptr())
+
+    # eager warm-up (sets kernel attributes), count launches of one step, then capture
+    step()
+    torch.cuda.synchronize(dev)
+    l0 = _lib.launch_count
+    step()
+    launches_per_step = _lib.launch_count - l0
+    torch.cuda.synchronize(dev)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    for _ in range(max(W, 3)):
+        graph.replay()
+    torch.cuda.synchronize(dev)
+
+    # ---- timed region: K graph replays, CUDA events on the launching stream, barrier + sync on both sides.
+    # Working set per step (activations ~1.0 GB x NB) far exceeds the 126 MB L2: no explicit flush needed.
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * K * NB / (ms_max / 1000.0)
+
+    # ---- the closing exchange of a real run (fp64 [2,H,W] all-reduce), timed on its own
+    allreduce_ms = None
+    if world > 1:
+        for _ in range(3):
+            dist.all_reduce(acc)
+        torch.cuda.synchronize(dev)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            dist.all_reduce(acc)
+        a1.record()
+        torch.cuda.synchronize(dev)
+        allreduce_ms = a0.elapsed_time(a1) / 10
+
+    # ---- roofline of the dominant kernel family (conv_gemm_kernel): per-launch CUDA-event timing, eager mode
+    conv_ms, other = time_conv_kernels(eng, ws, masks, xb, mc, seed, dev, reps=max(3, min(K, 10)))
+    conv_tflops = CONV_FLOP_PER_FORWARD * NB / (conv_ms / 1000.0) / 1e12
+    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (18 conv3x3 + 4 convT launches per step)",
+                "achieved": conv_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": conv_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+                "peak_source": peaks["src"] + " bf16_tflops_sustained (kernels timed inside a long step)",
+                "conv_ms_per_step": conv_ms, "step_ms": ms_max / K, "conv_share_of_step": conv_ms / (ms_max / K),
+                "other_kernels_ms_per_step": other}
+
+    # ---- e2e: the public API with HOST buffers (pinned), H2D of image + mask and D2H of mean/std/samples inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        T_e2e = args.e2e_iters
+        ev = U.DropBlockEval(model, num_iterations=T_e2e, return_num=25, iter_batch=NB)
+        im_h = synthetic.make_image(H0, W0, seed=1234).pin_memory()
+        fov_h = synthetic.make_fov_mask(H0, W0).pin_memory()
+        outs_h = [torch.empty(1, 1, H0, W0).pin_memory(), torch.empty(1, 1, H0, W0).pin_memory(),
+                  torch.empty(25, 1, 1, H0, W0).pin_memory()]
+
+        def e2e_once():
+            im_d = im_h.to(dev, non_blocking=True)
+            fov_d = fov_h.to(dev, non_blocking=True)
+            _, (mean, std, tens) = ev.predict_step((im_d, None, fov_d), 0)
+            outs_h[0].copy_(mean, non_blocking=True)
+            outs_h[1].copy_(std, non_blocking=True)
+            outs_h[2].copy_(tens, non_blocking=True)
+            torch.cuda.synchronize(dev)
+
+        e2e_once()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            e2e_once()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        # under torch.distributed predict_step shards T_e2e over the ranks, so T_e2e passes complete per call
+        e2e = {"value": reps * T_e2e / float(tt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": im_h.numel() * 4 + fov_h.numel() * 4,
+               "d2h_bytes_per_step": sum(o.numel() * 4 for o in outs_h),
+               "step": f"DropBlockEval.predict_step, {T_e2e} iterations per call (sharded over ranks), pinned host in/out",
+               "mc_1000_iter_projected_s": 1000.0 / (reps * T_e2e / float(tt.item()))}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        val, k, w, cores = oracle_mc_forward_timer(2, 0, budget_s=25.0)
+        cpu_baseline = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{k} MC-DropBlock forward passes of the same 584x565 image (oracle port, torch fp32, all host threads) after 1 warm-up"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "configs[2]: dependent MC-DropBlock uncertainty, canonical U-Net (filters 64, depth 4, GroupNorm 32), "
+                                   "one 584x565 image (autopad 592x576), DropBlock2D block_size 7 drop_prob 0.15",
+                       "iter_batch": NB, "passes_per_step": NB, "l2": "inputs larger than L2 (about 1 GB of activations per iteration)",
+                       "parallelism": f"mc-iteration sharding x{world}", "cuda_graph": True},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "tflops_whole_step": FLOP_PER_FORWARD * NB * world * K / (ms_max / 1000.0) / 1e12,
+            "mc_1000_iter_projected_s": 1000.0 / value, "allreduce_ms": allreduce_ms,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def time_conv_kernels(eng, ws, masks, xb, mc, seed, dev, reps):
+    """Eager replays with a CUDA event pair around every C-ABI launch; returns (sum of conv_gemm ms per step,
+    {entry point: ms per step} for everything else)."""
+    import torch
+    from unet_research_b200 import _lib
+    records = []
+    orig = _lib.call
+
+    def timed_call(name, *a):
+        if name in _lib._LAUNCHERS and not name.startswith("b2u_pack"):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            orig(name, *a)
+            e.record()
+            records.append((name, s, e))
+        else:
+            orig(name, *a)
+
+    import unet_research_b200.engine as E
+    E.call = timed_call
+    try:
+        for _ in range(reps):
+            masks.generate(seed)
+            eng.forward(xb, ws, masks, head_out=False, mc=mc)
+        torch.cuda.synchronize(dev)
+    finally:
+        E.call = orig
+    tot = {}
+    for name, s, e in records:
+        tot[name] = tot.get(name, 0.0) + s.elapsed_time(e)
+    per_step = {k: v / reps for k, v in tot.items()}
+    conv = per_step.pop("b2u_conv3x3_fwd", 0.0) + per_step.pop("b2u_convT2x2_fwd", 0.0)
+    return conv, per_step
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--iter-batch", type=int, default=5)
+    ap.add_argument("--e2e-iters", type=int, default=100)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

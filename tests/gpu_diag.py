@@ -83,7 +83,7 @@ def _conv_case(n, h, w, cin, cout, dtype, conv_t=False, block_n=0, stages=0):
     sr, _ = rel(ps, s_ref)
     nan = int(torch.isnan(got).sum())
     print(f"  {'convT' if conv_t else 'conv3'} n{n} {h}x{w} {cin}->{cout} dt{dtype} bn{block_n} st{stages}: rel {r:.3e} max {mx:.3e} stats_rel {sr:.3e} nan {nan} rows {rows.value} sgs {sgs.value}")
-    return r
+    return {"rel": r, "stats_rel": sr, "nan": nan}
 
 
 def sec_conv():
@@ -121,6 +121,7 @@ def sec_first():
     from unet_research_b200 import _lib
     from unet_research_b200._lib import call, ptr, stream_ptr
     dev = torch.device("cuda")
+    res = []
     for cin, (h0, w0), (h, w) in ((1, (120, 116), (128, 128)), (3, (64, 80), (64, 80)), (1, (584, 565), (592, 576))):
         g = torch.Generator().manual_seed(5)
         x = torch.rand(2, cin, h0, w0, generator=g).to(dev)
@@ -137,6 +138,8 @@ def sec_first():
         rs = ref.double().view(2, 32, -1)
         sr, _ = rel(ps, torch.stack([rs.sum(-1), (rs * rs).sum(-1)], -1))
         print(f"  first cin{cin} {h0}x{w0}->{h}x{w}: rel {r:.3e} max {mx:.3e} stats_rel {sr:.3e}")
+        res.append({"rel": r, "stats_rel": sr})
+    return res
 
 
 def sec_gn():
@@ -145,6 +148,7 @@ def sec_gn():
     from unet_research_b200 import _lib
     from unet_research_b200._lib import ApplyDesc, call, ptr, stream_ptr
     dev = torch.device("cuda")
+    res = []
     for c, h, w in ((64, 32, 48), (256, 20, 24), (1024, 8, 8)):
         n, G = 2, 32
         g = torch.Generator().manual_seed(c)
@@ -169,6 +173,8 @@ def sec_gn():
         ref = F.relu(F.group_norm(xr, G, gamma, beta, 1e-5))
         r, mx = rel(out.float().permute(0, 3, 1, 2), ref)
         print(f"  gn+relu c{c} {h}x{w}: rel {r:.3e} max {mx:.3e}")
+        res.append(r)
+    return res
 
 
 def sec_pool():
@@ -177,6 +183,7 @@ def sec_pool():
     from unet_research_b200 import _lib
     from unet_research_b200._lib import ApplyDesc, call, ptr, stream_ptr
     dev = torch.device("cuda")
+    res = []
     for c, h, w in ((64, 32, 48), (512, 12, 8)):
         n, G = 2, 32
         g = torch.Generator().manual_seed(c + 1)
@@ -209,6 +216,8 @@ def sec_pool():
         rs = pooled.float().permute(0, 3, 1, 2).double().reshape(n, G, -1)
         sr, _ = rel(ps, torch.stack([rs.sum(-1), (rs * rs).sum(-1)], -1))
         print(f"  apply_pool c{c}: skip rel {r1:.3e} pooled rel {r2:.3e} argmax match {argmatch:.6f} stats_rel {sr:.3e} first-half-untouched {float(cat[..., :c].abs().max()):.1f}")
+        res.append({"skip": r1, "pooled": r2, "argmax": argmatch, "stats_rel": sr, "untouched": float(cat[..., :c].abs().max())})
+    return res
 
 
 def sec_head():
@@ -241,6 +250,7 @@ def sec_head():
     r4, _ = rel(acc[1], (v.double() ** 2).sum(0))
     r5, _ = rel(samples, v[:2])
     print(f"  head: logits rel {r1:.3e} max {m1:.3e}; out rel {r2:.3e}; acc rel {r3:.3e} {r4:.3e}; samples rel {r5:.3e}")
+    return max(r1, r2, r3, r4, r5)
 
 
 def sec_dropblock():
@@ -248,6 +258,7 @@ def sec_dropblock():
     from oracle import unet_oracle as O
     from unet_research_b200.modules import DropBlock2D
     dev = torch.device("cuda")
+    res = []
     # (a) does torch compare `rand < gamma` in fp32?  (b) bit-exact masks vs the oracle using torch.rand on this GPU
     for shape in ((1, 64, 128, 128), (2, 32, 37, 36), (1, 64, 592, 576), (1, 1024, 37, 36), (3, 96, 9, 50)):
         x = torch.randn(*shape, device=dev)
@@ -268,6 +279,9 @@ def sec_dropblock():
         got = db(x)
         r, mx = rel(got, ref)
         print(f"  dropblock {shape}: mask mismatches {mism} / {m.numel()}  keep {int(keep)} vs {int(rec[0].sum())}  offset {off_got} vs {off_ref}  out rel {r:.2e}")
+        exact_keep = int(rec[0].double().sum())
+        res.append({"mismatches": mism, "keep": int(keep), "keep_ref": exact_keep, "offset": off_got, "offset_ref": off_ref, "out_rel": r})
+    return res
 
 
 def sec_rotate():
@@ -282,10 +296,13 @@ def sec_rotate():
     arr = (C.c_double * len(angs))(*angs)
     call("b2u_rotate_bilinear", ptr(x), ptr(out), len(angs), 1, 584, 565, arr, 1, stream_ptr())
     torch.cuda.synchronize()
+    res = []
     for i, a in enumerate(angs):
         ref = O.rotate_bilinear(x, a)
         r, mx = rel(out[i:i + 1], ref)
         print(f"  rotate {a}: rel {r:.3e} max {mx:.3e}")
+        res.append(mx)
+    return res
 
 
 def _build_model(dev, dropblock=False, compute="bf16", init_channels=1):
@@ -336,6 +353,7 @@ def _forward_case(h, w, n, compute):
     for tname, bname in names.items():
         rr, _ = rel(B[bname].float().permute(0, 3, 1, 2), taps[tname])
         print(f"     {tname:12s} rel {rr:.3e}")
+    return {"out_rel": r, "out_max": mx, "logits_rel": rl, "logits_max": ml}
 
 
 def sec_forward():
@@ -368,6 +386,7 @@ def sec_mc():
     x = synthetic.make_image(h, w, seed=1234).to(dev)
     fov = synthetic.make_fov_mask(h, w).to(dev)
     T = 6
+    res = []
     for graph in (False, True):
         ev = U.DropBlockEval(m, num_iterations=T, return_num=4, iter_batch=2, use_cuda_graph=graph)
         torch.manual_seed(77)
@@ -381,6 +400,9 @@ def sec_mc():
               f"max|std-ref| {rel(std, rstd)[1]:.3e} (std max {float(rstd.max()):.3f}) offset {off_got} vs {off_ref}")
         for i in range(4):
             print(f"     sample {i}: rel {rel(tens[i], rtens[i])[0]:.3e}")
+        res.append({"mean": rel(mean, rmean)[0], "std_maxabs": rel(std, rstd)[1], "samples": rel(tens, rtens)[0],
+                    "offset": off_got, "offset_ref": off_ref})
+    return res
 
 
 def sec_rot_ens():
@@ -399,6 +421,7 @@ def sec_rot_ens():
     _, (mean, std, tens) = ev.predict_step((x, None, fov), 0)
     rmean, rstd, rtens = O.rotation_ensemble(sd, x, fov, 5, 3)
     print(f"  rotation ensemble: mean rel {rel(mean, rmean)[0]:.3e} std rel {rel(std, rstd)[0]:.3e} max|d| {rel(std, rstd)[1]:.3e} samples rel {rel(tens, rtens)[0]:.3e}")
+    return {"mean": rel(mean, rmean)[0], "std_maxabs": rel(std, rstd)[1], "samples": rel(tens, rtens)[0]}
 
 
 def main():
