@@ -172,39 +172,21 @@ def run_gpu(args):
     model.apply(U.set_dropblock_on)
     x = synthetic.make_image(H0, W0, seed=1234).to(dev)
     fov2d = synthetic.make_fov_mask(H0, W0).to(dev).reshape(H0, W0).contiguous()
-    eng = model._get_engine(dev)
-    ws = eng.workspace(NB, H0, W0)
-    masks = model._mask_plan(eng, NB, 1, ws, 0.15, 7)
-    acc = torch.zeros(2, H0, W0, dtype=torch.float64, device=dev)
-    samples = torch.zeros(25, H0, W0, dtype=torch.float32, device=dev)
-    iter_base = torch.full((1,), rank * 1_000_000, dtype=torch.int64, device=dev)
-    xb = x.expand(NB, -1, -1, -1).contiguous()
-    mc = {"acc": acc, "fov": fov2d, "samples": samples, "iter_base": iter_base, "return_num": 25}
+    ev = U.DropBlockEval(model, num_iterations=1000, return_num=25, iter_batch=NB)
+    runner = ev._runner(NB, H0, W0, dev, True, 0.15, 7)
     seed = 1234
-    masks.set_stream_position(rank * (1 << 40))          # disjoint Philox windows per rank
-
-    def step():
-        masks.generate(seed)
-        eng.forward(xb, ws, masks, head_out=False, mc=mc)
-        masks.advance(NB)
-        call("b2u_advance_counter", ptr(iter_base), NB, stream_ptr())
-
-    # eager warm-up (sets kernel attributes), count launches of one step, then capture
-    step()
+    torch.manual_seed(seed)                                # the e2e leg reads the same key from torch's CUDA generator
+    # disjoint Philox windows / sample indices per rank: rank r starts at global iteration r * 10^6
+    runner.begin(x, fov2d, rank * 1_000_000, seed, 0)
+    # warm-up: one eager pair of steps (sets kernel attributes, counts launches), graph capture, replays
+    W_eff = max(W, 3)
+    runner.run_steps(4 + 2 * ((W_eff + 1) // 2))
     torch.cuda.synchronize(dev)
-    l0 = _lib.launch_count
-    step()
-    launches_per_step = _lib.launch_count - l0
-    torch.cuda.synchronize(dev)
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        step()
-    for _ in range(max(W, 3)):
-        graph.replay()
-    torch.cuda.synchronize(dev)
+    launches_per_step = runner.launches_per_step
+    acc = runner.acc
 
-    # ---- timed region: K graph replays, CUDA events on the launching stream, barrier + sync on both sides.
-    # Working set per step (activations ~1.0 GB x NB) far exceeds the 126 MB L2: no explicit flush needed.
+    # ---- timed region: K steps (graph replays of two steps each), CUDA events on the launching stream,
+    # barrier + sync on both sides.  Working set per step (~1 GB of activations x NB) far exceeds the 126 MB L2.
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -213,8 +195,7 @@ def run_gpu(args):
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(K):
-        graph.replay()
+    runner.run_steps(K)
     e1.record()
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -242,7 +223,7 @@ def run_gpu(args):
         allreduce_ms = a0.elapsed_time(a1) / 10
 
     # ---- roofline of the dominant kernel family (conv_gemm_kernel): per-launch CUDA-event timing, eager mode
-    conv_ms, other = time_conv_kernels(eng, ws, masks, xb, mc, seed, dev, reps=max(3, min(K, 10)))
+    conv_ms, other = time_conv_kernels(runner, dev, reps=max(3, min(K, 10)))
     conv_tflops = CONV_FLOP_PER_FORWARD * NB / (conv_ms / 1000.0) / 1e12
     roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (18 conv3x3 + 4 convT launches per step)",
                 "achieved": conv_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -255,7 +236,7 @@ def run_gpu(args):
     e2e = None
     if not args.no_e2e:
         T_e2e = args.e2e_iters
-        ev = U.DropBlockEval(model, num_iterations=T_e2e, return_num=25, iter_batch=NB)
+        ev.num_iterations = T_e2e
         im_h = synthetic.make_image(H0, W0, seed=1234).pin_memory()
         fov_h = synthetic.make_fov_mask(H0, W0).pin_memory()
         outs_h = [torch.empty(1, 1, H0, W0).pin_memory(), torch.empty(1, 1, H0, W0).pin_memory(),
@@ -302,7 +283,8 @@ def run_gpu(args):
             "config": {"workload": "configs[2]: dependent MC-DropBlock uncertainty, canonical U-Net (filters 64, depth 4, GroupNorm 32), "
                                    "one 584x565 image (autopad 592x576), DropBlock2D block_size 7 drop_prob 0.15",
                        "iter_batch": NB, "passes_per_step": NB, "l2": "inputs larger than L2 (about 1 GB of activations per iteration)",
-                       "parallelism": f"mc-iteration sharding x{world}", "cuda_graph": True},
+                       "parallelism": f"mc-iteration sharding x{world}", "cuda_graph": True,
+                       "mask_build": "side stream, overlapped with the forward of the previous step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "tflops_whole_step": FLOP_PER_FORWARD * NB * world * K / (ms_max / 1000.0) / 1e12,
@@ -314,7 +296,7 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def time_conv_kernels(eng, ws, masks, xb, mc, seed, dev, reps):
+def time_conv_kernels(runner, dev, reps):
     """Eager replays with a CUDA event pair around every C-ABI launch; returns (sum of conv_gemm ms per step,
     {entry point: ms per step} for everything else)."""
     import torch
@@ -336,8 +318,8 @@ def time_conv_kernels(eng, ws, masks, xb, mc, seed, dev, reps):
     E.call = timed_call
     try:
         for _ in range(reps):
-            masks.generate(seed)
-            eng.forward(xb, ws, masks, head_out=False, mc=mc)
+            runner.masks[0].generate(runner.seed)
+            runner.eng.forward(runner.x, runner.ws, runner.masks[0], head_out=False, mc=runner.mc)
         torch.cuda.synchronize(dev)
     finally:
         E.call = orig

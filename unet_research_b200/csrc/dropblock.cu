@@ -19,44 +19,47 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
                                               uint32_t k1, uint32_t (&out)[4]) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0;
-    const uint32_t n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    // one 32x32->64 multiply (IMAD.WIDE) yields both halves
+    const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
+    const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
+    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1;
+    c1 = static_cast<uint32_t>(p1);
+    c3 = static_cast<uint32_t>(p0);
+    c0 = n0;
+    c2 = n2;
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// grid = (blocks, n_calls).  Each warp-iteration: 32 consecutive thread indices of torch's launch, one trip.
+// grid = (ceil(torch_grid / 1), n_calls) blocks of 256 threads: block b, thread t IS torch's thread
+// idx = 256*b + t for every trip, so no index arithmetic beyond one add per trip.
 __global__ void __launch_bounds__(256) dropblock_centers_kernel(const b2u_dropblock_call* __restrict__ table, uint64_t seed,
                                          const unsigned long long* __restrict__ offset_base,
                                          uint32_t* __restrict__ center_bits) {
   const b2u_dropblock_call c = table[blockIdx.y];
+  if (blockIdx.x >= c.grid) return;
   const uint32_t tn = c.grid * 256u;
-  const uint64_t trips = (static_cast<uint64_t>(c.numel) - 1) / (static_cast<uint64_t>(tn) * 4) + 1;
-  const uint32_t warps_per_trip = tn / 32;
-  const uint64_t total_warp_items = trips * warps_per_trip;
+  const uint32_t trips = (c.numel - 1u) / (tn * 4u) + 1u;     // numel <= 2^32-1, tn*4 <= 2^21 * ... fits
   const uint64_t off = c.philox_offset + (offset_base ? *offset_base : 0ull);
-  const uint64_t ctr_base = off >> 2;                      // curand skipahead: offset counts 32-bit words
+  const uint64_t ctr_base = off >> 2;                         // curand skipahead: offset counts 32-bit words
   const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
   const int lane = threadIdx.x & 31;
+  const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+  const uint32_t idx0 = idx & ~31u;
   uint32_t* out = center_bits + c.center_word_off;
-  const uint64_t warp_global = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t warp_stride = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
-  for (uint64_t item = warp_global; item < total_warp_items; item += warp_stride) {
-    const uint64_t trip = item / warps_per_trip;
-    const uint32_t idx0 = static_cast<uint32_t>(item - trip * warps_per_trip) * 32u;
+  const uint32_t lo_t = c.thresh_lo, hi_t = c.thresh_hi;
+  for (uint32_t trip = 0; trip < trips; ++trip) {
     const uint64_t ctr = ctr_base + trip;
     uint32_t r[4];
-    philox4x32_10(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), idx0 + lane, 0u, k0, k1, r);
+    philox4x32_10(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), idx, 0u, k0, k1, r);
     uint32_t words[4];
 #pragma unroll
-    for (int ii = 0; ii < 4; ++ii) words[ii] = __ballot_sync(0xffffffffu, r[ii] < c.thresh_lo || r[ii] >= c.thresh_hi);
+    for (int ii = 0; ii < 4; ++ii) words[ii] = __ballot_sync(0xffffffffu, r[ii] < lo_t || r[ii] >= hi_t);
     if (lane < 4) {
-      const uint64_t p0 = trip * 4ull * tn + static_cast<uint64_t>(lane) * tn + idx0;   // first element of this word
+      const uint64_t p0 = (static_cast<uint64_t>(trip) * 4ull + lane) * tn + idx0;   // first element of this word
       if (p0 < c.numel) {
         const uint32_t wsel = lane == 0 ? words[0] : lane == 1 ? words[1] : lane == 2 ? words[2] : words[3];
         out[p0 >> 5] = wsel;
@@ -130,13 +133,23 @@ __global__ void __launch_bounds__(128) dropblock_dilate_kernel(const b2u_dropblo
 #pragma unroll
   for (int i = 0; i < RING; ++i) ring[i] = 0u;
   unsigned long long keep = 0;
-  // rows h-bs+1 .. h contribute to output row h; prime the window with rows h_begin-bs+1 .. h_begin-1
-  for (int r = h_begin - bs + 1; r < h_end; ++r) {
-    uint32_t sm = 0u;
+  // rows h-bs+1 .. h contribute to output row h; prime the window with rows h_begin-bs+1 .. h_begin-1.
+  // The two 32-bit windows of row r+1 are fetched before row r is processed (software prefetch).
+  auto fetch = [&](int r, uint32_t& lo, uint32_t& hi) {
+    lo = hi = 0u;
     if (r >= 0 && r < hc) {
       const uint64_t rowbit = plane_bit + static_cast<uint64_t>(r) * wc;
-      const uint32_t lo = row_bits(cb, rowbit, w0 - 32, wc);
-      const uint32_t hi = row_bits(cb, rowbit, w0, wc);
+      lo = row_bits(cb, rowbit, w0 - 32, wc);
+      hi = row_bits(cb, rowbit, w0, wc);
+    }
+  };
+  uint32_t nlo, nhi;
+  fetch(h_begin - bs + 1, nlo, nhi);
+  for (int r = h_begin - bs + 1; r < h_end; ++r) {
+    const uint32_t lo = nlo, hi = nhi;
+    if (r + 1 < h_end) fetch(r + 1, nlo, nhi);
+    uint32_t sm = 0u;
+    {
       uint64_t v = (static_cast<uint64_t>(hi) << 32) | lo;
       // OR of shifts 0..bs-1 by doubling
       int have = 1;
@@ -158,12 +171,14 @@ __global__ void __launch_bounds__(128) dropblock_dilate_kernel(const b2u_dropblo
     for (int i = 0; i < RING; ++i) drop |= ring[i];
     const uint32_t keepw = ~drop & valid_w;
     keep += __popc(keepw);
-    // 32x32 bit transpose: lane k ends with the word of pixel w0+k (bit j = channel cg*32+j)
-    uint32_t mine = 0u;
+    // 32x32 bit transpose (lane = channel -> lane = pixel) with 5 butterfly exchanges instead of 32 ballots:
+    // at distance j the off-diagonal j x j blocks of every 2j x 2j block swap between lanes i and i^j.
+    uint32_t mine = keepw;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const uint32_t wk = __ballot_sync(0xffffffffu, (keepw >> k) & 1u);
-      if (lane == k) mine = wk;
+    for (int j = 16; j >= 1; j >>= 1) {
+      const uint32_t m = j == 16 ? 0x0000FFFFu : j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+      const uint32_t y = __shfl_xor_sync(0xffffffffu, mine, j);
+      mine = (lane & j) ? ((mine & ~m) | ((y & ~m) >> j)) : ((mine & m) | ((y & m) << j));
     }
     if (w0 + lane < c.w) {
       mout[((static_cast<uint64_t>(img) * c.h + r) * c.w + (w0 + lane)) * cgs + cg] = mine;
@@ -182,7 +197,11 @@ using namespace b2u;
 extern "C" int b2u_dropblock_centers(const b2u_dropblock_call* table, int n_calls, uint64_t seed,
                                      const unsigned long long* offset_base, uint32_t* center_bits, void* stream) {
   B2U_REQUIRE(table && center_bits && n_calls > 0, "bad arguments");
-  dim3 grid(b2u_num_sms() * 2, n_calls);
+  int sms = 0, mt = 0;
+  int rc = b2u_device_info(&sms, &mt);
+  if (rc) return rc;
+  // torch's grid.x never exceeds SMs * (maxThreadsPerSM / 256); calls with a smaller grid exit early
+  dim3 grid(sms * (mt / 256), n_calls);
   dropblock_centers_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, seed, offset_base, center_bits);
   B2U_LAUNCH_CHECK();
   return B2U_OK;

@@ -153,42 +153,79 @@ struct ApplyParams {
   double numel_per_call2;
 };
 
-__device__ __forceinline__ void apply8(float (&f)[8], const float2* __restrict__ cf, uint32_t m1, bool relu) {
+struct Coef8 {
+  float a[8], b[8];
+  __device__ __forceinline__ void load(const float2* __restrict__ cf) {   // 8 consecutive channels = 64 B
+    const float4* p = reinterpret_cast<const float4*>(cf);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = __ldg(p + i);
+      a[2 * i] = t.x; b[2 * i] = t.y; a[2 * i + 1] = t.z; b[2 * i + 1] = t.w;
+    }
+  }
+};
+
+__device__ __forceinline__ void apply8(float (&f)[8], const Coef8& cf, uint32_t m1, bool relu) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    float2 ab = __ldg(cf + i);
-    float v = fmaf(f[i], ab.x, ab.y);
+    float v = fmaf(f[i], cf.a[i], cf.b[i]);
     v = ((m1 >> i) & 1u) ? v : 0.f;
     f[i] = relu ? fmaxf(v, 0.f) : v;
   }
 }
 
+// grid = (blocks per image, n); thread t owns channel vector t % cvs (coefficients live in registers) and
+// streams kApplyUnroll pixels per trip with all loads issued before the first use.
+constexpr int kApplyUnroll = 4;
 template <typename T>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, const float2* __restrict__ coef, const uint8_t* __restrict__ mask1,
                                 const uint8_t* __restrict__ mask2, const unsigned long long* __restrict__ keep2,
                                 T* __restrict__ out, ApplyParams p) {
+  const int n = blockIdx.y;
   const int cvs = p.c >> 3;
+  const int cv = threadIdx.x % cvs;
+  const int slot = threadIdx.x / cvs;
+  const int slots = blockDim.x / cvs;
   const long hw = static_cast<long>(p.h) * p.w;
-  const long total = static_cast<long>(p.n) * hw * cvs;
-  for (long v = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; v < total; v += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long pix = v / cvs;
-    const int cv = static_cast<int>(v - pix * cvs);
-    const int n = static_cast<int>(pix / hw);
-    Vec8<T> vec;
-    vec.load(x + pix * p.c + cv * 8);
-    float f[8];
-    vec.to_float(f);
-    const uint32_t m1 = mask1 ? mask1[pix * cvs + cv] : 0xFFu;
-    apply8(f, coef + static_cast<size_t>(n) * p.c + cv * 8, m1, p.relu != 0);
-    if (mask2) {
-      const uint32_t m2 = mask2[pix * (p.mask2_cstride >> 3) + (p.mask2_coffset >> 3) + cv];
-      const float s2 = static_cast<float>(p.numel_per_call2 / static_cast<double>(keep2[n / p.images_per_call2]));
+  Coef8 cf;
+  cf.load(coef + static_cast<size_t>(n) * p.c + cv * 8);
+  float s2 = 1.f;
+  if (mask2) s2 = static_cast<float>(p.numel_per_call2 / static_cast<double>(keep2[n / p.images_per_call2]));
+  const bool relu = p.relu != 0;
+  const long img0 = static_cast<long>(n) * hw;
+  const int m2s = p.mask2_cstride >> 3, m2o = (p.mask2_coffset >> 3) + cv;
+  const long stride = static_cast<long>(gridDim.x) * slots * kApplyUnroll;
+  for (long base = static_cast<long>(blockIdx.x) * slots * kApplyUnroll + slot; base < hw; base += stride) {
+    Vec8<T> vec[kApplyUnroll];
+    uint32_t m1[kApplyUnroll], m2[kApplyUnroll];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = ((m2 >> i) & 1u) ? f[i] * s2 : 0.f;
+    for (int u = 0; u < kApplyUnroll; ++u) {
+      const long pl = base + static_cast<long>(u) * slots;
+      if (pl < hw) {
+        const long pix = img0 + pl;
+        vec[u].load(x + pix * p.c + cv * 8);
+        m1[u] = mask1 ? mask1[pix * cvs + cv] : 0xFFu;
+        m2[u] = mask2 ? mask2[pix * m2s + m2o] : 0xFFu;
+      }
     }
-    round_for_storage<T>(f);
-    vec.from_float(f);
-    vec.store(out + pix * p.out_cstride + p.out_coffset + cv * 8);
+#pragma unroll
+    for (int u = 0; u < kApplyUnroll; ++u) {
+      const long pl = base + static_cast<long>(u) * slots;
+      if (pl < hw) {
+        const long pix = img0 + pl;
+        float f[8];
+        vec[u].to_float(f);
+        apply8(f, cf, m1[u], relu);
+        if (mask2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = ((m2[u] >> i) & 1u) ? f[i] * s2 : 0.f;
+        }
+        round_for_storage<T>(f);
+        Vec8<T> o;
+        o.from_float(f);
+        o.store(out + pix * p.out_cstride + p.out_coffset + cv * 8);
+      }
+    }
   }
 }
 
@@ -206,7 +243,8 @@ __global__ void __launch_bounds__(256) gn_apply_pool_kernel(const T* __restrict_
   const int slots = blockDim.x / cvs;
   const int ph = p.h >> 1, pw = p.w >> 1;
   const int npool = ph * pw;
-  const float2* cf = coef + static_cast<size_t>(n) * p.c + cv * 8;
+  Coef8 cf;
+  cf.load(coef + static_cast<size_t>(n) * p.c + cv * 8);
   float s2 = 1.f;
   if (mask2) s2 = static_cast<float>(p.numel_per_call2 / static_cast<double>(keep2[n / p.images_per_call2]));
   float s[8], q[8];
@@ -302,7 +340,9 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x, cons
       float f[8];
       vec.to_float(f);
       const uint32_t m1 = mask1 ? mask1[pix * lpp + lane_in] : 0xFFu;
-      apply8(f, coef + static_cast<size_t>(n) * d.c + lane_in * 8, m1, true);
+      Coef8 cf;
+      cf.load(coef + static_cast<size_t>(n) * d.c + lane_in * 8);
+      apply8(f, cf, m1, true);
       float dot = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) dot = fmaf(f[i], wh[i], dot);
@@ -527,15 +567,22 @@ extern "C" int b2u_gn_apply(const void* x, const float* coef, const uint32_t* ma
   if (rc) return rc;
   B2U_REQUIRE(x && coef && out, "null pointer");
   B2U_REQUIRE(!mask2 || (keep_counts2 && d->mask2_cstride % 8 == 0 && d->mask2_coffset % 8 == 0), "mask2 needs keep counts and 8-aligned channel layout");
-  const long total = static_cast<long>(d->n) * d->h * d->w * (d->c / 8);
-  const int grid = grid_for(total, 256);
+  B2U_REQUIRE(d->c / 8 <= 256, "at most 2048 channels");
+  const int threads = pick_threads(d->c / 8);
+  const int slots = threads / (d->c / 8);
+  const long hw = static_cast<long>(d->h) * d->w;
+  long bpi = (hw + static_cast<long>(slots) * kApplyUnroll - 1) / (static_cast<long>(slots) * kApplyUnroll);
+  const long cap = (static_cast<long>(b2u_num_sms()) * 16 + d->n - 1) / d->n;
+  if (bpi > cap) bpi = cap;
+  if (bpi < 1) bpi = 1;
+  dim3 grid(static_cast<unsigned>(bpi), d->n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (d->dtype == B2U_F32)
-    gn_apply_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), reinterpret_cast<const float2*>(coef),
+    gn_apply_kernel<float><<<grid, threads, 0, st>>>(static_cast<const float*>(x), reinterpret_cast<const float2*>(coef),
                                                  reinterpret_cast<const uint8_t*>(mask1), reinterpret_cast<const uint8_t*>(mask2),
                                                  keep_counts2, static_cast<float*>(out), p);
   else
-    gn_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), reinterpret_cast<const float2*>(coef),
+    gn_apply_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), reinterpret_cast<const float2*>(coef),
                                                          reinterpret_cast<const uint8_t*>(mask1), reinterpret_cast<const uint8_t*>(mask2),
                                                          keep_counts2, static_cast<__nv_bfloat16*>(out), p);
   B2U_LAUNCH_CHECK();

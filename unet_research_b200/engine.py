@@ -277,29 +277,34 @@ class UNetEngine:
 
     # ---- weights
     def load_weights(self, sd: Dict[str, torch.Tensor]):
+        """(Re)pack the weights.  Existing packed buffers are overwritten IN PLACE so that device pointers
+        baked into captured CUDA graphs stay valid across optimiser steps / load_state_dict."""
         dev, dt = self.device, _torch_dtype(self.dtype)
         st = stream_ptr()
-        self.w = {}
+
+        def slot(key, shape, dtype):
+            t = self.w.get(key)
+            if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+                t = torch.empty(shape, dtype=dtype, device=dev)
+                self.w[key] = t
+            return t
+
         for k, v in sd.items():
             v32 = v.detach().to(device=dev, dtype=torch.float32).contiguous()
             if v32.dim() == 4 and k == "down_blocks.0.0.0.weight":
-                self.w[k] = v32                                            # direct first-layer kernel reads fp32
+                slot(k, v32.shape, torch.float32).copy_(v32)               # direct first-layer kernel reads fp32
             elif v32.dim() == 4 and k.startswith("output_conv"):
                 if v32.shape[0] != 1:
                     raise NotImplementedError("head kernel supports output_channels == 1")
-                self.w[k] = v32.reshape(-1).contiguous()
+                slot(k, (v32.numel(),), torch.float32).copy_(v32.reshape(-1))
             elif v32.dim() == 4 and v32.shape[2] == 3:
                 cout, cin = v32.shape[0], v32.shape[1]
-                packed = torch.empty(9, cout, cin, dtype=dt, device=dev)
-                call("b2u_pack_conv3x3_weight", ptr(v32), ptr(packed), cout, cin, self.dtype, 0, st)
-                self.w[k] = packed
+                call("b2u_pack_conv3x3_weight", ptr(v32), ptr(slot(k, (9, cout, cin), dt)), cout, cin, self.dtype, 0, st)
             elif v32.dim() == 4 and v32.shape[2] == 2:
                 cin, cout = v32.shape[0], v32.shape[1]
-                packed = torch.empty(4, cout, cin, dtype=dt, device=dev)
-                call("b2u_pack_convT2x2_weight", ptr(v32), ptr(packed), cin, cout, self.dtype, st)
-                self.w[k] = packed
+                call("b2u_pack_convT2x2_weight", ptr(v32), ptr(slot(k, (4, cout, cin), dt)), cin, cout, self.dtype, st)
             else:
-                self.w[k] = v32
+                slot(k, v32.shape, torch.float32).copy_(v32)
         torch.cuda.current_stream().synchronize()      # v32 temporaries die here
 
     # ---- layout queries

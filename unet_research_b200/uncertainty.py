@@ -61,9 +61,122 @@ class _MCBase(nn.Module):
         return self._model(x)
 
 
+class MCRunner:
+    """Persistent state of the Monte-Carlo DropBlock loop for one (model, iteration batch, image size, p, bs):
+    workspace, two ping-pong DropBlock mask plans, static input / accumulator buffers and ONE captured CUDA
+    graph that covers two steps.  Inside the graph the integer-ALU-bound mask build of the NEXT step runs on
+    a side stream concurrently with the tensor-core-bound forward of the CURRENT step:
+
+        main :  forward(masks A) -------------------->  forward(masks B) -------------------->
+        side :  build masks B (next step) ---> join     build masks A (step after) ---> join
+
+    Nothing is allocated and no graph is captured after the first call."""
+
+    def __init__(self, model, nb: int, h0: int, w0: int, device, active: bool, drop_prob: float, block_size: int,
+                 return_num: int, use_cuda_graph: bool = True, overlap: bool = True):
+        self.model, self.nb, self.h0, self.w0, self.dev = model, nb, h0, w0, device
+        self.eng: UNetEngine = model._get_engine(device)
+        self.ws = self.eng.workspace(nb, h0, w0)
+        self.active = active
+        self.use_graph = use_cuda_graph
+        self.overlap = overlap and active
+        cin = self.eng.init_channels
+        if active:
+            mk = lambda: MaskPlan(nb, 1, self.ws.h, self.ws.w, self.eng.filters, self.eng.depth, drop_prob, block_size, device)
+            self.masks = [mk(), mk()] if self.overlap else [mk()]
+            self.per_iter = self.masks[0].offset_per_call
+        else:
+            self.masks, self.per_iter = [], 0
+        self.R = return_num
+        self.x = torch.zeros(nb, cin, h0, w0, dtype=torch.float32, device=device)
+        self.fov = torch.zeros(h0, w0, dtype=torch.float32, device=device)
+        self.acc = torch.zeros(2, h0, w0, dtype=torch.float64, device=device)
+        self.samples = torch.zeros(max(return_num, 1), h0, w0, dtype=torch.float32, device=device)
+        self.iter_base = torch.zeros(1, dtype=torch.int64, device=device)
+        self.mc = {"acc": self.acc, "fov": self.fov, "samples": self.samples if return_num > 0 else None,
+                   "iter_base": self.iter_base, "return_num": return_num}
+        self.side = torch.cuda.Stream(device=device) if self.overlap else None
+        self.graph = None
+        self.launches_per_step = 0
+        self.seed = 0
+
+    # ---- building blocks (all launch-only)
+    def _forward(self, k: int):
+        m = self.masks[k] if self.active else None
+        self.eng.forward(self.x, self.ws, m, head_out=False, mc=self.mc)
+        call("b2u_advance_counter", ptr(self.iter_base), self.nb, stream_ptr())
+
+    def _generate(self, k: int, stride_blocks: int):
+        m = self.masks[k]
+        m.generate(self.seed)
+        m.advance(stride_blocks * self.nb)
+
+    def _pair(self):
+        """Two steps.  Precondition: masks[0] hold the masks of the first step."""
+        if not self.active:
+            self._forward(0)
+            self._forward(0)
+            return
+        if not self.overlap:
+            self._forward(0)
+            self._generate(0, 1)
+            self._forward(0)
+            self._generate(0, 1)
+            return
+        main = torch.cuda.current_stream(self.dev)
+        for cur, nxt in ((0, 1), (1, 0)):
+            self.side.wait_stream(main)                 # fork: side sees everything enqueued so far
+            with torch.cuda.stream(self.side):
+                self._generate(nxt, 2)                  # masks for the following step, concurrently ...
+            self._forward(cur)                          # ... with this step's forward
+            main.wait_stream(self.side)                 # join
+
+    def begin(self, im: torch.Tensor, fov: torch.Tensor, t0: int, seed: int, stream_start: int):
+        """Load one image, reset the accumulators and position the Philox windows at global iteration t0."""
+        self.x.copy_(im.detach().to(torch.float32).expand(self.nb, -1, -1, -1))
+        self.fov.copy_(fov.reshape(self.h0, self.w0))
+        self.acc.zero_()
+        self.samples.zero_()
+        self.iter_base.fill_(t0)
+        if self.graph is not None and seed != self.seed:
+            self.graph = None                              # the Philox key is a captured kernel argument
+        self.seed = seed
+        if self.active:
+            base = stream_start + t0 * self.per_iter
+            self.masks[0].set_stream_position(base)
+            if self.overlap:
+                self.masks[1].set_stream_position(base + self.nb * self.per_iter)
+            self._generate(0, 2 if self.overlap else 1)           # prologue: masks of the first step
+
+    def run_steps(self, steps: int):
+        """`steps` batched steps (= steps * nb iterations)."""
+        pairs, odd = divmod(steps, 2)
+        if pairs:
+            if self.use_graph and self.graph is None and pairs >= 2:
+                l0 = _lib.launch_count
+                self._pair()                              # eager warm-up pair (sets kernel attributes)
+                self.launches_per_step = (_lib.launch_count - l0) // 2
+                pairs -= 1
+                torch.cuda.synchronize(self.dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._pair()
+                self.graph = g
+            for _ in range(pairs):
+                if self.graph is not None:
+                    self.graph.replay()
+                else:
+                    self._pair()
+        if odd:
+            # masks[0] already hold this step's masks (built by the prologue or by the previous pair)
+            self._forward(0)
+            if self.active and not self.overlap:
+                self._generate(0, 1)
+
+
 class DropBlockEval(_MCBase):
     def __init__(self, model, num_iterations=1000, return_num=25, mode='save', resize=-1, iter_batch: int = 5,
-                 use_cuda_graph: bool = True):
+                 use_cuda_graph: bool = True, overlap_masks: bool = True):
         super().__init__(model)
         self.num_iterations = num_iterations
         self.return_num = min(return_num, num_iterations)
@@ -71,11 +184,21 @@ class DropBlockEval(_MCBase):
         self.resize = resize
         self.iter_batch = iter_batch
         self.use_cuda_graph = use_cuda_graph
-        self._graphs = {}
+        self.overlap_masks = overlap_masks
+        self._runners = {}
 
     def set_mode(self, mode):
         self.mode = mode
         assert self.mode in ['save', 'evaluate']
+
+    def _runner(self, nb, h0, w0, dev, active, p, bs) -> MCRunner:
+        eng = self._model._get_engine(dev)              # re-packs weights if the parameters changed
+        key = (nb, h0, w0, str(dev), active, p, bs, self.return_num, id(eng))
+        r = self._runners.get(key)
+        if r is None:
+            r = MCRunner(self._model, nb, h0, w0, dev, active, p, bs, self.return_num, self.use_cuda_graph, self.overlap_masks)
+            self._runners[key] = r
+        return r
 
     # -------------------------------------------------------------------------------------------
     def mc_statistics(self, im: torch.Tensor, mask: torch.Tensor, num_iterations: Optional[int] = None):
@@ -91,56 +214,36 @@ class DropBlockEval(_MCBase):
         dist, rank, world = _dist()
         t0, t1 = shard_range(T, rank, world)
         dev = im.device
-        eng: UNetEngine = model._get_engine(dev)
         _, _, h0, w0 = im.shape
         npix = h0 * w0
-        acc = torch.zeros(2, h0, w0, dtype=torch.float64, device=dev)
         R = self.return_num
-        samples = torch.zeros(max(R, 1), h0, w0, dtype=torch.float32, device=dev)
-        fov = mask.reshape(h0, w0).to(torch.float32).contiguous()
-        iter_base = torch.full((1,), t0, dtype=torch.int64, device=dev)
         gen = _gen_for(dev)
         seed, stream_start = gen.initial_seed(), gen.get_offset()
-        x1 = im.detach().to(torch.float32).contiguous()
-
+        acc = None
+        samples = None
+        per_iter = 0
         done = t0
-        per_iter_offset = 0
         while done < t1:
             nb = min(self.iter_batch, t1 - done)
-            ws = eng.workspace(nb, h0, w0)
-            masks = model._mask_plan(eng, nb, 1, ws, p, bs) if active else None
-            if masks is not None:
-                per_iter_offset = masks.offset_per_call
-                masks.set_stream_position(stream_start + done * per_iter_offset)
-            xb = x1.expand(nb, -1, -1, -1).contiguous()
-            mc = {"acc": acc, "fov": fov, "samples": samples if R > 0 else None, "iter_base": iter_base, "return_num": R}
             steps = (t1 - done) // nb
-
-            def step():
-                if masks is not None:
-                    masks.generate(seed)
-                eng.forward(xb, ws, masks, head_out=False, mc=mc)
-                if masks is not None:
-                    masks.advance(nb)
-                call("b2u_advance_counter", ptr(iter_base), nb, stream_ptr())
-
-            if self.use_cuda_graph and steps >= 3:
-                step()                                   # warm-up (also sets kernel attributes) outside capture
-                torch.cuda.synchronize(dev)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    step()
-                # the capture itself does not execute; one eager step is done, replay the rest
-                for _ in range(steps - 1):
-                    g.replay()
-                self._last_graph = g
-            else:
-                for _ in range(steps):
-                    step()
+            r = self._runner(nb, h0, w0, dev, active, p, bs)
+            per_iter = r.per_iter
+            r.begin(im, mask, done, seed, stream_start)
+            r.run_steps(steps)
+            if acc is None:
+                acc, samples = r.acc, r.samples
+            else:                                      # remainder batch: fold into the first runner's buffers
+                acc += r.acc
+                samples += r.samples
             done += steps * nb
+        if acc is None:                                # this rank owns no iterations
+            acc = torch.zeros(2, h0, w0, dtype=torch.float64, device=dev)
+            samples = torch.zeros(max(R, 1), h0, w0, dtype=torch.float32, device=dev)
         if active:
             # leave the torch generator where T reference forwards would have left it
-            gen.set_offset(stream_start + T * per_iter_offset)
+            if per_iter == 0:
+                per_iter = self._runner(1, h0, w0, dev, active, p, bs).per_iter
+            gen.set_offset(stream_start + T * per_iter)
         if dist is not None and world > 1:
             dist.all_reduce(acc)                       # the ONE exchange step of the path (fp64 [2,H,W])
             if R > 0:
