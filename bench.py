@@ -62,16 +62,23 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summary over the samples that arrived inside [t_begin, t_end] (the timed region); the sampler is
+        started before the warm-up because nvidia-smi needs a few hundred ms to produce its first line."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for (ts, ln) in self.lines if t_begin is None or (t_begin <= ts <= t_end + 0.12)]
+        window = "timed region"
+        if not inside:
+            inside = [ln for (_, ln) in self.lines[-5:]]
+            window = "last samples before the end of the timed region (region shorter than the sampling period)"
+        for ln in inside:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -85,7 +92,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def dist_env():
@@ -166,6 +173,9 @@ def run_gpu(args):
     from unet_research_b200.smoke_test import build_canonical
 
     peaks = load_peaks()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     NB = args.iter_batch
     K, W = args.steps, args.warmup
     model, _ = build_canonical(dev, dropblock=True, compute="bf16")
@@ -187,21 +197,20 @@ def run_gpu(args):
 
     # ---- timed region: K steps (graph replays of two steps each), CUDA events on the launching stream,
     # barrier + sync on both sides.  Working set per step (~1 GB of activations x NB) far exceeds the 126 MB L2.
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
     e0.record()
     runner.run_steps(K)
     e1.record()
     torch.cuda.synchronize(dev)
+    t_end = time.perf_counter()
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -334,7 +343,7 @@ def time_conv_kernels(runner, dev, reps):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--iter-batch", type=int, default=5)

@@ -95,7 +95,12 @@ class MCRunner:
         self.iter_base = torch.zeros(1, dtype=torch.int64, device=device)
         self.mc = {"acc": self.acc, "fov": self.fov, "samples": self.samples if return_num > 0 else None,
                    "iter_base": self.iter_base, "return_num": return_num}
-        self.side = torch.cuda.Stream(device=device) if self.overlap else None
+        # The forward runs on a HIGH-priority stream and the mask build on a low-priority one: with equal
+        # priorities the block scheduler drains one grid before it starts the next, so nothing overlaps;
+        # with priorities the mask-build CTAs (no shared memory, 26 registers) fill the SM resources the
+        # shared-memory-bound conv CTAs leave idle.  Graph kernel nodes inherit the capture stream's priority.
+        self.main = torch.cuda.Stream(device=device, priority=-1)
+        self.side = torch.cuda.Stream(device=device, priority=0) if self.overlap else None
         self.graph = None
         self.launches_per_step = 0
         self.seed = 0
@@ -149,7 +154,15 @@ class MCRunner:
             self._generate(0, 2 if self.overlap else 1)           # prologue: masks of the first step
 
     def run_steps(self, steps: int):
-        """`steps` batched steps (= steps * nb iterations)."""
+        """`steps` batched steps (= steps * nb iterations), enqueued on the runner's high-priority stream and
+        ordered after / before the caller's current stream."""
+        cur = torch.cuda.current_stream(self.dev)
+        self.main.wait_stream(cur)
+        with torch.cuda.stream(self.main):
+            self._run_steps(steps)
+        cur.wait_stream(self.main)
+
+    def _run_steps(self, steps: int):
         pairs, odd = divmod(steps, 2)
         if pairs:
             if self.use_graph and self.graph is None and pairs >= 2:
@@ -159,7 +172,7 @@ class MCRunner:
                 pairs -= 1
                 torch.cuda.synchronize(self.dev)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, stream=self.main):
                     self._pair()
                 self.graph = g
             for _ in range(pairs):
