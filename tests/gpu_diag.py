@@ -18,7 +18,7 @@ import traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["info", "conv", "convt", "first", "gn", "pool", "head", "dropblock", "rotate", "forward", "mc", "rot_ens", "tf32"]
+SECTIONS = ["info", "conv", "convv1", "convv2", "convt", "first", "gn", "pool", "head", "dropblock", "rotate", "forward", "mc", "rot_ens", "tf32"]
 
 
 def rel(a, b):
@@ -36,7 +36,7 @@ def sec_info():
     print("torch", torch.__version__, "cuda", torch.version.cuda)
 
 
-def _conv_case(n, h, w, cin, cout, dtype, conv_t=False, block_n=0, stages=0):
+def _conv_case(n, h, w, cin, cout, dtype, conv_t=False, block_n=0, stages=0, version=0, mt=0):
     import torch
     import torch.nn.functional as F
     from unet_research_b200 import _lib
@@ -53,7 +53,7 @@ def _conv_case(n, h, w, cin, cout, dtype, conv_t=False, block_n=0, stages=0):
     G = 32
     d = ConvDesc()
     d.n, d.h, d.w, d.cin, d.cout, d.dtype, d.num_groups, d.x_cstride = n, h, w, cin, cout, dtype, G, cin
-    d.reserved[0], d.reserved[1] = block_n, stages
+    d.reserved[0], d.reserved[1], d.reserved[2], d.reserved[3] = block_n, stages, version, mt
     rows, sgs = C.c_int(0), C.c_int(0)
     call("b2u_convT2x2_stat_layout" if conv_t else "b2u_conv3x3_stat_layout", C.byref(d), C.byref(rows), C.byref(sgs))
     oh, ow = (2 * h, 2 * w) if conv_t else (h, w)
@@ -82,7 +82,7 @@ def _conv_case(n, h, w, cin, cout, dtype, conv_t=False, block_n=0, stages=0):
     s_ref = torch.stack([rs.sum(-1), (rs * rs).sum(-1)], -1)
     sr, _ = rel(ps, s_ref)
     nan = int(torch.isnan(got).sum())
-    print(f"  {'convT' if conv_t else 'conv3'} n{n} {h}x{w} {cin}->{cout} dt{dtype} bn{block_n} st{stages}: rel {r:.3e} max {mx:.3e} stats_rel {sr:.3e} nan {nan} rows {rows.value} sgs {sgs.value}")
+    print(f"  {'convT' if conv_t else 'conv3'} n{n} {h}x{w} {cin}->{cout} dt{dtype} bn{block_n} st{stages} v{version} mt{mt}: rel {r:.3e} max {mx:.3e} stats_rel {sr:.3e} nan {nan} rows {rows.value} sgs {sgs.value}")
     return {"rel": r, "stats_rel": sr, "nan": nan}
 
 
@@ -98,6 +98,72 @@ def sec_conv():
     _conv_case(1, 33, 47, 64, 128, _lib.BF16, block_n=64)
     _conv_case(1, 32, 32, 256, 256, _lib.BF16, block_n=128, stages=2)
     _conv_case(1, 592, 576, 64, 64, _lib.BF16)
+
+
+def sec_convv1():
+    from unet_research_b200 import _lib
+    _conv_case(2, 24, 40, 64, 64, _lib.BF16, version=1)
+    _conv_case(1, 37, 36, 128, 128, _lib.BF16, version=1)
+    _conv_case(1, 74, 72, 512, 512, _lib.BF16, version=1)
+    _conv_case(1, 33, 47, 64, 128, _lib.BF16, block_n=64, version=1)
+
+
+def sec_convv2():
+    from unet_research_b200 import _lib
+    for mt in (1, 2):
+        _conv_case(1, 16, 16, 64, 64, _lib.BF16, mt=mt)
+        _conv_case(3, 24, 40, 64, 64, _lib.BF16, mt=mt)
+        _conv_case(1, 37, 36, 128, 128, _lib.BF16, mt=mt)
+        _conv_case(2, 20, 24, 128, 256, _lib.BF16, mt=mt)
+        _conv_case(1, 33, 47, 128, 256, _lib.BF16, block_n=64, mt=mt)
+        _conv_case(1, 33, 47, 128, 256, _lib.BF16, block_n=128, mt=mt)
+    _conv_case(1, 74, 72, 512, 512, _lib.BF16)
+    _conv_case(5, 37, 36, 1024, 1024, _lib.BF16)
+    _conv_case(1, 592, 576, 64, 64, _lib.BF16)
+    _conv_case(2, 24, 40, 128, 256, _lib.F32, mt=2)
+
+
+def sec_convbench():
+    """Times every conv3x3 shape of the canonical U-Net at batch 5 for the v1 kernel and the v2 variants."""
+    import torch
+    from unet_research_b200 import _lib
+    from unet_research_b200._lib import ConvDesc, call, ptr, stream_ptr
+    dev = torch.device("cuda")
+    n = 5
+    shapes = [(592, 576, 64, 64), (592, 576, 128, 64), (296, 288, 64, 128), (296, 288, 128, 128), (296, 288, 256, 128),
+              (148, 144, 128, 256), (148, 144, 256, 256), (148, 144, 512, 256), (74, 72, 256, 512), (74, 72, 512, 512),
+              (74, 72, 1024, 512), (37, 36, 512, 1024), (37, 36, 1024, 1024)]
+    total = {}
+    for (h, w, cin, cout) in shapes:
+        x = torch.randn(n, h, w, cin, device=dev).to(torch.bfloat16)
+        wp = torch.randn(9, cout, cin, device=dev).to(torch.bfloat16)
+        y = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device=dev)
+        flop = 2.0 * n * h * w * cout * 9 * cin
+        line = f"  {h}x{w} {cin}->{cout}:"
+        variants = [("v1", 1, 0, 0)] + [(f"v2 bn{bn} mt{mt}", 0, bn, mt) for bn in (64, 128, 256) if cout % bn == 0 and bn <= cout for mt in (1, 2)]
+        best = None
+        for name, ver, bn, mt in variants:
+            d = ConvDesc()
+            d.n, d.h, d.w, d.cin, d.cout, d.dtype, d.num_groups, d.x_cstride = n, h, w, cin, cout, _lib.BF16, 32, cin
+            d.reserved[0], d.reserved[2], d.reserved[3] = bn, ver, mt
+            rows, sgs = C.c_int(0), C.c_int(0)
+            call("b2u_conv3x3_stat_layout", C.byref(d), C.byref(rows), C.byref(sgs))
+            parts = torch.empty(n, rows.value, cout // sgs.value, 2, dtype=torch.float32, device=dev)
+            for _ in range(2):
+                call("b2u_conv3x3_fwd", ptr(x), ptr(wp), ptr(y), ptr(parts), C.byref(d), stream_ptr())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                call("b2u_conv3x3_fwd", ptr(x), ptr(wp), ptr(y), ptr(parts), C.byref(d), stream_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            tf = flop / ms / 1e9
+            line += f"  {name} {ms * 1000:.0f}us {tf:.0f}TF"
+            if best is None or ms < best[1]:
+                best = (name, ms)
+            total[name] = total.get(name, 0.0) + ms
+        print(line + f"   best {best[0]}", flush=True)
 
 
 def sec_convt():

@@ -182,6 +182,17 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// Same, with an explicit stride between 8-row groups (shifted views of a halo patch use 10 rows = 1280 B) and a
+// start address that only needs 128 B (one row) alignment: the swizzle is a function of the absolute address.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor: fp32 accumulate, A/B both K-major, format 1 = bf16 (kind::f16) or 2 = tf32.
 __host__ __device__ constexpr uint32_t umma_idesc(int m, int n, int ab_format) {
   return (1u << 4) | (static_cast<uint32_t>(ab_format) << 7) | (static_cast<uint32_t>(ab_format) << 10) |

@@ -1,0 +1,402 @@
+// conv3x3 v2: persistent, halo-patch-reuse implicit GEMM (sm_100a, tcgen05 + TMEM + TMA).
+//
+// v1 (conv_gemm.cu) re-fetches a 16 KB activation tile for each of the 9 filter taps: the shallow layers are
+// L2->SM bandwidth bound (profiles/r01_conv_ncu.md).  v2 changes three things:
+//
+//  1. HALO PATCH REUSE.  A pixel tile is 8 wide x 16 tall.  Per 64-channel chunk ONE TMA box {128 B, 10, 18}
+//     brings the (16+2) x (8+2) input patch into shared memory (180 rows x 128 B, 128B swizzle; TMA zero fill =
+//     conv padding).  The 9 taps are 9 UMMA descriptors over that patch: start address + (r*10 + s) rows,
+//     8-row-group stride (SBO) = 10 rows = 1280 B.  A K-major SWIZZLE_128B descriptor may start at any 128 B
+//     row because the swizzle is a function of the absolute shared-memory address (hardware experiment
+//     tests/exp_umma_shift.cu, profiles/r01_exp_umma_shift.log).  Activation traffic drops from 9x to 1.41x.
+//  2. WEIGHT-STAGE SHARING.  A work item is MT (1 or 2) pixel tiles x BLOCK_N channels: each (tap, chunk)
+//     weight stage feeds MT accumulators, halving weight traffic per FLOP for MT = 2.
+//  3. PERSISTENT CTAs, double-buffered TMEM.  grid = min(items, SMs * resident CTAs); a CTA loops over items
+//     (n-tile-major order, so concurrently running CTAs share weight tiles in L2); when 2*MT*BLOCK_N <= 512
+//     columns the epilogue of item j overlaps the main loop of item j+1.
+//
+// Warp roles (224 threads): warp 0 = activation-patch TMA producer, warp 6 = weight TMA producer,
+// warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue (TMEM -> GroupNorm partials -> bf16/fp32 -> global).
+#include "b2u_common.cuh"
+#include "conv_host.cuh"
+
+namespace b2u {
+
+struct ConvV2Params {
+  int n, h, w;                // image grid
+  int tiles_w, tiles_h;       // 8 x 16 tiles per image
+  int total_tiles;            // n * tiles_w * tiles_h
+  int num_mgroups;            // ceil(total_tiles / MT)
+  int num_items;              // num_mgroups * n_tiles
+  int kc_chunks;              // Cin / (128 B of channels)
+  int cout;
+  int sa, sb;                 // pipeline depths of the patch ring and the weight ring
+  int sgs_log2;               // statistics sub-group size (log2), -1 = none
+  void* y;
+  float* partials;            // [n][tiles_per_image][cout/sgs][2]
+};
+
+constexpr int kPatchRows = 180;                      // (16 + 2) * (8 + 2)
+constexpr int kPatchBytes = kPatchRows * 128;        // 23040
+constexpr int kPatchStride = 23552;                  // rounded up to the 1024 B swizzle-atom alignment
+constexpr int kV2Threads = 224;
+
+template <int NV>
+__device__ __forceinline__ void v2_epilogue_stats(const float (&x)[32], bool valid, int lane, float* scratch) {
+  constexpr int NSG = NV / 2;
+  constexpr int SGS = 32 / NSG;
+  float v[NV];
+#pragma unroll
+  for (int j = 0; j < NSG; ++j) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < SGS; ++i) {
+      float t = x[j * SGS + i];
+      s += t;
+      q += t * t;
+    }
+    v[2 * j] = valid ? s : 0.f;
+    v[2 * j + 1] = valid ? q : 0.f;
+  }
+  warp_transpose_reduce<NV>(v, lane);
+  constexpr int LPV = 32 / NV;
+  if (lane % LPV == 0) scratch[lane / LPV] = v[0];
+}
+
+template <int BLOCK_N, int MT, bool kTf32>
+__global__ void __launch_bounds__(kV2Threads, 1)
+conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvV2Params p) {
+  using OutT = typename std::conditional<kTf32, float, __nv_bfloat16>::type;
+  constexpr int kBBytes = BLOCK_N * 128;
+  constexpr int kKElems = kTf32 ? 32 : 64;
+  constexpr int kUmmaK = kTf32 ? 8 : 16;
+  constexpr uint32_t kIdesc = umma_idesc(128, BLOCK_N, kTf32 ? 2 : 1);
+  constexpr int kAccCols = MT * BLOCK_N;                       // TMEM columns of one accumulator buffer
+  constexpr int kNumBuf = (2 * kAccCols <= 512) ? 2 : 1;
+  constexpr int kTmemCols = (kNumBuf * kAccCols <= 64) ? 64 : (kNumBuf * kAccCols <= 128) ? 128 : (kNumBuf * kAccCols <= 256) ? 256 : 512;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int SA = p.sa, SB = p.sb;
+  uint8_t* smA = smem;                                         // [SA][MT][kPatchStride]
+  uint8_t* smB = smem + SA * MT * kPatchStride;                // [SB][kBBytes]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smB + SB * kBBytes);
+  uint64_t* a_empty = a_full + SA;
+  uint64_t* b_full = a_empty + SA;
+  uint64_t* b_empty = b_full + SB;
+  uint64_t* t_full = b_empty + SB;                             // [2]
+  uint64_t* t_empty = t_full + 2;                              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  float* stat_scratch = reinterpret_cast<float*>(tmem_slot + 2);   // [4 warps][128]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_per_image = p.tiles_w * p.tiles_h;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // All three single-thread role loops below keep (stage, phase) pairs that advance by compare-and-wrap:
+  // no runtime division / modulo on the issue path (a single thread issues every TMA / MMA of the CTA, so
+  // its instruction count per filter tap bounds the tensor pipe at small BLOCK_N).
+  if (warp == 0) {
+    // ===================== activation-patch producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;                                          // first pass over a fresh barrier: wait(1) returns
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int mg = item % p.num_mgroups;
+        int cw[MT], ch[MT], cn[MT];
+#pragma unroll
+        for (int t = 0; t < MT; ++t) {
+          const int tile = mg * MT + t;                        // tiles past the end are fully out of bounds -> zeros
+          const int img = tile / tiles_per_image;
+          const int r = tile - img * tiles_per_image;
+          const int ty = r / p.tiles_w;
+          cn[t] = img;
+          ch[t] = ty * 16 - 1;
+          cw[t] = (r - ty * p.tiles_w) * 8 - 1;
+        }
+        for (int kc = 0; kc < p.kc_chunks; ++kc) {
+          mbar_wait(&a_empty[s], ph);
+          mbar_arrive_expect_tx(&a_full[s], MT * kPatchBytes);
+#pragma unroll
+          for (int t = 0; t < MT; ++t)
+            tma_load_4d(smA + (s * MT + t) * kPatchStride, &tmA, &a_full[s], kc * kKElems, cw[t], ch[t], cn[t]);
+          if (++s == SA) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int n0 = (item / p.num_mgroups) * BLOCK_N;
+        for (int kc = 0; kc < p.kc_chunks; ++kc) {
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[s], ph);
+            mbar_arrive_expect_tx(&b_full[s], kBBytes);
+            tma_load_3d(smB + s * kBBytes, &tmB, &b_full[s], kc * kKElems, n0, tap);
+            if (++s == SB) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int sa = 0, sb = 0, buf = 0;
+      uint32_t pa = 0, pb = 0, pt = 1;                           // pt: parity to wait on t_empty[buf]
+      const uint64_t adesc0 = umma_desc_k_sw128_sbo(smem_u32(smA), 1280);
+      const uint64_t bdesc0 = umma_desc_k_sw128(smem_u32(smB));
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        mbar_wait(&t_empty[buf], pt);                            // epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + buf * kAccCols;
+        for (int kc = 0; kc < p.kc_chunks; ++kc) {
+          mbar_wait(&a_full[sa], pa);
+          const uint64_t adesc_stage = adesc0 + static_cast<uint64_t>((sa * MT * kPatchStride) >> 4);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((sb * kBBytes) >> 4);
+            constexpr int kRowsPerGroup = 10;
+            const int row_off = (tap / 3) * kRowsPerGroup + (tap % 3);     // compile-time: shifted view of the patch
+#pragma unroll
+            for (int t = 0; t < MT; ++t) {
+              const uint64_t adesc = adesc_stage + static_cast<uint64_t>((t * kPatchStride + row_off * 128) >> 4);
+#pragma unroll
+              for (int k = 0; k < kKElems / kUmmaK; ++k) {
+                const uint32_t accumulate = (tap == 0 && k == 0) ? (kc != 0 ? 1u : 0u) : 1u;
+                umma_ss<kTf32>(acc0 + t * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, kIdesc, accumulate);
+              }
+            }
+            umma_commit(&b_empty[sb]);
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+          umma_commit(&a_empty[sa]);
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+        }
+        umma_commit(&t_full[buf]);
+        if (++buf == kNumBuf) { buf = 0; pt ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int dh = row >> 3, dw = row & 7;
+    float* my_scratch = stat_scratch + q * 128;
+    const int et = threadIdx.x - 64;                             // 0..127
+    int buf = 0;
+    uint32_t pf = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const int n0 = (item / p.num_mgroups) * BLOCK_N;
+      const int mg = item % p.num_mgroups;
+      mbar_wait(&t_full[buf], pf);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < MT; ++t) {
+        const int tile = mg * MT + t;
+        const bool tile_ok = tile < p.total_tiles;
+        const int img = tile / tiles_per_image;
+        const int r = tile - img * tiles_per_image;
+        const int ty = r / p.tiles_w, tx = r - ty * p.tiles_w;
+        const int hh = ty * 16 + dh, ww = tx * 8 + dw;
+        const bool valid = tile_ok && hh < p.h && ww < p.w;
+        OutT* yrow = reinterpret_cast<OutT*>(p.y) + ((static_cast<size_t>(img) * p.h + hh) * p.w + ww) * p.cout + n0;
+#pragma unroll 1
+        for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+          uint32_t rr[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccCols + t * BLOCK_N + chunk * 32, rr);
+          tmem_ld_wait();
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(rr[i]);
+          if (p.sgs_log2 >= 0) {
+            switch (p.sgs_log2) {
+              case 1: v2_epilogue_stats<32>(x, valid, lane, my_scratch + chunk * 32); break;
+              case 2: v2_epilogue_stats<16>(x, valid, lane, my_scratch + chunk * 16); break;
+              case 3: v2_epilogue_stats<8>(x, valid, lane, my_scratch + chunk * 8); break;
+              case 4: v2_epilogue_stats<4>(x, valid, lane, my_scratch + chunk * 4); break;
+              default: v2_epilogue_stats<2>(x, valid, lane, my_scratch + chunk * 2); break;
+            }
+          }
+          if (valid) {
+            if constexpr (kTf32) {
+              float4* dst = reinterpret_cast<float4*>(yrow + chunk * 32);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) dst[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(yrow + chunk * 32);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 a = __floats2bfloat162_rn(x[8 * i], x[8 * i + 1]);
+                __nv_bfloat162 b = __floats2bfloat162_rn(x[8 * i + 2], x[8 * i + 3]);
+                __nv_bfloat162 c = __floats2bfloat162_rn(x[8 * i + 4], x[8 * i + 5]);
+                __nv_bfloat162 d = __floats2bfloat162_rn(x[8 * i + 6], x[8 * i + 7]);
+                uint4 v;
+                v.x = *reinterpret_cast<uint32_t*>(&a);
+                v.y = *reinterpret_cast<uint32_t*>(&b);
+                v.z = *reinterpret_cast<uint32_t*>(&c);
+                v.w = *reinterpret_cast<uint32_t*>(&d);
+                dst[i] = v;
+              }
+            }
+          }
+        }
+        if (p.sgs_log2 >= 0) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");           // all four quarter-tile partials are in smem
+          const int nslots = (BLOCK_N * 2) >> p.sgs_log2;
+          if (et < nslots && tile_ok) {
+            const float s = stat_scratch[et] + stat_scratch[128 + et] + stat_scratch[256 + et] + stat_scratch[384 + et];
+            const int slots_per_row = (p.cout * 2) >> p.sgs_log2;
+            p.partials[(static_cast<size_t>(img) * tiles_per_image + r) * slots_per_row + ((n0 * 2) >> p.sgs_log2) + et] = s;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");           // scratch may be overwritten by the next tile
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[buf]);
+      if (++buf == kNumBuf) { buf = 0; pf ^= 1; }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+struct V2Plan {
+  int block_n, mt, sa, sb, tiles_w, tiles_h, sgs;
+  size_t smem;
+};
+
+static int v2_make_plan(const b2u_conv_desc* d, V2Plan* pl) {
+  pl->tiles_w = (d->w + 7) / 8;
+  pl->tiles_h = (d->h + 15) / 16;
+  int bn = d->cout % 256 == 0 ? 256 : (d->cout % 128 == 0 ? 128 : 64);
+  if (d->reserved[0] == 64 || d->reserved[0] == 128 || d->reserved[0] == 256) {
+    B2U_REQUIRE(d->cout % d->reserved[0] == 0, "BLOCK_N override %d does not divide cout", d->reserved[0]);
+    bn = d->reserved[0];
+  }
+  // measured on B200 (tests/gpu_diag.py convbench): BLOCK_N 256 wants the double-buffered accumulator (MT 1),
+  // narrower tiles want the shared weight stage (MT 2)
+  int mt = bn == 256 ? 1 : 2;
+  if (d->reserved[3] == 1 || d->reserved[3] == 2) mt = d->reserved[3];
+  pl->block_n = bn;
+  pl->mt = mt;
+  // pipeline depths: fill ~200 KB; the weight ring gets at least 3 stages, the patch ring at least 2
+  const size_t budget = 222 * 1024 - 4096;
+  int sa = 2, sb = 3;
+  auto bytes = [&](int a, int b) { return static_cast<size_t>(a) * mt * kPatchStride + static_cast<size_t>(b) * bn * 128; };
+  while (bytes(sa, sb + 1) <= budget && sb < 6) ++sb;
+  while (bytes(sa + 1, sb) <= budget && sa < 3) ++sa;
+  while (bytes(sa, sb + 1) <= budget && sb < 9) ++sb;
+  if (d->reserved[1] >= 2 && d->reserved[1] <= 12) sb = d->reserved[1];
+  B2U_REQUIRE(bytes(sa, sb) <= budget, "conv3x3 v2: pipeline does not fit shared memory (BLOCK_N %d MT %d)", bn, mt);
+  pl->sa = sa;
+  pl->sb = sb;
+  pl->smem = bytes(sa, sb) + 1024 + (2 * sa + 2 * sb + 4) * 8 + 16 + 4 * 128 * 4;
+  pl->sgs = conv_stat_subgroup(d->cout, d->num_groups);
+  return B2U_OK;
+}
+
+template <int BN, int MT, bool TF>
+static int v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Params& gp, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2U_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_v2_kernel<BN, MT, TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv3x3_v2_kernel<BN, MT, TF><<<grid, kV2Threads, smem, st>>>(ta, tb, gp);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+int conv3x3_v2_stat_layout(const b2u_conv_desc* d, int* rows_per_image, int* subgroup_size) {
+  int rc = conv_validate_desc(d);
+  if (rc) return rc;
+  V2Plan pl;
+  rc = v2_make_plan(d, &pl);
+  if (rc) return rc;
+  if (rows_per_image) *rows_per_image = pl.tiles_w * pl.tiles_h;
+  if (subgroup_size) *subgroup_size = pl.sgs;
+  return B2U_OK;
+}
+
+int conv3x3_v2_run(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d, void* stream) {
+  int rc = conv_validate_desc(d);
+  if (rc) return rc;
+  V2Plan pl;
+  rc = v2_make_plan(d, &pl);
+  if (rc) return rc;
+  B2U_REQUIRE(x && wpacked && y, "null tensor pointer");
+  B2U_REQUIRE(d->num_groups == 0 || partials != nullptr, "partials required when num_groups > 0");
+  const int es = d->dtype == B2U_F32 ? 4 : 2;
+  const int ke = 128 / es;
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->x_cstride), static_cast<cuuint64_t>(d->w), static_cast<cuuint64_t>(d->h),
+                          static_cast<cuuint64_t>(d->n)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(d->x_cstride) * es, static_cast<cuuint64_t>(d->w) * d->x_cstride * es,
+                             static_cast<cuuint64_t>(d->h) * d->w * d->x_cstride * es};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(ke), 10, 18, 1};
+    rc = conv_encode_map(&ta, d->dtype, 4, x, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(d->cin), static_cast<cuuint64_t>(d->cout), 9};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(d->cin) * es, static_cast<cuuint64_t>(d->cout) * d->cin * es};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(ke), static_cast<cuuint32_t>(pl.block_n), 1};
+    rc = conv_encode_map(&tb, d->dtype, 3, wpacked, dims, strides, box);
+    if (rc) return rc;
+  }
+  ConvV2Params gp;
+  gp.n = d->n; gp.h = d->h; gp.w = d->w;
+  gp.tiles_w = pl.tiles_w; gp.tiles_h = pl.tiles_h;
+  gp.total_tiles = d->n * pl.tiles_w * pl.tiles_h;
+  gp.num_mgroups = (gp.total_tiles + pl.mt - 1) / pl.mt;
+  gp.num_items = gp.num_mgroups * (d->cout / pl.block_n);
+  gp.kc_chunks = d->cin / ke;
+  gp.cout = d->cout;
+  gp.sa = pl.sa; gp.sb = pl.sb;
+  gp.sgs_log2 = pl.sgs > 0 ? conv_ilog2(pl.sgs) : -1;
+  gp.y = y;
+  gp.partials = partials;
+  int grid = b2u_num_sms();
+  if (grid > gp.num_items) grid = gp.num_items;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool tf = d->dtype == B2U_F32;
+#define B2U_V2_CASE(BN, MTV)                                                                                        \
+  if (pl.block_n == BN && pl.mt == MTV)                                                                              \
+    return tf ? v2_launch<BN, MTV, true>(ta, tb, gp, grid, pl.smem, st) : v2_launch<BN, MTV, false>(ta, tb, gp, grid, pl.smem, st);
+  B2U_V2_CASE(64, 1) B2U_V2_CASE(64, 2) B2U_V2_CASE(128, 1) B2U_V2_CASE(128, 2) B2U_V2_CASE(256, 1) B2U_V2_CASE(256, 2)
+#undef B2U_V2_CASE
+  b2u_set_error("conv3x3 v2: no kernel for BLOCK_N %d MT %d", pl.block_n, pl.mt);
+  return B2U_ERR_UNSUPPORTED;
+}
+
+}  // namespace b2u

@@ -15,6 +15,7 @@
 // One output tile per CTA; several CTAs co-reside per SM (shared memory permitting) so one CTA's
 // epilogue overlaps another's main loop.
 #include "b2u_common.cuh"
+#include "conv_host.cuh"
 
 #include <mutex>
 
@@ -124,7 +125,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int kb = 0;
+      int s = 0;
+      uint32_t ph = 1;
       for (int tap = 0; tap < p.taps; ++tap) {
         int dy = 0, dx = 0, btap = tap_fixed;
         if (p.mode == 0) {
@@ -132,32 +134,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           dx = tap % 3 - 1;
           btap = tap;
         }
-        for (int kc = 0; kc < p.kc_per_tap; ++kc, ++kb) {
-          const int s = kb % stages;
-          const uint32_t ph = (kb / stages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
+        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          mbar_wait(&empty_bar[s], ph);
           mbar_arrive_expect_tx(&full_bar[s], kABytes + kBBytes);
           tma_load_4d(smA + s * kABytes, &tmA, &full_bar[s], kc * kKElems, w0 + dx, h0 + dy, img);
           tma_load_3d(smB + s * kBBytes, &tmB, &full_bar[s], kc * kKElems, n0, btap);
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint64_t adesc0 = umma_desc_k_sw128(smem_u32(smA));
+      const uint64_t bdesc0 = umma_desc_k_sw128(smem_u32(smB));
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint64_t adesc = umma_desc_k_sw128(smem_u32(smA + s * kABytes));
-        const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smB + s * kBBytes));
+        const uint64_t adesc = adesc0 + static_cast<uint64_t>((s * kABytes) >> 4);
+        const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((s * kBBytes) >> 4);
 #pragma unroll
         for (int k = 0; k < kKElems / kUmmaK; ++k) {
           // +32 bytes of K inside the 128-byte swizzle atom = +2 in the 16-byte address field
           umma_ss<kTf32>(tmem_base, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);           // frees the smem stage once these MMAs retire
+        if (++s == stages) { s = 0; ph ^= 1; }
       }
       umma_commit(tmem_full_bar);             // accumulator complete
     }
@@ -261,8 +265,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int encode_map(CUtensorMap* map, int dtype, int rank, const void* base, const cuuint64_t* dims,
-                      const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+int conv_encode_map(CUtensorMap* map, int dtype, int rank, const void* base, const cuuint64_t* dims,
+                    const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     b2u_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -279,7 +283,7 @@ static int encode_map(CUtensorMap* map, int dtype, int rank, const void* base, c
   return B2U_OK;
 }
 
-static int ilog2(int v) {
+int conv_ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
   return l;
@@ -300,7 +304,7 @@ static void choose_box(int h, int w, int* bw_out, int* bh_out) {
   }
 }
 
-static int stat_subgroup(int cout, int num_groups) {
+int conv_stat_subgroup(int cout, int num_groups) {
   if (num_groups <= 0) return 0;
   int gsize = cout / num_groups;
   return gsize < 32 ? gsize : 32;
@@ -311,7 +315,7 @@ struct Plan {
   size_t smem;
 };
 
-static int make_plan(const b2u_conv_desc* d, bool conv_t, Plan* pl) {
+int conv_validate_desc(const b2u_conv_desc* d) {
   B2U_REQUIRE(d != nullptr, "null descriptor");
   B2U_REQUIRE(d->dtype == B2U_BF16 || d->dtype == B2U_F32, "dtype must be B2U_BF16 or B2U_F32");
   const int ke = d->dtype == B2U_F32 ? 32 : 64;
@@ -325,6 +329,12 @@ static int make_plan(const b2u_conv_desc* d, bool conv_t, Plan* pl) {
     int gs = d->cout / d->num_groups;
     B2U_REQUIRE(gs >= 2 && (gs & (gs - 1)) == 0, "group size %d must be a power of two >= 2", gs);
   }
+  return B2U_OK;
+}
+
+static int make_plan(const b2u_conv_desc* d, bool conv_t, Plan* pl) {
+  int vrc = conv_validate_desc(d);
+  if (vrc) return vrc;
   choose_box(d->h, d->w, &pl->bw, &pl->bh);
   pl->tiles_w = (d->w + pl->bw - 1) / pl->bw;
   pl->tiles_h = (d->h + pl->bh - 1) / pl->bh;
@@ -340,7 +350,7 @@ static int make_plan(const b2u_conv_desc* d, bool conv_t, Plan* pl) {
   while (stages > 2 && static_cast<size_t>(stages) * stage_bytes + 4096 > 227 * 1024) --stages;
   pl->stages = stages;
   pl->smem = static_cast<size_t>(stages) * stage_bytes + 1024 /*align*/ + (2 * stages + 1) * 8 + 16 + 4 * 128 * 4;
-  pl->sgs = stat_subgroup(d->cout, d->num_groups);
+  pl->sgs = conv_stat_subgroup(d->cout, d->num_groups);
   (void)conv_t;
   return B2U_OK;
 }
@@ -378,7 +388,7 @@ static int run_gemm(const void* x, const void* wpacked, void* y, float* partials
                              static_cast<cuuint64_t>(d->w) * d->x_cstride * es,
                              static_cast<cuuint64_t>(d->h) * d->w * d->x_cstride * es};
     cuuint32_t box[4] = {static_cast<cuuint32_t>(ke), static_cast<cuuint32_t>(pl.bw), static_cast<cuuint32_t>(pl.bh), 1};
-    rc = encode_map(&ta, d->dtype, 4, x, dims, strides, box);
+    rc = conv_encode_map(&ta, d->dtype, 4, x, dims, strides, box);
     if (rc) return rc;
   }
   {
@@ -386,14 +396,14 @@ static int run_gemm(const void* x, const void* wpacked, void* y, float* partials
                           static_cast<cuuint64_t>(taps_w)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(d->cin) * es, static_cast<cuuint64_t>(d->cout) * d->cin * es};
     cuuint32_t box[3] = {static_cast<cuuint32_t>(ke), static_cast<cuuint32_t>(pl.block_n), 1};
-    rc = encode_map(&tb, d->dtype, 3, wpacked, dims, strides, box);
+    rc = conv_encode_map(&tb, d->dtype, 3, wpacked, dims, strides, box);
     if (rc) return rc;
   }
 
   GemmParams gp;
   gp.n = d->n; gp.h = d->h; gp.w = d->w;
   gp.tiles_w = pl.tiles_w; gp.tiles_h = pl.tiles_h;
-  gp.bw_log2 = ilog2(pl.bw); gp.bh = pl.bh;
+  gp.bw_log2 = conv_ilog2(pl.bw); gp.bh = pl.bh;
   gp.taps = conv_t ? 1 : 9;
   gp.kc_per_tap = d->cin / ke;
   gp.cout = d->cout;
@@ -402,7 +412,7 @@ static int run_gemm(const void* x, const void* wpacked, void* y, float* partials
   gp.out_h = conv_t ? 2 * d->h : d->h;
   gp.out_w = conv_t ? 2 * d->w : d->w;
   gp.stages = pl.stages;
-  gp.sgs_log2 = pl.sgs > 0 ? ilog2(pl.sgs) : -1;
+  gp.sgs_log2 = pl.sgs > 0 ? conv_ilog2(pl.sgs) : -1;
   gp.rows_per_image = pl.tiles_w * pl.tiles_h * (conv_t ? 4 : 1);
   gp.y = y;
   gp.partials = partials;
@@ -447,7 +457,11 @@ __global__ void pack_convT_kernel(const float* __restrict__ w, T* __restrict__ o
 
 using namespace b2u;
 
+// reserved[2] == 1 selects the v1 kernel (one 16x8 tile per CTA, per-tap activation reload); default is v2.
+static bool use_v1(const b2u_conv_desc* d) { return d != nullptr && d->reserved[2] == 1; }
+
 extern "C" int b2u_conv3x3_stat_layout(const b2u_conv_desc* d, int* rows_per_image, int* subgroup_size) {
+  if (!use_v1(d)) return conv3x3_v2_stat_layout(d, rows_per_image, subgroup_size);
   Plan pl;
   int rc = make_plan(d, false, &pl);
   if (rc) return rc;
@@ -465,6 +479,7 @@ extern "C" int b2u_convT2x2_stat_layout(const b2u_conv_desc* d, int* rows_per_im
 }
 extern "C" int b2u_conv3x3_fwd(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d,
                                void* stream) {
+  if (!use_v1(d)) return conv3x3_v2_run(x, wpacked, y, partials, d, stream);
   return run_gemm(x, wpacked, y, partials, d, false, stream);
 }
 extern "C" int b2u_convT2x2_fwd(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d,
