@@ -88,11 +88,12 @@ int b2u_conv_first_fwd(const float* x_nchw, const float* wgt /*[cout,cin,3,3] fp
  *   a = gamma * rstd * s,  b = (beta - mean * gamma * rstd) * s
  * where s = numel_per_call / keep_count is the DropBlock rescale of the site that follows the norm
  * (utils_modules.py:64; s > 0 so relu(s*z) = s*relu(z)); keep_counts == NULL means s = 1.
- * coef: float2[n][c].  count = elements per (image, group) = (c/num_groups) * H * W. */
+ * coef: float2[n][c].  count = elements per (image, group) = (c/num_groups) * H * W.
+ * mean_rstd (optional, training): float2[n][num_groups] (mean, rstd) kept for the backward pass. */
 int b2u_gn_finalize(const float* partials, int rows_per_image, int subgroup_size, const float* gamma,
                     const float* beta, float* coef, int n, int c, int num_groups, double count, float eps,
                     const unsigned long long* keep_counts, int images_per_call, double numel_per_call,
-                    void* stream);
+                    float* mean_rstd, void* stream);
 
 /* Fused normalise-affine [+ DropBlock mask] [+ ReLU] [+ second mask and rescale]: the elementwise tail
  * of a conv unit (GroupNorm -> DropBlock -> ReLU, utils_unet.py:177-182) and, with mask2, the DropBlock
@@ -180,6 +181,67 @@ int b2u_dropblock_dilate(const b2u_dropblock_call* table, int n_calls, const b2u
 /* centre bitmap from caller-supplied uniforms (parity mode: feed the oracle's captured torch.rand values) */
 int b2u_dropblock_centers_from_uniform(const float* u, uint32_t* center_bits, long long numel, float gamma,
                                        void* stream);
+
+/* ------------------------------------------------------------------ backward pass (training step,
+ * utils_training.py:21-39: loss.backward() through UNet.forward).
+ *
+ * Elementwise backward of one unit (GroupNorm -> DropBlock -> ReLU, utils_unet.py:177-182), two passes over the
+ * same inputs plus a finalize; the upstream gradient is the sum of up to three sources that are never materialised:
+ *   grad_a   : dense NHWC tensor (channel window [a_coffset, a_coffset+c) of a tensor with a_cstride channels),
+ *              optionally times the concat-site keep mask / rescale (backward of dropblock(cat([up, skip])), :382-383);
+ *   grad_pool: pooled-resolution gradient routed through the stored max-pool argmax (nn.MaxPool2d, :265-266);
+ *   grad_out : head mode, dlogit * w_head with dlogit = grad_out * out * (1 - out) inside h0 x w0
+ *              (Conv2d 1x1 + Sigmoid + crop, :397-404,440).
+ * pass 1 writes partials float[n][rows][c][3] = (sum dZ, sum dZ*xhat, sum dlogit*act); finalize reduces them to
+ * dgamma / dbeta / dw_head and to the per-(image, group) GroupNorm-backward coefficients float2[n][G];
+ * pass 2 writes dY (gradient w.r.t. the raw conv output), NHWC or space-to-depth [n,h/2,w/2,4,c]. */
+typedef struct {
+  int32_t n, h, w, c, dtype, relu, num_groups, s2d;
+  int32_t images_per_call1, a_cstride, a_coffset, mask2_cstride, mask2_coffset, images_per_call2, h0, w0;
+  double numel_per_call1, numel_per_call2;
+  const void* y;                         /* raw conv output of the unit [n,h,w,c]                              */
+  const float* coef;                     /* float2[n][c] from b2u_gn_finalize                                  */
+  const float* mean_rstd;                /* float2[n][G]                                                       */
+  const float* gamma;                    /* [c]                                                                */
+  const uint32_t* mask1;                 /* own-site keep mask or NULL                                         */
+  const unsigned long long* keep_counts1;
+  const void* grad_a;
+  const uint32_t* mask2;
+  const unsigned long long* keep_counts2;
+  const void* grad_pool;                 /* [n,h/2,w/2,c]                                                      */
+  const uint8_t* argmax;                 /* [n,h/2,w/2,c]                                                      */
+  const float* grad_out;                 /* [n,1,h0,w0]                                                        */
+  const float* out;                      /* [n,1,h0,w0]                                                        */
+  const float* w_head;                   /* [c]                                                                */
+} b2u_unit_bwd_desc;
+int b2u_unit_bwd_rows(int h, int w, int c, int* rows_per_image);
+int b2u_unit_bwd_stats(const b2u_unit_bwd_desc* d, float* partials, void* stream);
+int b2u_unit_bwd_finalize(const float* partials, int n, int rows_per_image, int c, int num_groups, const float* gamma,
+                          double count, float* group_coef, float* dgamma, float* dbeta, float* dw_head, void* stream);
+int b2u_unit_bwd_apply(const b2u_unit_bwd_desc* d, const float* group_coef, void* dy, void* stream);
+
+/* Weight gradients as tcgen05 GEMMs with K = pixels (both operands MN-major, straight from the NHWC tensors):
+ *   conv3x3 (taps = 9): dW[co][ci][r][s] = sum_p g[p][co] * x[p + (r-1, s-1)][ci]   (nn.Conv2d backward)
+ *   1x1     (taps = 1): dW[cg][cx]       = sum_p g[p][cg] * x[p][cx]                (transposed conv, with g in the
+ *                                                                                    space-to-depth layout)
+ * g: [n,h,w,cg] gradient w.r.t. the raw conv output, x: [n,h,w,x_cstride] the conv's input.  Split-K partial sums go to
+ * `workspace` (float[slices][taps][cg][cx], size from b2u_wgrad_workspace_floats) and are reduced in a fixed order into
+ * dw with the PyTorch layout selected by `layout`: 0 = Conv2d [cg][cx][3][3], 1 = ConvTranspose2d [cx][cg/4][2][2]
+ * (cg = 4 * Cout, tap-major). */
+typedef struct {
+  int32_t n, h, w, cg, cx, x_cstride, taps, layout, dtype;
+  int32_t reserved[3];
+} b2u_wgrad_desc;
+int b2u_wgrad_workspace_floats(const b2u_wgrad_desc* d, long long* floats);
+int b2u_wgrad(const void* g, const void* x, float* workspace, float* dw, const b2u_wgrad_desc* d, void* stream);
+/* first layer (Cin 1 or 3): dW[co][ci][3][3] = sum_p g[p][co] * x_nchw[p + tap][ci], direct kernel on the fp32 input */
+int b2u_wgrad_first(const void* g, const float* x_nchw, float* workspace, float* dw, int n, int cin, int h0, int w0, int h,
+                    int w, int cout, int dtype, void* stream);
+/* plain 1x1 GEMM y[p][co] = sum_k x[p][k] * w[co][k] on the tcgen05 path (data gradient of the transposed conv:
+ * x = dY in space-to-depth layout with k = 4*Cout, w packed [1][cin][4*Cout]) */
+int b2u_gemm1x1_fwd(const void* x, const void* wpacked, void* y, const b2u_conv_desc* d, void* stream);
+/* nn.ConvTranspose2d weight [Cin,Cout,2,2] fp32 -> [1][Cin][4*Cout] (k = tap*Cout + co) for b2u_gemm1x1_fwd */
+int b2u_pack_convT2x2_dgrad_weight(const float* w, void* packed, int cin, int cout, int dtype, void* stream);
 
 /* ------------------------------------------------------------------ rotation (torchvision TF.rotate, BILINEAR,
  * fill 0, as called at Rotational_Uncertainty.py:54,58): affine grid in fp32, grid_sample(bilinear, zeros,

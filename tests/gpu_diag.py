@@ -18,7 +18,7 @@ import traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["info", "conv", "convv1", "convv2", "convt", "first", "gn", "pool", "head", "dropblock", "rotate", "forward", "mc", "rot_ens", "tf32"]
+SECTIONS = ["info", "conv", "convv1", "convv2", "wgrad", "bwdk", "convt", "first", "gn", "pool", "head", "dropblock", "rotate", "forward", "mc", "rot_ens", "tf32"]
 
 
 def rel(a, b):
@@ -166,6 +166,198 @@ def sec_convbench():
         print(line + f"   best {best[0]}", flush=True)
 
 
+def _wgrad_case(n, h, w, cg, cx, taps, layout=0, x_cstride=None):
+    import torch
+    import torch.nn.functional as F
+    from unet_research_b200 import _lib
+    from unet_research_b200._lib import WgradDesc, call, ptr, stream_ptr
+    dev = torch.device("cuda")
+    xs = x_cstride or cx
+    gen = torch.Generator().manual_seed(cg + cx + h)
+    g = torch.randn(n, h, w, cg, generator=gen).to(dev).to(torch.bfloat16)
+    x = torch.randn(n, h, w, xs, generator=gen).to(dev).to(torch.bfloat16)
+    d = WgradDesc()
+    d.n, d.h, d.w, d.cg, d.cx, d.x_cstride, d.taps, d.layout, d.dtype = n, h, w, cg, cx, xs, taps, layout, _lib.BF16
+    fl = C.c_longlong(0)
+    call("b2u_wgrad_workspace_floats", C.byref(d), C.byref(fl))
+    ws = torch.empty(fl.value, dtype=torch.float32, device=dev)
+    if layout == 0:
+        dw = torch.full((cg, cx, 3, 3) if taps == 9 else (cg, cx), float("nan"), device=dev)
+    else:
+        dw = torch.full((cx, cg // 4, 2, 2), float("nan"), device=dev)
+    call("b2u_wgrad", ptr(g), ptr(x), ptr(ws), ptr(dw), C.byref(d), stream_ptr())
+    torch.cuda.synchronize()
+    gd = g.double().permute(0, 3, 1, 2)
+    xd = x[..., :cx].double().permute(0, 3, 1, 2)
+    if taps == 9:
+        wv = torch.zeros(cg, cx, 3, 3, dtype=torch.float64, device=dev, requires_grad=True)
+        (F.conv2d(xd, wv, padding=1) * gd).sum().backward()
+        ref = wv.grad
+    else:
+        ref = torch.einsum("ngp,nxp->gx", gd.flatten(2), xd.flatten(2))
+        if layout == 1:
+            cout = cg // 4
+            ref = ref.view(4, cout, cx).permute(2, 1, 0).reshape(cx, cout, 2, 2)
+    r, mx = rel(dw, ref)
+    print(f"  wgrad n{n} {h}x{w} cg{cg} cx{cx} taps{taps} layout{layout} xs{xs}: rel {r:.3e} max {mx:.3e} nan {int(torch.isnan(dw).sum())}")
+    return r
+
+
+def sec_wgrad():
+    _wgrad_case(1, 16, 16, 64, 64, 1)
+    _wgrad_case(1, 16, 16, 128, 64, 1)
+    _wgrad_case(1, 16, 16, 64, 64, 9)
+    _wgrad_case(2, 24, 40, 128, 64, 9)
+    _wgrad_case(1, 37, 36, 256, 128, 9)
+    _wgrad_case(1, 33, 47, 64, 128, 9, x_cstride=256)
+    _wgrad_case(2, 20, 24, 512, 128, 1, layout=1)
+    _wgrad_case(1, 592, 576, 64, 64, 9)
+    _wgrad_case(1, 37, 36, 1024, 1024, 9)
+
+
+def sec_bwdk():
+    """unit backward kernels (GroupNorm/DropBlock/ReLU + pool + concat sources), 1x1 GEMM, first-layer wgrad vs autograd"""
+    import torch
+    import torch.nn.functional as F
+    from unet_research_b200 import _lib
+    from unet_research_b200._lib import ConvDesc, UnitBwdDesc, call, ptr, stream_ptr
+    dev = torch.device("cuda")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    G = 32
+    for (n, c, h, w, use_pool, use_a, use_head, s2d) in ((2, 64, 16, 24, True, True, False, False), (1, 256, 8, 8, False, True, False, True),
+                                                         (2, 64, 32, 48, False, False, True, False), (1, 128, 12, 16, True, True, False, False)):
+        gen = torch.Generator().manual_seed(c + h)
+        y = (torch.randn(n, c, h, w, generator=gen) * 1.5 + 0.3).to(dev)
+        y_nhwc = y.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+        yr = y_nhwc.float().permute(0, 3, 1, 2).double().requires_grad_(True)
+        gamma = (1 + 0.2 * torch.randn(c, generator=gen)).to(dev)
+        beta = (0.2 * torch.randn(c, generator=gen)).to(dev)
+        m1 = (torch.rand(n, c, h, w, generator=gen) > 0.15).to(dev)
+        s1 = m1.numel() / m1.sum().item()
+        # forward reference (fp64)
+        z = F.group_norm(yr, G, gamma.double(), beta.double(), 1e-5)
+        act = F.relu(z * m1 * s1)
+        loss = 0.0
+        ga = gp = None
+        if use_a:
+            ga = torch.randn(n, h, w, 2 * c, generator=gen).to(dev).to(torch.bfloat16)
+            m2 = (torch.rand(n, 2 * c, h, w, generator=gen) > 0.15).to(dev)
+            s2 = m2.numel() / m2.sum().item()
+            loss = loss + (act * m2[:, c:] * s2 * ga[..., c:].float().permute(0, 3, 1, 2).double()).sum()
+        if use_pool:
+            gp = torch.randn(n, h // 2, w // 2, c, generator=gen).to(dev).to(torch.bfloat16)
+            pooled, idx = F.max_pool2d(act, 2, 2, return_indices=True)
+            loss = loss + (pooled * gp.float().permute(0, 3, 1, 2).double()).sum()
+        if use_head:
+            h0, w0 = h - 3, w - 5
+            wh = (torch.randn(c, generator=gen) / 8).to(dev)
+            go = torch.randn(n, 1, h0, w0, generator=gen).to(dev)
+            logit = (act * wh.double().view(1, c, 1, 1)).sum(1, keepdim=True)[:, :, :h0, :w0]
+            out = torch.sigmoid(logit)
+            loss = loss + (out * go.double()).sum()
+        whp = wh.double().requires_grad_(True) if False else None
+        gparams = torch.autograd.grad(loss, [yr], retain_graph=True)[0]
+        # parameter grads through an independent graph
+        gam_d = gamma.double().requires_grad_(True)
+        bet_d = beta.double().requires_grad_(True)
+        z2 = F.group_norm(yr.detach(), G, gam_d, bet_d, 1e-5)
+        act2 = F.relu(z2 * m1 * s1)
+        loss2 = 0.0
+        if use_a:
+            loss2 = loss2 + (act2 * m2[:, c:] * s2 * ga[..., c:].float().permute(0, 3, 1, 2).double()).sum()
+        if use_pool:
+            loss2 = loss2 + (F.max_pool2d(act2, 2, 2) * gp.float().permute(0, 3, 1, 2).double()).sum()
+        if use_head:
+            whd = wh.double().requires_grad_(True)
+            out2 = torch.sigmoid((act2 * whd.view(1, c, 1, 1)).sum(1, keepdim=True)[:, :, :h0, :w0])
+            loss2 = loss2 + (out2 * go.double()).sum()
+            dgam, dbet, dwh = torch.autograd.grad(loss2, [gam_d, bet_d, whd])
+        else:
+            dgam, dbet = torch.autograd.grad(loss2, [gam_d, bet_d])
+        # our kernels: forward finalize to get coef / mean_rstd, masks as bits
+        def pack_bits(m):   # [n, C, h, w] bool -> uint32 [n,h,w,C/32]
+            mm = m.permute(0, 2, 3, 1).reshape(n, h, w, -1, 32).to(torch.int64)
+            return (mm << torch.arange(32, device=dev)).sum(-1).to(torch.int32).contiguous()
+        gs = c // G
+        sgs = min(gs, 32)
+        yv = y_nhwc.float().permute(0, 3, 1, 2).double().reshape(n, c // sgs, sgs * h * w)
+        parts = torch.stack([yv.sum(-1), (yv * yv).sum(-1)], -1).float().view(n, 1, c // sgs, 2).contiguous()
+        coef = torch.empty(n, c, 2, device=dev)
+        mr = torch.empty(n, G, 2, device=dev)
+        keep1 = torch.tensor([int(m1.sum().item())], dtype=torch.int64, device=dev)
+        call("b2u_gn_finalize", ptr(parts), 1, sgs, ptr(gamma), ptr(beta), ptr(coef), n, c, G, float(gs * h * w), 1e-5, ptr(keep1), n,
+             float(m1.numel()), ptr(mr), stream_ptr())
+        d = UnitBwdDesc()
+        d.n, d.h, d.w, d.c, d.dtype, d.relu, d.num_groups, d.s2d = n, h, w, c, _lib.BF16, 1, G, int(s2d)
+        d.images_per_call1, d.numel_per_call1 = n, float(m1.numel())
+        d.y, d.coef, d.mean_rstd, d.gamma = ptr(y_nhwc), ptr(coef), ptr(mr), ptr(gamma)
+        m1b = pack_bits(m1)
+        d.mask1, d.keep_counts1 = ptr(m1b), ptr(keep1)
+        keep = [m1b, keep1]
+        if use_a:
+            m2b = pack_bits(m2)
+            keep2 = torch.tensor([int(m2.sum().item())], dtype=torch.int64, device=dev)
+            d.grad_a, d.a_cstride, d.a_coffset = ptr(ga), 2 * c, c
+            d.mask2, d.mask2_cstride, d.mask2_coffset, d.keep_counts2 = ptr(m2b), 2 * c, c, ptr(keep2)
+            d.images_per_call2, d.numel_per_call2 = n, float(m2.numel())
+            keep += [m2b, keep2]
+        if use_pool:
+            iy, ix = idx // w, idx % w
+            am = ((iy % 2) * 2 + (ix % 2)).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+            d.grad_pool, d.argmax = ptr(gp), ptr(am)
+            keep += [am]
+        if use_head:
+            outf = out.detach().float().contiguous()
+            d.grad_out, d.out, d.w_head, d.h0, d.w0 = ptr(go), ptr(outf), ptr(wh), h0, w0
+            keep += [outf]
+        rows = C.c_int(0)
+        call("b2u_unit_bwd_rows", h, w, c, C.byref(rows))
+        bparts = torch.empty(n, rows.value, c, 3, device=dev)
+        gcoef = torch.empty(n, G, 2, device=dev)
+        dgamma = torch.empty(c, device=dev)
+        dbeta = torch.empty(c, device=dev)
+        dwh_o = torch.empty(c, device=dev)
+        call("b2u_unit_bwd_stats", C.byref(d), ptr(bparts), stream_ptr())
+        call("b2u_unit_bwd_finalize", ptr(bparts), n, rows.value, c, G, ptr(gamma), float(gs * h * w), ptr(gcoef), ptr(dgamma), ptr(dbeta),
+             ptr(dwh_o) if use_head else None, stream_ptr())
+        dy = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=dev) if not s2d else torch.empty(n, h // 2, w // 2, 4, c, dtype=torch.bfloat16, device=dev)
+        call("b2u_unit_bwd_apply", C.byref(d), ptr(gcoef), ptr(dy), stream_ptr())
+        torch.cuda.synchronize()
+        if s2d:
+            got = dy.float().view(n, h // 2, w // 2, 2, 2, c).permute(0, 5, 1, 3, 2, 4).reshape(n, c, h, w)
+        else:
+            got = dy.float().permute(0, 3, 1, 2)
+        msg = f"  unit_bwd n{n} c{c} {h}x{w} pool{int(use_pool)} a{int(use_a)} head{int(use_head)} s2d{int(s2d)}: dY rel {rel(got, gparams)[0]:.3e} dgamma rel {rel(dgamma, dgam)[0]:.3e} dbeta rel {rel(dbeta, dbet)[0]:.3e}"
+        if use_head:
+            msg += f" dw_head rel {rel(dwh_o, dwh)[0]:.3e}"
+        print(msg)
+    # 1x1 GEMM
+    n, h, w, k, co = 2, 20, 24, 512, 128
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(n, h, w, k, generator=gen).to(dev).to(torch.bfloat16)
+    wt = (torch.randn(co, k, generator=gen) / k ** 0.5).to(dev).to(torch.bfloat16)
+    yo = torch.empty(n, h, w, co, dtype=torch.bfloat16, device=dev)
+    cd = ConvDesc()
+    cd.n, cd.h, cd.w, cd.cin, cd.cout, cd.dtype, cd.num_groups, cd.x_cstride = n, h, w, k, co, _lib.BF16, 0, k
+    call("b2u_gemm1x1_fwd", ptr(x), ptr(wt), ptr(yo), C.byref(cd), stream_ptr())
+    torch.cuda.synchronize()
+    print(f"  gemm1x1: rel {rel(yo.float(), x.double() @ wt.double().t())[0]:.3e}")
+    # first-layer wgrad
+    for cin in (1, 3):
+        n, h0, w0, hh, ww, co = 2, 29, 45, 32, 48, 64
+        xin = torch.rand(n, cin, h0, w0, generator=gen).to(dev)
+        g = torch.randn(n, hh, ww, co, generator=gen).to(dev).to(torch.bfloat16)
+        wsb = torch.empty(n * 64 * co * cin * 9, device=dev)
+        dw = torch.empty(co, cin, 3, 3, device=dev)
+        call("b2u_wgrad_first", ptr(g), ptr(xin), ptr(wsb), ptr(dw), n, cin, h0, w0, hh, ww, co, _lib.BF16, stream_ptr())
+        torch.cuda.synchronize()
+        wv = torch.zeros(co, cin, 3, 3, dtype=torch.float64, device=dev, requires_grad=True)
+        xp = F.pad(xin, (0, ww - w0, 0, hh - h0)).double()
+        (F.conv2d(xp, wv, padding=1) * g.double().permute(0, 3, 1, 2)).sum().backward()
+        print(f"  wgrad_first cin{cin}: rel {rel(dw, wv.grad)[0]:.3e}")
+
+
 def sec_convt():
     from unet_research_b200 import _lib
     _conv_case(1, 16, 16, 128, 64, _lib.BF16, conv_t=True)
@@ -229,7 +421,7 @@ def sec_gn():
         v = xr.double().reshape(n, c // sgs, sgs * h * w)
         parts = torch.stack([v.sum(-1), (v * v).sum(-1)], -1).float().view(n, 1, c // sgs, 2).contiguous()
         coef = torch.empty(n, c, 2, dtype=torch.float32, device=dev)
-        call("b2u_gn_finalize", ptr(parts), 1, sgs, ptr(gamma), ptr(beta), ptr(coef), n, c, G, float(gs * h * w), 1e-5, None, 1, 0.0, stream_ptr())
+        call("b2u_gn_finalize", ptr(parts), 1, sgs, ptr(gamma), ptr(beta), ptr(coef), n, c, G, float(gs * h * w), 1e-5, None, 1, 0.0, None, stream_ptr())
         a = ApplyDesc()
         a.n, a.h, a.w, a.c, a.dtype, a.relu, a.out_cstride, a.out_coffset = n, h, w, c, _lib.BF16, 1, c, 0
         a.images_per_call2 = 1

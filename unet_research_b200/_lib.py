@@ -38,6 +38,18 @@ class HeadDesc(C.Structure):
                 ("reserved", C.c_int32 * 3)]
 
 
+class UnitBwdDesc(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("n", "h", "w", "c", "dtype", "relu", "num_groups", "s2d", "images_per_call1", "a_cstride",
+                                          "a_coffset", "mask2_cstride", "mask2_coffset", "images_per_call2", "h0", "w0")] +
+                [("numel_per_call1", C.c_double), ("numel_per_call2", C.c_double)] +
+                [(n, C.c_void_p) for n in ("y", "coef", "mean_rstd", "gamma", "mask1", "keep_counts1", "grad_a", "mask2",
+                                           "keep_counts2", "grad_pool", "argmax", "grad_out", "out", "w_head")])
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n", "h", "w", "cg", "cx", "x_cstride", "taps", "layout", "dtype")] + [("reserved", C.c_int32 * 3)]
+
+
 class DropblockCall(C.Structure):
     _fields_ = [("philox_offset", C.c_uint64), ("center_word_off", C.c_uint64), ("mask_word_off", C.c_uint64),
                 ("numel", C.c_uint32), ("grid", C.c_uint32), ("thresh_lo", C.c_uint32), ("thresh_hi", C.c_uint32),
@@ -64,7 +76,16 @@ SIGNATURES = {
     "b2u_convT2x2_fwd": (_I, [_P, _P, _P, _P, C.POINTER(ConvDesc), _P]),
     "b2u_conv_first_stat_layout": (_I, [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I)]),
     "b2u_conv_first_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
-    "b2u_gn_finalize": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _D, _F, _P, _I, _D, _P]),
+    "b2u_gn_finalize": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _D, _F, _P, _I, _D, _P, _P]),
+    "b2u_unit_bwd_rows": (_I, [_I, _I, _I, C.POINTER(_I)]),
+    "b2u_unit_bwd_stats": (_I, [C.POINTER(UnitBwdDesc), _P, _P]),
+    "b2u_unit_bwd_finalize": (_I, [_P, _I, _I, _I, _I, _P, _D, _P, _P, _P, _P, _P]),
+    "b2u_unit_bwd_apply": (_I, [C.POINTER(UnitBwdDesc), _P, _P, _P]),
+    "b2u_wgrad_workspace_floats": (_I, [C.POINTER(WgradDesc), C.POINTER(_LL)]),
+    "b2u_wgrad": (_I, [_P, _P, _P, _P, C.POINTER(WgradDesc), _P]),
+    "b2u_wgrad_first": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "b2u_gemm1x1_fwd": (_I, [_P, _P, _P, C.POINTER(ConvDesc), _P]),
+    "b2u_pack_convT2x2_dgrad_weight": (_I, [_P, _P, _I, _I, _I, _P]),
     "b2u_gn_apply": (_I, [_P, _P, _P, _P, _P, _P, C.POINTER(ApplyDesc), _P]),
     "b2u_pool_stat_layout": (_I, [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I)]),
     "b2u_gn_apply_pool": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, C.POINTER(ApplyDesc), _P]),
@@ -84,7 +105,9 @@ _LAUNCHERS = {"b2u_conv3x3_fwd": 1, "b2u_convT2x2_fwd": 1, "b2u_conv_first_fwd":
               "b2u_gn_apply": 1, "b2u_gn_apply_pool": 1, "b2u_head_fwd": 1, "b2u_mc_finalize": 1,
               "b2u_mc_accumulate": 1, "b2u_advance_counter": 1, "b2u_dropblock_centers": 1,
               "b2u_dropblock_dilate": 1, "b2u_dropblock_centers_from_uniform": 1, "b2u_rotate_bilinear": 1,
-              "b2u_pack_conv3x3_weight": 1, "b2u_pack_convT2x2_weight": 1}
+              "b2u_pack_conv3x3_weight": 1, "b2u_pack_convT2x2_weight": 1, "b2u_unit_bwd_stats": 1, "b2u_unit_bwd_finalize": 2,
+              "b2u_unit_bwd_apply": 1, "b2u_wgrad": 2, "b2u_wgrad_first": 2, "b2u_gemm1x1_fwd": 1,
+              "b2u_pack_convT2x2_dgrad_weight": 1}
 
 
 def load() -> C.CDLL:

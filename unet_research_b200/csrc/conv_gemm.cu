@@ -128,7 +128,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int s = 0;
       uint32_t ph = 1;
       for (int tap = 0; tap < p.taps; ++tap) {
-        int dy = 0, dx = 0, btap = tap_fixed;
+        int dy = 0, dx = 0, btap = p.mode == 1 ? tap_fixed : 0;
         if (p.mode == 0) {
           dy = tap / 3 - 1;
           dx = tap % 3 - 1;
@@ -174,7 +174,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int hh = h0 + dh, ww = w0 + dw;
     const bool valid = (hh < p.h) && (ww < p.w);
     size_t out_pix;
-    if (p.mode == 0) {
+    if (p.mode != 1) {
       out_pix = (static_cast<size_t>(img) * p.out_h + hh) * p.out_w + ww;
     } else {
       out_pix = (static_cast<size_t>(img) * p.out_h + (2 * hh + (tap_fixed >> 1))) * p.out_w + (2 * ww + (tap_fixed & 1));
@@ -231,7 +231,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int t = threadIdx.x - 64;
       if (t < nslots) {
         float s = stat_scratch[t] + stat_scratch[128 + t] + stat_scratch[256 + t] + stat_scratch[384 + t];
-        const int row_idx = (p.mode == 0) ? mt_in_img : mt_in_img * 4 + tap_fixed;
+        const int row_idx = (p.mode != 1) ? mt_in_img : mt_in_img * 4 + tap_fixed;
         const int slots_per_row = (p.cout * 2) >> p.sgs_log2;
         p.partials[(static_cast<size_t>(img) * p.rows_per_image + row_idx) * slots_per_row +
                    ((n0 * 2) >> p.sgs_log2) + t] = s;
@@ -369,8 +369,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   return B2U_OK;
 }
 
+// mode 0 = conv3x3 (v1), 1 = convT2x2, 2 = plain 1x1 GEMM
 static int run_gemm(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d,
-                    bool conv_t, void* stream) {
+                    int mode, void* stream) {
+  const bool conv_t = mode == 1;
   Plan pl;
   int rc = make_plan(d, conv_t, &pl);
   if (rc) return rc;
@@ -378,7 +380,7 @@ static int run_gemm(const void* x, const void* wpacked, void* y, float* partials
   B2U_REQUIRE(d->num_groups == 0 || partials != nullptr, "partials required when num_groups > 0");
   const int es = d->dtype == B2U_F32 ? 4 : 2;
   const int ke = 128 / es;
-  const int taps_w = conv_t ? 4 : 9;
+  const int taps_w = mode == 1 ? 4 : (mode == 0 ? 9 : 1);
 
   CUtensorMap ta, tb;
   {
@@ -404,10 +406,10 @@ static int run_gemm(const void* x, const void* wpacked, void* y, float* partials
   gp.n = d->n; gp.h = d->h; gp.w = d->w;
   gp.tiles_w = pl.tiles_w; gp.tiles_h = pl.tiles_h;
   gp.bw_log2 = conv_ilog2(pl.bw); gp.bh = pl.bh;
-  gp.taps = conv_t ? 1 : 9;
+  gp.taps = mode == 0 ? 9 : 1;
   gp.kc_per_tap = d->cin / ke;
   gp.cout = d->cout;
-  gp.mode = conv_t ? 1 : 0;
+  gp.mode = mode;
   gp.n_tiles_per_tap = d->cout / pl.block_n;
   gp.out_h = conv_t ? 2 * d->h : d->h;
   gp.out_w = conv_t ? 2 * d->w : d->w;
@@ -480,11 +482,15 @@ extern "C" int b2u_convT2x2_stat_layout(const b2u_conv_desc* d, int* rows_per_im
 extern "C" int b2u_conv3x3_fwd(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d,
                                void* stream) {
   if (!use_v1(d)) return conv3x3_v2_run(x, wpacked, y, partials, d, stream);
-  return run_gemm(x, wpacked, y, partials, d, false, stream);
+  return run_gemm(x, wpacked, y, partials, d, 0, stream);
 }
 extern "C" int b2u_convT2x2_fwd(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d,
                                 void* stream) {
-  return run_gemm(x, wpacked, y, partials, d, true, stream);
+  return run_gemm(x, wpacked, y, partials, d, 1, stream);
+}
+extern "C" int b2u_gemm1x1_fwd(const void* x, const void* wpacked, void* y, const b2u_conv_desc* d, void* stream) {
+  B2U_REQUIRE(d && d->num_groups == 0, "b2u_gemm1x1_fwd computes no statistics: set num_groups = 0");
+  return run_gemm(x, wpacked, y, nullptr, d, 2, stream);
 }
 extern "C" int b2u_pack_conv3x3_weight(const float* w, void* packed, int cout, int cin, int dtype, int transpose_flip,
                                        void* stream) {

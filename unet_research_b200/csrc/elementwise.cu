@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
 __global__ void gn_finalize_kernel(const float* __restrict__ partials, int rows, int sgs, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float2* __restrict__ coef, int c, int num_groups,
                                    double count, float eps, const unsigned long long* __restrict__ keep,
-                                   int images_per_call, double numel_per_call) {
+                                   int images_per_call, double numel_per_call, float2* __restrict__ mean_rstd) {
   const int g = blockIdx.x, n = blockIdx.y;
   const int gsize = c / num_groups;
   const int nsg_total = c / sgs;
@@ -135,6 +135,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partials, int rows,
   const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   float scale = 1.f;
   if (keep) scale = static_cast<float>(numel_per_call / static_cast<double>(keep[n / images_per_call]));
+  if (mean_rstd && threadIdx.x == 0) mean_rstd[static_cast<size_t>(n) * num_groups + g] = make_float2(static_cast<float>(mean), rstd);
   for (int i = threadIdx.x; i < gsize; i += blockDim.x) {
     const int ch = g * gsize + i;
     const float a = gamma[ch] * rstd;
@@ -534,7 +535,7 @@ extern "C" int b2u_conv_first_fwd(const float* x_nchw, const float* w, void* y, 
 extern "C" int b2u_gn_finalize(const float* partials, int rows_per_image, int subgroup_size, const float* gamma,
                                const float* beta, float* coef, int n, int c, int num_groups, double count, float eps,
                                const unsigned long long* keep_counts, int images_per_call, double numel_per_call,
-                               void* stream) {
+                               float* mean_rstd, void* stream) {
   B2U_REQUIRE(partials && gamma && beta && coef, "null pointer");
   B2U_REQUIRE(n > 0 && c > 0 && num_groups > 0 && c % num_groups == 0, "bad n/c/groups");
   B2U_REQUIRE(subgroup_size > 0 && (c / num_groups) % subgroup_size == 0, "subgroup size %d does not divide group size %d",
@@ -543,7 +544,7 @@ extern "C" int b2u_gn_finalize(const float* partials, int rows_per_image, int su
   dim3 grid(num_groups, n);
   gn_finalize_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       partials, rows_per_image, subgroup_size, gamma, beta, reinterpret_cast<float2*>(coef), c, num_groups, count, eps,
-      keep_counts, images_per_call > 0 ? images_per_call : 1, numel_per_call);
+      keep_counts, images_per_call > 0 ? images_per_call : 1, numel_per_call, reinterpret_cast<float2*>(mean_rstd));
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -183,6 +183,7 @@ class _Stat:
     rows: int
     sgs: int
     coef: torch.Tensor
+    mr: Optional[torch.Tensor] = None          # float2[n][G] (mean, rstd), kept for the backward pass
 
 
 class Workspace:
@@ -203,7 +204,8 @@ class Workspace:
 
         def stat(name, rows, sgs, c):
             self.stat[name] = _Stat(torch.empty(n, rows, c // sgs, 2, dtype=torch.float32, device=dev), rows, sgs,
-                                    torch.empty(n, c, 2, dtype=torch.float32, device=dev))
+                                    torch.empty(n, c, 2, dtype=torch.float32, device=dev),
+                                    torch.empty(n, eng.num_groups, 2, dtype=torch.float32, device=dev))
 
         c = f
         for lvl in range(d):
@@ -352,7 +354,7 @@ class UNetEngine:
         else:
             keep, ipc, numel = None, 1, 0.0
         call("b2u_gn_finalize", ptr(st.partials), st.rows, st.sgs, ptr(self.w[gkey + ".weight"]), ptr(self.w[gkey + ".bias"]),
-             ptr(st.coef), n, c, self.num_groups, count, GN_EPS, keep, ipc, numel, stream_ptr())
+             ptr(st.coef), n, c, self.num_groups, count, GN_EPS, keep, ipc, numel, ptr(st.mr), stream_ptr())
 
     def _apply_desc(self, n, h, w, c, relu, out_cstride, out_coffset, masks, site2, m2_cstride=0, m2_coffset=0) -> ApplyDesc:
         a = ApplyDesc()
