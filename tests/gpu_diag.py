@@ -18,7 +18,7 @@ import traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["info", "conv", "convv1", "convv2", "wgrad", "bwdk", "convt", "first", "gn", "pool", "head", "dropblock", "rotate", "forward", "mc", "rot_ens", "tf32"]
+SECTIONS = ["info", "conv", "convv1", "convv2", "wgrad", "bwdk", "convt", "first", "gn", "pool", "head", "dropblock", "rotate", "forward", "mc", "rot_ens", "tf32", "train"]
 
 
 def rel(a, b):
@@ -661,6 +661,136 @@ def sec_mc():
         res.append({"mean": rel(mean, rmean)[0], "std_maxabs": rel(std, rstd)[1], "samples": rel(tens, rtens)[0],
                     "offset": off_got, "offset_ref": off_ref})
     return res
+
+
+def _train_case(h, w, n, dropblock):
+    import torch
+    from torch import nn
+    from oracle import unet_oracle as O
+    import unet_research_b200 as U
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m, sd = _build_model(dev, dropblock=dropblock)
+    m.train()
+    x = synthetic.make_image(h, w, seed=1234, batch=n).to(dev)
+    gt = synthetic.make_gt(h, w, batch=n).to(dev)
+    fov = synthetic.make_fov_mask(h, w, batch=n).to(dev)
+    tm = U.BaseUNetTraining(m, nn.BCELoss(), None)
+    torch.manual_seed(4321)
+    loss = tm.training_step((x.clone(), gt, fov), 0)
+    loss.backward()
+    torch.cuda.synchronize()
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    torch.manual_seed(4321)
+    rloss = O.train_step_loss(params, x, gt, fov, O.DropBlockCfg(0.15, 7, True) if dropblock else None)
+    rloss.backward()
+    worst = []
+    for k, p in m.named_parameters():
+        r, _ = rel(p.grad, params[k].grad)
+        worst.append((r, k))
+    if os.environ.get("B2U_VERBOSE"):
+        for r_, k_ in worst:
+            print(f"      {k_:32s} rel {r_:.3e}  |g| {float(params[k_].grad.norm()):.3e}")
+    worst.sort(reverse=True)
+    allg = torch.cat([p.grad.flatten() for _, p in m.named_parameters()])
+    allr = torch.cat([params[k].grad.flatten() for k, _ in m.named_parameters()])
+    print(f"  train n{n} {h}x{w} dropblock={dropblock}: loss {loss.item():.6f} vs {rloss.item():.6f}; all-grad rel {rel(allg, allr)[0]:.3e}; "
+          f"median per-tensor rel {worst[len(worst) // 2][0]:.3e}; worst {[(round(a, 4), b) for a, b in worst[:4]]}")
+    return {"loss": loss.item(), "loss_ref": rloss.item(), "grad_rel": rel(allg, allr)[0], "worst": worst[0][0], "median": worst[len(worst) // 2][0]}
+
+
+def sec_train():
+    res = [_train_case(120, 116, 1, False), _train_case(120, 116, 2, True), _train_case(584, 565, 1, True)]
+    return res
+
+
+def sec_trainbench():
+    """fwd + bwd (+ SGD) of the canonical U-Net, batch 1, 584x565, DropBlock p=.15 (BASELINE configs[1]); eager launches."""
+    import time
+    import torch
+    from torch import nn
+    import unet_research_b200 as U
+    from unet_research_b200 import synthetic, _lib
+    dev = torch.device("cuda")
+    m, sd = _build_model(dev, dropblock=True)
+    m.train()
+    h, w = 584, 565
+    x = synthetic.make_image(h, w, seed=1234).to(dev)
+    gt = synthetic.make_gt(h, w).to(dev)
+    fov = synthetic.make_fov_mask(h, w).to(dev)
+    tm = U.BaseUNetTraining(m, nn.BCELoss(), None)
+    opt = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.99)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = tm.training_step((x.clone(), gt, fov), 0)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 0.5)
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    K = 10
+    for _ in range(K):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(f"  train step 584x565 b1: {e0.elapsed_time(e1) / K:.3f} ms/step (GPU events), {dt / K * 1e3:.3f} ms wall, "
+          f"{(_lib.launch_count - l0) / K:.0f} b2u launches/step, loss {loss.item():.4f}, 1.5 TFLOP/step -> {1501.0 / (e0.elapsed_time(e1) / K):.0f} TFLOP/s")
+    # kernel-only time of fwd and bwd: event pairs around the autograd function pieces
+    from unet_research_b200.backward import unet_backward
+    eng = m._get_engine(x.device)
+    ws = eng.workspace(1, h, w)
+    tb = ws.train_buffers
+    masks = m._mask_plan(eng, 1, 1, ws, 0.15, 7)
+    xin = x.contiguous()
+    go = torch.randn(1, 1, h, w, device=dev) * 1e-5
+    for name, fn in (("masks", lambda: masks.generate(1234)), ("forward", lambda: eng.forward(xin, ws, masks, argmax=tb.argmax)),
+                     ("backward", lambda: unet_backward(eng, ws, tb, masks, xin, ws.out, go))):
+        fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"     {name}: {e0.elapsed_time(e1) / 5:.3f} ms")
+    # per entry point breakdown of the backward
+    import unet_research_b200.backward as BW
+    recs = []
+    orig = BW.call
+
+    def timed(name, *a):
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        orig(name, *a)
+        e_.record()
+        recs.append((name, a[-2] if name == "b2u_wgrad" else None, s_, e_))
+
+    BW.call = timed
+    try:
+        for _ in range(3):
+            unet_backward(eng, ws, tb, masks, xin, ws.out, go)
+        torch.cuda.synchronize()
+    finally:
+        BW.call = orig
+    tot = {}
+    for name, _, s_, e_ in recs:
+        tot[name] = tot.get(name, 0.0) + s_.elapsed_time(e_) / 3
+    print("     backward breakdown (ms/step):", {k: round(v, 3) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])})
+    per = [(round(s_.elapsed_time(e_), 3)) for name, _, s_, e_ in recs[:len(recs) // 3] if name == "b2u_wgrad"]
+    print("     wgrad launches (ms):", per)
+    per = [(round(s_.elapsed_time(e_), 3)) for name, _, s_, e_ in recs[:len(recs) // 3] if name == "b2u_conv3x3_fwd"]
+    print("     dgrad launches (ms):", per)
 
 
 def sec_rot_ens():

@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ApplyDesc, ConvDesc, DropblockCall, HeadDesc, call, ptr, stream_ptr
+from ._lib import ApplyDesc, ConvDesc, DropblockCall, HeadDesc, UnitBwdDesc, WgradDesc, call, ptr, stream_ptr
 
 GN_EPS = 1e-5
 
@@ -275,6 +275,8 @@ class UNetEngine:
         self.init_channels, self.filters, self.depth, self.num_groups, self.dtype = init_channels, filters, depth, num_groups, dtype
         self.w: Dict[str, torch.Tensor] = {}
         self._workspaces: Dict[Tuple[int, int, int], Workspace] = {}
+        self.training_weights = False          # set by enable_training(): also keep the dgrad-packed weights
+        self._sd_ref = state_dict
         self.load_weights(state_dict)
 
     # ---- weights
@@ -291,6 +293,7 @@ class UNetEngine:
                 self.w[key] = t
             return t
 
+        self._sd_ref = sd
         for k, v in sd.items():
             v32 = v.detach().to(device=dev, dtype=torch.float32).contiguous()
             if v32.dim() == 4 and k == "down_blocks.0.0.0.weight":
@@ -302,9 +305,13 @@ class UNetEngine:
             elif v32.dim() == 4 and v32.shape[2] == 3:
                 cout, cin = v32.shape[0], v32.shape[1]
                 call("b2u_pack_conv3x3_weight", ptr(v32), ptr(slot(k, (9, cout, cin), dt)), cout, cin, self.dtype, 0, st)
+                if self.training_weights:                                  # data-gradient operand: transposed, taps rotated 180
+                    call("b2u_pack_conv3x3_weight", ptr(v32), ptr(slot(k + "#dgrad", (9, cin, cout), dt)), cout, cin, self.dtype, 1, st)
             elif v32.dim() == 4 and v32.shape[2] == 2:
                 cin, cout = v32.shape[0], v32.shape[1]
                 call("b2u_pack_convT2x2_weight", ptr(v32), ptr(slot(k, (4, cout, cin), dt)), cin, cout, self.dtype, st)
+                if self.training_weights:
+                    call("b2u_pack_convT2x2_dgrad_weight", ptr(v32), ptr(slot(k + "#dgrad", (1, cin, 4 * cout), dt)), cin, cout, self.dtype, st)
             else:
                 slot(k, v32.shape, torch.float32).copy_(v32)
         torch.cuda.current_stream().synchronize()      # v32 temporaries die here
@@ -345,6 +352,13 @@ class UNetEngine:
         d = self._conv_desc(n, h, w, cin, cout, cin)
         call("b2u_convT2x2_fwd" if conv_t else "b2u_conv3x3_fwd", ptr(ws.buf[xname]), ptr(self.w[wkey]), ptr(ws.buf[yname]),
              ptr(ws.stat[sname].partials), C.byref(d), stream_ptr())
+
+    def enable_training(self):
+        if not self.training_weights:
+            if self.dtype != _lib.BF16:
+                raise NotImplementedError("the backward pass is implemented for compute_dtype='bf16'")
+            self.training_weights = True
+            self.load_weights(self._sd_ref)
 
     def _finalize(self, ws, sname, gkey, n, c, hw, masks: Optional[MaskPlan], site: Optional[int]):
         st = ws.stat[sname]

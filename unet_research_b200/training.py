@@ -1,19 +1,64 @@
-"""Training-step mirror of `BaseUNetTraining` (unet_code/utils/utils_training.py:8-78).
-
-The forward runs the B200 kernel schedule; the backward pass (dgrad / wgrad tcgen05 GEMMs, GroupNorm,
-DropBlock, max-pool and up-conv gradients) is the next row of the scope table and is not built yet, so
-a forward under autograd raises instead of silently falling back to PyTorch ops.
+"""Training-step mirror of `BaseUNetTraining` (unet_code/utils/utils_training.py:8-78) and the autograd bridge
+of `UNet.forward`: forward and backward both run the B200 kernel schedules (engine.py / backward.py); PyTorch
+only carries the loss (`nn.BCELoss` on the returned probabilities, training.py:195) and the optimiser.
 """
 from __future__ import annotations
 
 import torch
 from torch import nn
 
+from . import _lib
+
+
+class _UNetFunction(torch.autograd.Function):
+    """out = UNet(x); backward returns one gradient per parameter, in `model.parameters()` order."""
+
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        from .backward import TrainBuffers
+        eng = model._get_engine(x.device)
+        eng.enable_training()
+        n, _, h0, w0 = x.shape
+        model._original_size = (h0, w0)
+        ws = eng.workspace(n, h0, w0)
+        tb = getattr(ws, "train_buffers", None)
+        if tb is None:
+            tb = TrainBuffers(eng, ws)
+            ws.train_buffers = tb
+        xin = x.detach().to(torch.float32).contiguous()
+        active, p, bs = model._dropblock_state()
+        masks = None
+        if active:
+            masks = model._mask_plan(eng, 1, n, ws, p, bs)
+            idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+            gen = torch.cuda.default_generators[idx]
+            masks.set_stream_position(gen.get_offset())
+            masks.generate(gen.initial_seed())
+            gen.set_offset(gen.get_offset() + masks.offset_per_call)
+        out = eng.forward(xin, ws, masks, argmax=tb.argmax).clone()
+        ctx.model, ctx.eng, ctx.ws, ctx.tb, ctx.masks, ctx.xin = model, eng, ws, tb, masks, xin
+        ctx.keys = [k for k, _ in model.named_parameters()]
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from .backward import unet_backward
+        (out,) = ctx.saved_tensors
+        grads = unet_backward(ctx.eng, ctx.ws, ctx.tb, ctx.masks, ctx.xin, out, grad_out)
+        missing = [k for k in ctx.keys if k not in grads]
+        if missing:
+            raise _lib.B2uError(f"backward produced no gradient for {missing[:3]}...")
+        return (None, None) + tuple(grads[k] for k in ctx.keys)
+
 
 def unet_autograd_forward(model, x):
-    raise NotImplementedError(
-        "unet_research_b200: the backward pass of the U-Net is not implemented yet; run inference under "
-        "torch.no_grad() (there is deliberately no PyTorch fallback)")
+    """The workspace is shared between forward and backward: one forward/backward pair at a time per
+    (batch, H, W), exactly like the reference's activation-checkpointed blocks hold one set of activations."""
+    if model.compute_dtype != "bf16":
+        raise NotImplementedError("training runs with compute_dtype='bf16'")
+    params = [p for _, p in model.named_parameters()]
+    return _UNetFunction.apply(model, x, *params)
 
 
 class BaseUNetTraining(nn.Module):
