@@ -52,6 +52,7 @@ class TrainBuffers:
         self.partials = torch.empty(max_part, dtype=torch.float32, device=dev)
         self.gcoef = torch.empty(n * eng.num_groups * 2, dtype=torch.float32, device=dev)
         self.wg_ws: Optional[torch.Tensor] = None
+        self.reducer: Optional["GradReducer"] = None
         self.first_ws = torch.empty(n * 64 * f * eng.init_channels * 9, dtype=torch.float32, device=dev)
 
     def wgrad_workspace(self, floats: int, dev) -> torch.Tensor:
@@ -102,6 +103,42 @@ def _unit_bwd(eng: UNetEngine, ws: Workspace, tb: TrainBuffers, grads: Dict[str,
     call("b2u_unit_bwd_apply", C.byref(d), ptr(tb.gcoef), ptr(dy), sp)
 
 
+class GradReducer:
+    """Data-parallel gradient exchange (the implicit Lightning DDP of the reference): every large
+    weight gradient is all-reduced over NCCL as soon as its wgrad kernel has been enqueued, so the transfer
+    over NVLink overlaps the rest of the backward; the small GroupNorm / head gradients travel in one flat
+    bucket at the end.  `finish()` waits for the handles and averages (DDP semantics)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+        self.handles = []
+        self.big = []
+        self.bytes = 0
+
+    def submit(self, t: torch.Tensor):
+        self.big.append(t)
+        self.bytes += t.numel() * 4
+        self.handles.append(self.dist.all_reduce(t, group=self.group, async_op=True))
+
+    def finish(self, grads: Dict[str, torch.Tensor]):
+        big_ids = {id(t) for t in self.big}
+        small = [(k, v) for k, v in grads.items() if id(v) not in big_ids]
+        if small:
+            flat = torch.cat([v.reshape(-1) for _, v in small])
+            self.bytes += flat.numel() * 4
+            self.dist.all_reduce(flat, group=self.group)
+            off = 0
+            for k, v in small:
+                v.copy_(flat[off:off + v.numel()].view_as(v))
+                off += v.numel()
+        for h in self.handles:
+            h.wait()
+        inv = 1.0 / self.world
+        torch._foreach_mul_(list(grads.values()), inv)
+
+
 def _wgrad(eng, tb, grads, key, g: torch.Tensor, x: torch.Tensor, n, h, w, cg, cx, x_cstride, taps, layout, shape):
     d = WgradDesc()
     d.n, d.h, d.w, d.cg, d.cx, d.x_cstride, d.taps, d.layout, d.dtype = n, h, w, cg, cx, x_cstride, taps, layout, eng.dtype
@@ -111,6 +148,8 @@ def _wgrad(eng, tb, grads, key, g: torch.Tensor, x: torch.Tensor, n, h, w, cg, c
     dw = torch.empty(shape, dtype=torch.float32, device=eng.device)
     call("b2u_wgrad", ptr(g), ptr(x), ptr(wsb), ptr(dw), C.byref(d), stream_ptr())
     grads[key] = dw
+    if tb.reducer is not None:
+        tb.reducer.submit(dw)
 
 
 def _dgrad3x3(eng, key, g: torch.Tensor, out: torch.Tensor, n, h, w, cout_fwd, cin_fwd):
@@ -121,8 +160,10 @@ def _dgrad3x3(eng, key, g: torch.Tensor, out: torch.Tensor, n, h, w, cout_fwd, c
 
 
 def unet_backward(eng: UNetEngine, ws: Workspace, tb: TrainBuffers, masks: Optional[MaskPlan], xin: torch.Tensor,
-                  out: torch.Tensor, grad_out: torch.Tensor) -> Dict[str, torch.Tensor]:
-    """Returns {state-dict key: fp32 gradient in the PyTorch parameter layout}.  Launches only."""
+                  out: torch.Tensor, grad_out: torch.Tensor, data_parallel: bool = False) -> Dict[str, torch.Tensor]:
+    """Returns {state-dict key: fp32 gradient in the PyTorch parameter layout}.  Launches only (plus, with
+    data_parallel, NCCL all-reduces overlapped with the remaining backward kernels)."""
+    tb.reducer = GradReducer() if data_parallel else None
     n, f, dpt = ws.n, eng.filters, eng.depth
     B = ws.buf
     grads: Dict[str, torch.Tensor] = {}
@@ -202,4 +243,8 @@ def unet_backward(eng: UNetEngine, ws: Workspace, tb: TrainBuffers, masks: Optio
                  eng.dtype, stream_ptr())
             grads[p + ".0.weight"] = dw
     grads["output_conv.0.weight"] = grads["output_conv.0.weight"].view(1, f, 1, 1)
+    if tb.reducer is not None:
+        tb.reducer.finish(grads)
+        tb.last_allreduce_bytes = tb.reducer.bytes
+        tb.reducer = None
     return grads

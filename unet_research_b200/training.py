@@ -45,7 +45,9 @@ class _UNetFunction(torch.autograd.Function):
     def backward(ctx, grad_out):
         from .backward import unet_backward
         (out,) = ctx.saved_tensors
-        grads = unet_backward(ctx.eng, ctx.ws, ctx.tb, ctx.masks, ctx.xin, out, grad_out)
+        import torch.distributed as dist
+        dp = bool(getattr(ctx.model, "data_parallel", False)) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        grads = unet_backward(ctx.eng, ctx.ws, ctx.tb, ctx.masks, ctx.xin, out, grad_out, data_parallel=dp)
         missing = [k for k in ctx.keys if k not in grads]
         if missing:
             raise _lib.B2uError(f"backward produced no gradient for {missing[:3]}...")

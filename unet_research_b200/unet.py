@@ -55,6 +55,7 @@ class UNet(nn.Module):
         self._model_depth = model_depth
         self._checkpointing = checkpointing       # activation recompute is a memory trick; values are unchanged
         self.compute_dtype = "bf16"               # "bf16" (tcgen05 kind::f16) or "tf32" (fp32 storage, kind::tf32)
+        self.data_parallel = False                # True: backward all-reduces (averages) the gradients over torch.distributed
         self._engine: Optional[UNetEngine] = None
         self._engine_key = None
         self._mask_plans = {}
