@@ -328,7 +328,7 @@ def time_conv_kernels(runner, dev, reps):
     try:
         for _ in range(reps):
             runner.masks[0].generate(runner.seed)
-            runner.eng.forward(runner.x, runner.ws, runner.masks[0], head_out=False, mc=runner.mc)
+            runner.eng.forward(runner.x, runner.ws, runner.masks[0], head_out=False, mc=runner.mc, shared_input=True)
         torch.cuda.synchronize(dev)
     finally:
         E.call = orig

@@ -94,6 +94,13 @@ int b2u_gn_finalize(const float* partials, int rows_per_image, int subgroup_size
                     const float* beta, float* coef, int n, int c, int num_groups, double count, float eps,
                     const unsigned long long* keep_counts, int images_per_call, double numel_per_call,
                     float* mean_rstd, void* stream);
+/* Same, with shared_partials = 1: all n images share the partial rows of image 0 (Monte-Carlo DropBlock: the n
+ * batched iterations see the same image, so the first conv and its statistics are computed once; only the
+ * DropBlock rescale s differs per iteration, Dropblock_Uncertainty.py:64). */
+int b2u_gn_finalize_ex(const float* partials, int rows_per_image, int subgroup_size, const float* gamma,
+                       const float* beta, float* coef, int n, int c, int num_groups, double count, float eps,
+                       const unsigned long long* keep_counts, int images_per_call, double numel_per_call,
+                       float* mean_rstd, int shared_partials, void* stream);
 
 /* Fused normalise-affine [+ DropBlock mask] [+ ReLU] [+ second mask and rescale]: the elementwise tail
  * of a conv unit (GroupNorm -> DropBlock -> ReLU, utils_unet.py:177-182) and, with mask2, the DropBlock
@@ -107,7 +114,7 @@ typedef struct {
   int32_t out_cstride, out_coffset; /* output tensor channel count and first channel written        */
   int32_t mask2_cstride, mask2_coffset; /* channel count / offset of the mask2 tensor (concat site)  */
   int32_t images_per_call2;       /* images sharing one keep count of site 2                        */
-  int32_t reserved[3];
+  int32_t reserved[3];            /* reserved[0] == 1: every image reads x of image 0 (b2u_gn_apply only) */
   double numel_per_call2;         /* numel of one DropBlock call of site 2                          */
 } b2u_apply_desc;
 int b2u_gn_apply(const void* x, const float* coef, const uint32_t* mask1, const uint32_t* mask2,

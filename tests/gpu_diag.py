@@ -166,6 +166,40 @@ def sec_convbench():
         print(line + f"   best {best[0]}", flush=True)
 
 
+def sec_convtbench():
+    """Times the four transposed convolutions of the canonical U-Net at batch 5: v1 (CTA per tile and tap) vs v2 (persistent)."""
+    import torch
+    from unet_research_b200 import _lib
+    from unet_research_b200._lib import ConvDesc, call, ptr, stream_ptr
+    dev = torch.device("cuda")
+    n = 5
+    for (h, w, cin, cout) in [(37, 36, 1024, 512), (74, 72, 512, 256), (148, 144, 256, 128), (296, 288, 128, 64)]:
+        x = torch.randn(n, h, w, cin, device=dev).to(torch.bfloat16)
+        wp = torch.randn(4, cout, cin, device=dev).to(torch.bfloat16)
+        y = torch.empty(n, 2 * h, 2 * w, cout, dtype=torch.bfloat16, device=dev)
+        flop = 2.0 * n * h * w * 4 * cout * cin
+        nbytes = x.numel() * 2 + y.numel() * 2
+        line = f"  convT {h}x{w} {cin}->{cout}:"
+        for name, ver in (("v1", 1), ("v2", 0)):
+            d = ConvDesc()
+            d.n, d.h, d.w, d.cin, d.cout, d.dtype, d.num_groups, d.x_cstride = n, h, w, cin, cout, _lib.BF16, 32, cin
+            d.reserved[2] = ver
+            rows, sgs = C.c_int(0), C.c_int(0)
+            call("b2u_convT2x2_stat_layout", C.byref(d), C.byref(rows), C.byref(sgs))
+            parts = torch.empty(n, rows.value, cout // sgs.value, 2, dtype=torch.float32, device=dev)
+            for _ in range(2):
+                call("b2u_convT2x2_fwd", ptr(x), ptr(wp), ptr(y), ptr(parts), C.byref(d), stream_ptr())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                call("b2u_convT2x2_fwd", ptr(x), ptr(wp), ptr(y), ptr(parts), C.byref(d), stream_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            line += f"  {name} {ms * 1000:.0f}us {flop / ms / 1e9:.0f}TF {nbytes / ms / 1e6:.0f}GB/s"
+        print(line, flush=True)
+
+
 def _wgrad_case(n, h, w, cg, cx, taps, layout=0, x_cstride=None):
     import torch
     import torch.nn.functional as F

@@ -77,6 +77,7 @@ SIGNATURES = {
     "b2u_conv_first_stat_layout": (_I, [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I)]),
     "b2u_conv_first_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b2u_gn_finalize": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _D, _F, _P, _I, _D, _P, _P]),
+    "b2u_gn_finalize_ex": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _D, _F, _P, _I, _D, _P, _I, _P]),
     "b2u_unit_bwd_rows": (_I, [_I, _I, _I, C.POINTER(_I)]),
     "b2u_unit_bwd_stats": (_I, [C.POINTER(UnitBwdDesc), _P, _P]),
     "b2u_unit_bwd_finalize": (_I, [_P, _I, _I, _I, _I, _P, _D, _P, _P, _P, _P, _P]),
@@ -101,7 +102,7 @@ SIGNATURES = {
 
 _lib: Optional[C.CDLL] = None
 launch_count = 0          # kernels launched through this binding (bench.py reports it as gpu_launches)
-_LAUNCHERS = {"b2u_conv3x3_fwd": 1, "b2u_convT2x2_fwd": 1, "b2u_conv_first_fwd": 1, "b2u_gn_finalize": 1,
+_LAUNCHERS = {"b2u_conv3x3_fwd": 1, "b2u_convT2x2_fwd": 1, "b2u_conv_first_fwd": 1, "b2u_gn_finalize": 1, "b2u_gn_finalize_ex": 1,
               "b2u_gn_apply": 1, "b2u_gn_apply_pool": 1, "b2u_head_fwd": 1, "b2u_mc_finalize": 1,
               "b2u_mc_accumulate": 1, "b2u_advance_counter": 1, "b2u_dropblock_centers": 1,
               "b2u_dropblock_dilate": 1, "b2u_dropblock_centers_from_uniform": 1, "b2u_rotate_bilinear": 1,

@@ -472,6 +472,7 @@ extern "C" int b2u_conv3x3_stat_layout(const b2u_conv_desc* d, int* rows_per_ima
   return B2U_OK;
 }
 extern "C" int b2u_convT2x2_stat_layout(const b2u_conv_desc* d, int* rows_per_image, int* subgroup_size) {
+  if (!use_v1(d)) return convT_v2_stat_layout(d, rows_per_image, subgroup_size);
   Plan pl;
   int rc = make_plan(d, true, &pl);
   if (rc) return rc;
@@ -486,6 +487,7 @@ extern "C" int b2u_conv3x3_fwd(const void* x, const void* wpacked, void* y, floa
 }
 extern "C" int b2u_convT2x2_fwd(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d,
                                 void* stream) {
+  if (!use_v1(d)) return convT_v2_run(x, wpacked, y, partials, d, stream);
   return run_gemm(x, wpacked, y, partials, d, 1, stream);
 }
 extern "C" int b2u_gemm1x1_fwd(const void* x, const void* wpacked, void* y, const b2u_conv_desc* d, void* stream) {

@@ -14,4 +14,8 @@ int conv_ilog2(int v);
 int conv3x3_v2_stat_layout(const b2u_conv_desc* d, int* rows_per_image, int* subgroup_size);
 int conv3x3_v2_run(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d, void* stream);
 
+// convT2x2 v2 (convT_v2.cu): persistent, all taps of an N tile share one activation fetch
+int convT_v2_stat_layout(const b2u_conv_desc* d, int* rows_per_image, int* subgroup_size);
+int convT_v2_run(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d, void* stream);
+
 }  // namespace b2u

@@ -15,17 +15,23 @@
 
 namespace b2u {
 
+// 32x32 -> 64 multiply as ONE IMAD.WIDE.U32 (the C++ uint64 product makes ptxas add a zero high-word
+// correction: 2 wasted adds per round, 20 per call)
+__device__ __forceinline__ void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+  asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t (&out)[4]) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    // one 32x32->64 multiply (IMAD.WIDE) yields both halves
-    const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
-    const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
-    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0;
-    const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1;
-    c1 = static_cast<uint32_t>(p1);
-    c3 = static_cast<uint32_t>(p0);
+    uint32_t h0, l0, h1, l1;
+    mulhilo(0xD2511F53u, c0, h0, l0);
+    mulhilo(0xCD9E8D57u, c2, h1, l1);
+    const uint32_t n0 = h1 ^ c1 ^ k0;
+    const uint32_t n2 = h0 ^ c3 ^ k1;
+    c1 = l1;
+    c3 = l0;
     c0 = n0;
     c2 = n2;
     k0 += 0x9E3779B9u;
@@ -84,16 +90,17 @@ __global__ void dropblock_centers_from_uniform_kernel(const float* __restrict__ 
 
 // 32 bits of a centre row: bit k = centre[x = xa + k] (0 outside [0, wc)); row starts at bit `rowbit`
 // of the flat bitmap.
-__device__ __forceinline__ uint32_t row_bits(const uint32_t* __restrict__ bits, uint64_t rowbit, int xa, int wc) {
+// (all bit indices fit 32 bits: numel of one torch.rand call is < 2^32, checked by the host)
+__device__ __forceinline__ uint32_t row_bits(const uint32_t* __restrict__ bits, uint32_t rowbit, int xa, int wc) {
   if (xa <= -32 || xa >= wc) return 0u;
   int shift_in = 0;
   if (xa < 0) {
     shift_in = -xa;
     xa = 0;
   }
-  const uint64_t q = rowbit + static_cast<uint64_t>(xa);
-  const uint64_t wi = q >> 5;
-  const uint32_t sh = static_cast<uint32_t>(q & 31);
+  const uint32_t q = rowbit + static_cast<uint32_t>(xa);
+  const uint32_t wi = q >> 5;
+  const uint32_t sh = q & 31u;
   uint32_t v = __funnelshift_r(__ldg(bits + wi), __ldg(bits + wi + 1), sh);
   const int cnt = wc - xa;                                  // valid bits from xa
   if (cnt < 32) v &= (1u << cnt) - 1u;
@@ -102,7 +109,9 @@ __device__ __forceinline__ uint32_t row_bits(const uint32_t* __restrict__ bits, 
 
 // One warp: 32 channels (lane = channel) x 32 pixels of one image row band.
 // grid = (bands * wwords, c/32 * n_img, n_calls).
-template <int RING>
+// BS_CT > 0: block size known at compile time (the reference default 7): the smear, the ring and the slot
+// arithmetic unroll into straight-line code.
+template <int RING, int BS_CT>
 __global__ void __launch_bounds__(128) dropblock_dilate_kernel(const b2u_dropblock_call* __restrict__ table,
                                         const uint32_t* __restrict__ center_bits, uint32_t* __restrict__ mask_bits,
                                         unsigned long long* __restrict__ keep_counts, int band_rows) {
@@ -117,11 +126,11 @@ __global__ void __launch_bounds__(128) dropblock_dilate_kernel(const b2u_dropblo
   if (item >= bands * wwords || plane_grp >= cgs * c.n_img) return;     // uniform per warp
   const int band = item / wwords, wj = item - band * wwords;
   const int img = plane_grp / cgs, cg = plane_grp - img * cgs;
-  const int bs = c.block_size;
+  const int bs = BS_CT > 0 ? BS_CT : c.block_size;
   const int hc = c.h - bs + 1, wc = c.w - bs + 1;
   const int ch = cg * 32 + lane;
   const uint32_t* cb = center_bits + c.center_word_off;
-  const uint64_t plane_bit = (static_cast<uint64_t>(img) * c.c + ch) * static_cast<uint64_t>(hc) * wc;
+  const uint32_t plane_bit = (static_cast<uint32_t>(img) * c.c + ch) * static_cast<uint32_t>(hc) * wc;
   const int w0 = wj * 32;
   const int h_begin = band * band_rows;
   const int h_end = min(h_begin + band_rows, c.h);
@@ -138,13 +147,16 @@ __global__ void __launch_bounds__(128) dropblock_dilate_kernel(const b2u_dropblo
   auto fetch = [&](int r, uint32_t& lo, uint32_t& hi) {
     lo = hi = 0u;
     if (r >= 0 && r < hc) {
-      const uint64_t rowbit = plane_bit + static_cast<uint64_t>(r) * wc;
+      const uint32_t rowbit = plane_bit + static_cast<uint32_t>(r) * wc;
       lo = row_bits(cb, rowbit, w0 - 32, wc);
       hi = row_bits(cb, rowbit, w0, wc);
     }
   };
   uint32_t nlo, nhi;
   fetch(h_begin - bs + 1, nlo, nhi);
+  int slot = (((h_begin - bs + 1) % bs) + bs) % bs;          // ring slot = r mod bs, advanced incrementally
+  uint32_t* orow = mout + ((static_cast<size_t>(img) * c.h + h_begin) * c.w + (w0 + lane)) * cgs + cg;
+  const size_t orow_stride = static_cast<size_t>(c.w) * cgs;
   for (int r = h_begin - bs + 1; r < h_end; ++r) {
     const uint32_t lo = nlo, hi = nhi;
     if (r + 1 < h_end) fetch(r + 1, nlo, nhi);
@@ -160,11 +172,10 @@ __global__ void __launch_bounds__(128) dropblock_dilate_kernel(const b2u_dropblo
       }
       sm = static_cast<uint32_t>(v >> 32);
     }
-    // ring slot = r mod bs (r may be negative)
-    const int slot = ((r % bs) + bs) % bs;
 #pragma unroll
     for (int i = 0; i < RING; ++i)
       if (i == slot) ring[i] = sm;
+    if (++slot == bs) slot = 0;
     if (r < h_begin) continue;
     uint32_t drop = 0u;
 #pragma unroll
@@ -180,9 +191,8 @@ __global__ void __launch_bounds__(128) dropblock_dilate_kernel(const b2u_dropblo
       const uint32_t y = __shfl_xor_sync(0xffffffffu, mine, j);
       mine = (lane & j) ? ((mine & ~m) | ((y & ~m) >> j)) : ((mine & m) | ((y & m) << j));
     }
-    if (w0 + lane < c.w) {
-      mout[((static_cast<uint64_t>(img) * c.h + r) * c.w + (w0 + lane)) * cgs + cg] = mine;
-    }
+    if (w0 + lane < c.w) *orow = mine;
+    orow += orow_stride;
   }
   // integer count: atomics are order-independent, the result is deterministic
 #pragma unroll
@@ -227,10 +237,15 @@ extern "C" int b2u_dropblock_dilate(const b2u_dropblock_call* table, int n_calls
   }
   B2U_REQUIRE(max_planes <= 65535, "too many channel groups x images (%d)", max_planes);
   dim3 grid((max_items + 3) / 4, max_planes, n_calls);
-  if (max_bs <= 7)
-    dropblock_dilate_kernel<7><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, center_bits, mask_bits, keep_counts, band_rows);
+  bool all7 = true;
+  for (int i = 0; i < n_calls; ++i) all7 = all7 && host_table[i].block_size == 7;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (all7)
+    dropblock_dilate_kernel<7, 7><<<grid, 128, 0, st>>>(table, center_bits, mask_bits, keep_counts, band_rows);
+  else if (max_bs <= 7)
+    dropblock_dilate_kernel<7, 0><<<grid, 128, 0, st>>>(table, center_bits, mask_bits, keep_counts, band_rows);
   else
-    dropblock_dilate_kernel<31><<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, center_bits, mask_bits, keep_counts, band_rows);
+    dropblock_dilate_kernel<31, 0><<<grid, 128, 0, st>>>(table, center_bits, mask_bits, keep_counts, band_rows);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -50,13 +50,17 @@ __device__ void block_stats_to_partials(const float (&s)[8], const float (&q)[8]
 
 // ---------------------------------------------------------------------------------------------
 // First layer: direct 3x3 conv, Cin in {1,3}, fp32 NCHW input read with autopad semantics.
+constexpr int kFirstStrip = 4;
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ wgt, T* __restrict__ y,
                                   float* __restrict__ partials, int h0, int w0, int h, int w, int cout, int sgs) {
   extern __shared__ float sm[];
-  float* wsm = sm;                                  // [cout][CIN*9]
+  float* wsm = sm;                                  // [CIN*9][cout]: tap-major, so a thread's 8 channels are two LDS.128
   float* red = sm + cout * CIN * 9;
-  for (int i = threadIdx.x; i < cout * CIN * 9; i += blockDim.x) wsm[i] = wgt[i];
+  for (int i = threadIdx.x; i < cout * CIN * 9; i += blockDim.x) {
+    const int co = i / (CIN * 9), j = i - co * (CIN * 9);
+    wsm[j * cout + co] = wgt[i];
+  }
   __syncthreads();
   const int n = blockIdx.y;
   const int cvs = cout >> 3;
@@ -67,33 +71,58 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  const int npix = h * w;
-  for (int pix = blockIdx.x * slots + slot; pix < npix; pix += gridDim.x * slots) {
-    const int ph = pix / w, pw = pix - ph * w;
-    float in[CIN * 9];
+  // one thread = 8 output channels x a strip of kFirstStrip pixels along W: the 3 x (strip + 2) input window is
+  // loaded once, every weight vector (2 x LDS.128) feeds kFirstStrip x 8 FMAs
+  constexpr int S = kFirstStrip;
+  const int strips_w = w / S;
+  const int nstrips = h * strips_w;
+  for (int strip = blockIdx.x * slots + slot; strip < nstrips; strip += gridDim.x * slots) {
+    const int ph = strip / strips_w, pw = (strip - ph * strips_w) * S;
+    float in[CIN][3][S + 2];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < S + 2; ++c) {
+          const int yy = ph + r - 1, xx = pw + c - 1;
+          in[ci][r][c] = (yy >= 0 && yy < h0 && xx >= 0 && xx < w0) ? __ldg(xn + (static_cast<size_t>(ci) * h0 + yy) * w0 + xx) : 0.f;
+        }
+    float o[S][8];
+#pragma unroll
+    for (int px = 0; px < S; ++px)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[px][k] = 0.f;
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const int yy = ph + r - 1, xx = pw + c - 1;
-          in[ci * 9 + r * 3 + c] = (yy >= 0 && yy < h0 && xx >= 0 && xx < w0) ? __ldg(xn + (static_cast<size_t>(ci) * h0 + yy) * w0 + xx) : 0.f;
+          const int j = ci * 9 + r * 3 + c;
+          const float4 wa = *reinterpret_cast<const float4*>(wsm + j * cout + cv * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(wsm + j * cout + cv * 8 + 4);
+#pragma unroll
+          for (int px = 0; px < S; ++px) {
+            const float v = in[ci][r][px + c];
+            o[px][0] = fmaf(v, wa.x, o[px][0]); o[px][1] = fmaf(v, wa.y, o[px][1]);
+            o[px][2] = fmaf(v, wa.z, o[px][2]); o[px][3] = fmaf(v, wa.w, o[px][3]);
+            o[px][4] = fmaf(v, wb.x, o[px][4]); o[px][5] = fmaf(v, wb.y, o[px][5]);
+            o[px][6] = fmaf(v, wb.z, o[px][6]); o[px][7] = fmaf(v, wb.w, o[px][7]);
+          }
         }
-    float o[8];
+    const size_t pix0 = static_cast<size_t>(n) * h * w + static_cast<size_t>(ph) * w + pw;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float* wk = wsm + (cv * 8 + k) * CIN * 9;
-      float acc = 0.f;
+    for (int px = 0; px < S; ++px) {
 #pragma unroll
-      for (int j = 0; j < CIN * 9; ++j) acc = fmaf(in[j], wk[j], acc);
-      o[k] = acc;
-      s[k] += acc;
-      q[k] += acc * acc;
+      for (int k = 0; k < 8; ++k) {
+        s[k] += o[px][k];
+        q[k] += o[px][k] * o[px][k];
+      }
+      Vec8<T> v;
+      v.from_float(o[px]);
+      v.store(y + (pix0 + px) * cout + cv * 8);
     }
-    Vec8<T> v;
-    v.from_float(o);
-    v.store(y + (static_cast<size_t>(n) * npix + pix) * cout + cv * 8);
   }
   if (partials) {
     block_stats_to_partials(s, q, cout, sgs, red,
@@ -105,12 +134,13 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
 __global__ void gn_finalize_kernel(const float* __restrict__ partials, int rows, int sgs, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float2* __restrict__ coef, int c, int num_groups,
                                    double count, float eps, const unsigned long long* __restrict__ keep,
-                                   int images_per_call, double numel_per_call, float2* __restrict__ mean_rstd) {
+                                   int images_per_call, double numel_per_call, float2* __restrict__ mean_rstd,
+                                   int shared_partials) {
   const int g = blockIdx.x, n = blockIdx.y;
   const int gsize = c / num_groups;
   const int nsg_total = c / sgs;
   const int sg_per_group = gsize / sgs;              // >= 1 (sgs = min(gsize, 32))
-  const float* base = partials + static_cast<size_t>(n) * rows * nsg_total * 2;
+  const float* base = partials + (shared_partials ? 0 : static_cast<size_t>(n) * rows * nsg_total * 2);
   double s = 0.0, q = 0.0;
   for (int i = threadIdx.x; i < rows * sg_per_group; i += blockDim.x) {
     const int r = i / sg_per_group, k = i - r * sg_per_group;
@@ -152,6 +182,7 @@ struct ApplyParams {
   int mask2_cstride, mask2_coffset;
   int images_per_call2;
   double numel_per_call2;
+  int x_shared;                 // 1: every image reads the input tensor of image 0 (Monte-Carlo: same image, same first conv)
 };
 
 struct Coef8 {
@@ -179,7 +210,7 @@ __device__ __forceinline__ void apply8(float (&f)[8], const Coef8& cf, uint32_t 
 // streams kApplyUnroll pixels per trip with all loads issued before the first use.
 constexpr int kApplyUnroll = 4;
 template <typename T>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, const float2* __restrict__ coef, const uint8_t* __restrict__ mask1,
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(const T* __restrict__ x, const float2* __restrict__ coef, const uint8_t* __restrict__ mask1,
                                 const uint8_t* __restrict__ mask2, const unsigned long long* __restrict__ keep2,
                                 T* __restrict__ out, ApplyParams p) {
   const int n = blockIdx.y;
@@ -194,6 +225,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
   if (mask2) s2 = static_cast<float>(p.numel_per_call2 / static_cast<double>(keep2[n / p.images_per_call2]));
   const bool relu = p.relu != 0;
   const long img0 = static_cast<long>(n) * hw;
+  const long xoff = p.x_shared ? -img0 : 0;               // input pixel index = pix + xoff
   const int m2s = p.mask2_cstride >> 3, m2o = (p.mask2_coffset >> 3) + cv;
   const long stride = static_cast<long>(gridDim.x) * slots * kApplyUnroll;
   for (long base = static_cast<long>(blockIdx.x) * slots * kApplyUnroll + slot; base < hw; base += stride) {
@@ -204,7 +236,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
       const long pl = base + static_cast<long>(u) * slots;
       if (pl < hw) {
         const long pix = img0 + pl;
-        vec[u].load(x + pix * p.c + cv * 8);
+        vec[u].load(x + (pix + xoff) * p.c + cv * 8);
         m1[u] = mask1 ? mask1[pix * cvs + cv] : 0xFFu;
         m2[u] = mask2 ? mask2[pix * m2s + m2o] : 0xFFu;
       }
@@ -231,8 +263,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
 }
 
 // Encoder tail: apply + skip store (with concat mask) + 2x2 max-pool + pooled GroupNorm partials.
+constexpr int kPoolUnroll = 2;
 template <typename T>
-__global__ void __launch_bounds__(256) gn_apply_pool_kernel(const T* __restrict__ x, const float2* __restrict__ coef, const uint8_t* __restrict__ mask1,
+__global__ void __launch_bounds__(256, 2) gn_apply_pool_kernel(const T* __restrict__ x, const float2* __restrict__ coef, const uint8_t* __restrict__ mask1,
                                      const uint8_t* __restrict__ mask2, const unsigned long long* __restrict__ keep2,
                                      T* __restrict__ skip_out, T* __restrict__ pooled, float* __restrict__ pool_partials,
                                      uint8_t* __restrict__ argmax, int pool_sgs, ApplyParams p) {
@@ -251,57 +284,80 @@ __global__ void __launch_bounds__(256) gn_apply_pool_kernel(const T* __restrict_
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  for (int pp = blockIdx.x * slots + slot; pp < npool; pp += gridDim.x * slots) {
-    const int py = pp / pw, px = pp - py * pw;
-    float best[8];
-    uint32_t arg[8];
+  const bool relu = p.relu != 0;
+  const int m2s = p.mask2_cstride >> 3, m2o = (p.mask2_coffset >> 3) + cv;
+  constexpr int U = kPoolUnroll;                        // pooled pixels per trip: 8 x 16 B loads in flight per thread
+  const int stride = gridDim.x * slots * U;
+  for (int base = blockIdx.x * slots * U + slot; base < npool; base += stride) {
+    Vec8<T> vec[U][4];
+    uint32_t m1[U][4], m2[U][4];
+    long pix00[U];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long pix = (static_cast<long>(n) * p.h + (2 * py + (k >> 1))) * p.w + (2 * px + (k & 1));
-      Vec8<T> vec;
-      vec.load(x + pix * p.c + cv * 8);
-      float f[8];
-      vec.to_float(f);
-      const uint32_t m1 = mask1 ? mask1[pix * cvs + cv] : 0xFFu;
-      apply8(f, cf, m1, p.relu != 0);
+    for (int u = 0; u < U; ++u) {
+      const int pp = base + u * slots;
+      if (pp < npool) {
+        const int py = pp / pw, px = pp - py * pw;
+        pix00[u] = (static_cast<long>(n) * p.h + 2 * py) * p.w + 2 * px;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        // ATen max_pool2d: first maximum in row-major window order wins (val > maxval || isnan(val))
-        if (k == 0 || f[i] > best[i] || f[i] != f[i]) {
-          best[i] = f[i];
-          arg[i] = k;
+        for (int k = 0; k < 4; ++k) {
+          const long pix = pix00[u] + (k >> 1) * p.w + (k & 1);
+          vec[u][k].load(x + pix * p.c + cv * 8);
+          m1[u][k] = mask1 ? mask1[pix * cvs + cv] : 0xFFu;
+          m2[u][k] = mask2 ? mask2[pix * m2s + m2o] : 0xFFu;
         }
       }
-      if (skip_out) {
-        float g[8];
-        if (mask2) {
-          const uint32_t m2 = mask2[pix * (p.mask2_cstride >> 3) + (p.mask2_coffset >> 3) + cv];
+    }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = ((m2 >> i) & 1u) ? f[i] * s2 : 0.f;
-        } else {
+    for (int u = 0; u < U; ++u) {
+      const int pp = base + u * slots;
+      if (pp < npool) {
+        float best[8];
+        uint32_t arg_lo = 0u, arg_hi = 0u;                 // window index (0..3) of the maximum, one byte per channel
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = f[i];
+        for (int k = 0; k < 4; ++k) {
+          float f[8];
+          vec[u][k].to_float(f);
+          apply8(f, cf, m1[u][k], relu);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // ATen max_pool2d: first maximum in row-major window order wins (val > maxval || isnan(val))
+            if (k == 0 || f[i] > best[i] || f[i] != f[i]) {
+              best[i] = f[i];
+              if (k > 0) {
+                uint32_t& a = i < 4 ? arg_lo : arg_hi;
+                const int sh = 8 * (i & 3);
+                a = (a & ~(0xFFu << sh)) | (static_cast<uint32_t>(k) << sh);
+              }
+            }
+          }
+          if (skip_out) {
+            float g[8];
+            if (mask2) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) g[i] = ((m2[u][k] >> i) & 1u) ? f[i] * s2 : 0.f;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) g[i] = f[i];
+            }
+            round_for_storage<T>(g);
+            Vec8<T> o;
+            o.from_float(g);
+            o.store(skip_out + (pix00[u] + (k >> 1) * p.w + (k & 1)) * p.out_cstride + p.out_coffset + cv * 8);
+          }
         }
-        round_for_storage<T>(g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += best[i];
+          q[i] += best[i] * best[i];
+        }
+        const long po = (static_cast<long>(n) * npool + pp) * p.c + cv * 8;
         Vec8<T> o;
-        o.from_float(g);
-        o.store(skip_out + pix * p.out_cstride + p.out_coffset + cv * 8);
+        o.from_float(best);
+        o.store(pooled + po);
+        if (argmax) {
+          *reinterpret_cast<uint2*>(argmax + po) = make_uint2(arg_lo, arg_hi);
+        }
       }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      s[i] += best[i];
-      q[i] += best[i] * best[i];
-    }
-    const long po = (static_cast<long>(n) * npool + pp) * p.c + cv * 8;
-    Vec8<T> o;
-    o.from_float(best);
-    o.store(pooled + po);
-    if (argmax) {
-      uint2 a;
-      a.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
-      a.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
-      *reinterpret_cast<uint2*>(argmax + po) = a;
     }
   }
   if (pool_partials) {
@@ -312,8 +368,9 @@ __global__ void __launch_bounds__(256) gn_apply_pool_kernel(const T* __restrict_
 
 // ---------------------------------------------------------------------------------------------
 // Output head.  LPP = c/8 lanes cooperate on one pixel (c <= 256); each lane owns 8 channels.
+constexpr int kHeadPix = 2;
 template <typename T>
-__global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x, const float2* __restrict__ coef, const uint8_t* __restrict__ mask1,
+__global__ void __launch_bounds__(256, 3) head_kernel(const T* __restrict__ x, const float2* __restrict__ coef, const uint8_t* __restrict__ mask1,
                             const float* __restrict__ w_head, float* __restrict__ out, float* __restrict__ logits,
                             const float* __restrict__ fov, double* __restrict__ acc, float* __restrict__ samples,
                             const long long* __restrict__ iter_base, b2u_head_desc d) {
@@ -322,51 +379,85 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x, cons
   const long group = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) / lpp;
   const long ngroups = (static_cast<long>(gridDim.x) * blockDim.x) / lpp;
   const long npix0 = static_cast<long>(d.h0) * d.w0;
+  const long img_stride = static_cast<long>(d.h) * d.w;
   float wh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) wh[i] = __ldg(w_head + lane_in * 8 + i);
   const long long base_iter = iter_base ? *iter_base : 0;
-  // every lane of a warp runs the same trip count (shuffles below need the full warp)
-  const long trips = (npix0 + ngroups - 1) / ngroups;
+  // every lane of a warp runs the same trip count (shuffles below need the full warp).  A lane group walks
+  // kHeadPix pixels per trip; the loads of image n+1 are issued before image n is reduced (register double
+  // buffer), so 2 * kHeadPix 16-byte loads per thread stay in flight across the shuffle / exp / fp64 section.
+  constexpr int P = kHeadPix;
+  const long trips = (npix0 + ngroups * P - 1) / (ngroups * P);
   for (long tr = 0; tr < trips; ++tr) {
-    const long op = tr * ngroups + group;
-    const bool active = op < npix0;
-    const long opc = active ? op : 0;
-    const int oh = static_cast<int>(opc / d.w0), ow = static_cast<int>(opc - static_cast<long>(oh) * d.w0);
-    double s1 = 0.0, s2 = 0.0;
-    for (int n = 0; n < d.n; ++n) {
-      const long pix = (static_cast<long>(n) * d.h + oh) * d.w + ow;
-      Vec8<T> vec;
-      vec.load(x + pix * d.c + lane_in * 8);
-      float f[8];
-      vec.to_float(f);
-      const uint32_t m1 = mask1 ? mask1[pix * lpp + lane_in] : 0xFFu;
-      Coef8 cf;
-      cf.load(coef + static_cast<size_t>(n) * d.c + lane_in * 8);
-      apply8(f, cf, m1, true);
-      float dot = 0.f;
+    long op[P];
+    bool active[P];
+    long pixbase[P];
+    double s1[P], s2[P];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dot = fmaf(f[i], wh[i], dot);
-      for (int o = lpp >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-      if (active && lane_in == 0) {
-        float yv = 1.f / (1.f + expf(-dot));
-        yv = fminf(fmaxf(yv, 0.f), 1.f);
-        if (yv != yv) yv = 0.f;
-        if (logits) logits[static_cast<long>(n) * npix0 + op] = dot;
-        if (out) out[static_cast<long>(n) * npix0 + op] = yv;
-        if (acc) {
-          const float fv = fov ? fov[(d.fov_per_image ? static_cast<long>(n) * npix0 : 0) + op] : 1.f;
-          const float v = yv * fv;
-          s1 += static_cast<double>(v);
-          s2 += static_cast<double>(v) * static_cast<double>(v);
-          const long long it = base_iter + n;
-          if (samples && it < d.return_num) samples[it * npix0 + op] = v;
+    for (int j = 0; j < P; ++j) {
+      op[j] = (tr * P + j) * ngroups + group;
+      active[j] = op[j] < npix0;
+      const long opc = active[j] ? op[j] : 0;
+      const int oh = static_cast<int>(opc / d.w0), ow = static_cast<int>(opc - static_cast<long>(oh) * d.w0);
+      pixbase[j] = static_cast<long>(oh) * d.w + ow;
+      s1[j] = s2[j] = 0.0;
+    }
+    Vec8<T> cur[P], nxt[P];
+    uint32_t mcur[P], mnxt[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      cur[j].load(x + pixbase[j] * d.c + lane_in * 8);
+      mcur[j] = mask1 ? mask1[pixbase[j] * lpp + lane_in] : 0xFFu;
+    }
+    for (int n = 0; n < d.n; ++n) {
+      if (n + 1 < d.n) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+          const long pix = static_cast<long>(n + 1) * img_stride + pixbase[j];
+          nxt[j].load(x + pix * d.c + lane_in * 8);
+          mnxt[j] = mask1 ? mask1[pix * lpp + lane_in] : 0xFFu;
         }
       }
+      Coef8 cf;
+      cf.load(coef + static_cast<size_t>(n) * d.c + lane_in * 8);
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        float f[8];
+        cur[j].to_float(f);
+        apply8(f, cf, mcur[j], true);
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dot = fmaf(f[i], wh[i], dot);
+        for (int o = lpp >> 1; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (active[j] && lane_in == 0) {
+          float yv = 1.f / (1.f + expf(-dot));
+          yv = fminf(fmaxf(yv, 0.f), 1.f);
+          if (yv != yv) yv = 0.f;
+          if (logits) logits[static_cast<long>(n) * npix0 + op[j]] = dot;
+          if (out) out[static_cast<long>(n) * npix0 + op[j]] = yv;
+          if (acc) {
+            const float fv = fov ? fov[(d.fov_per_image ? static_cast<long>(n) * npix0 : 0) + op[j]] : 1.f;
+            const float v = yv * fv;
+            s1[j] += static_cast<double>(v);
+            s2[j] += static_cast<double>(v) * static_cast<double>(v);
+            const long long it = base_iter + n;
+            if (samples && it < d.return_num) samples[it * npix0 + op[j]] = v;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        cur[j] = nxt[j];
+        mcur[j] = mnxt[j];
+      }
     }
-    if (acc && active && lane_in == 0) {
-      acc[op] += s1;
-      acc[npix0 + op] += s2;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      if (acc && active[j] && lane_in == 0) {
+        acc[op[j]] += s1[j];
+        acc[npix0 + op[j]] += s2[j];
+      }
     }
   }
 }
@@ -498,7 +589,8 @@ extern "C" int b2u_conv_first_stat_layout(int h, int w, int cout, int num_groups
   B2U_REQUIRE(h > 0 && w > 0 && cout > 0 && cout % 8 == 0 && cout <= 256, "bad shape h=%d w=%d cout=%d", h, w, cout);
   B2U_REQUIRE(num_groups > 0 && cout % num_groups == 0, "cout %d not divisible by groups %d", cout, num_groups);
   const int threads = pick_threads(cout / 8);
-  if (rows_per_image) *rows_per_image = blocks_per_image_for(static_cast<long>(h) * w, threads / (cout / 8));
+  B2U_REQUIRE(w % kFirstStrip == 0, "padded width %d must be a multiple of %d", w, kFirstStrip);
+  if (rows_per_image) *rows_per_image = blocks_per_image_for(static_cast<long>(h) * (w / kFirstStrip), threads / (cout / 8));
   if (subgroup_size) *subgroup_size = stat_sgs(cout, num_groups);
   return B2U_OK;
 }
@@ -536,6 +628,14 @@ extern "C" int b2u_gn_finalize(const float* partials, int rows_per_image, int su
                                const float* beta, float* coef, int n, int c, int num_groups, double count, float eps,
                                const unsigned long long* keep_counts, int images_per_call, double numel_per_call,
                                float* mean_rstd, void* stream) {
+  return b2u_gn_finalize_ex(partials, rows_per_image, subgroup_size, gamma, beta, coef, n, c, num_groups, count, eps,
+                            keep_counts, images_per_call, numel_per_call, mean_rstd, 0, stream);
+}
+
+extern "C" int b2u_gn_finalize_ex(const float* partials, int rows_per_image, int subgroup_size, const float* gamma,
+                                  const float* beta, float* coef, int n, int c, int num_groups, double count, float eps,
+                                  const unsigned long long* keep_counts, int images_per_call, double numel_per_call,
+                                  float* mean_rstd, int shared_partials, void* stream) {
   B2U_REQUIRE(partials && gamma && beta && coef, "null pointer");
   B2U_REQUIRE(n > 0 && c > 0 && num_groups > 0 && c % num_groups == 0, "bad n/c/groups");
   B2U_REQUIRE(subgroup_size > 0 && (c / num_groups) % subgroup_size == 0, "subgroup size %d does not divide group size %d",
@@ -544,7 +644,8 @@ extern "C" int b2u_gn_finalize(const float* partials, int rows_per_image, int su
   dim3 grid(num_groups, n);
   gn_finalize_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       partials, rows_per_image, subgroup_size, gamma, beta, reinterpret_cast<float2*>(coef), c, num_groups, count, eps,
-      keep_counts, images_per_call > 0 ? images_per_call : 1, numel_per_call, reinterpret_cast<float2*>(mean_rstd));
+      keep_counts, images_per_call > 0 ? images_per_call : 1, numel_per_call, reinterpret_cast<float2*>(mean_rstd),
+      shared_partials);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -558,6 +659,7 @@ static int fill_apply(const b2u_apply_desc* d, ApplyParams* p) {
   p->mask2_cstride = d->mask2_cstride; p->mask2_coffset = d->mask2_coffset;
   p->images_per_call2 = d->images_per_call2 > 0 ? d->images_per_call2 : 1;
   p->numel_per_call2 = d->numel_per_call2;
+  p->x_shared = d->reserved[0] == 1 ? 1 : 0;
   return B2U_OK;
 }
 
@@ -595,7 +697,7 @@ extern "C" int b2u_pool_stat_layout(int h, int w, int c, int num_groups, int* ro
   B2U_REQUIRE(c > 0 && c % 8 == 0 && c / 8 <= 256, "bad channel count %d", c);
   B2U_REQUIRE(num_groups > 0 && c % num_groups == 0, "c %d not divisible by groups %d", c, num_groups);
   const int threads = pick_threads(c / 8);
-  if (rows_per_image) *rows_per_image = blocks_per_image_for(static_cast<long>(h / 2) * (w / 2), threads / (c / 8));
+  if (rows_per_image) *rows_per_image = blocks_per_image_for(static_cast<long>(h / 2) * (w / 2), threads / (c / 8) * kPoolUnroll);
   if (subgroup_size) *subgroup_size = stat_sgs(c, num_groups);
   return B2U_OK;
 }
@@ -609,6 +711,7 @@ extern "C" int b2u_gn_apply_pool(const void* x, const float* coef, const uint32_
   if (rc) return rc;
   B2U_REQUIRE(x && coef && pooled, "null pointer");
   B2U_REQUIRE(!mask2 || keep_counts2, "mask2 needs keep counts");
+  B2U_REQUIRE(p.x_shared == 0, "b2u_gn_apply_pool does not support a shared input");
   int rows = 0, sgs = 1;
   rc = b2u_pool_stat_layout(d->h, d->w, d->c, pool_num_groups > 0 ? pool_num_groups : 1, &rows, &sgs);
   if (rc) return rc;
@@ -641,7 +744,7 @@ extern "C" int b2u_head_fwd(const void* x, const float* coef, const uint32_t* ma
   B2U_REQUIRE(d->h0 > 0 && d->w0 > 0 && d->h0 <= d->h && d->w0 <= d->w && d->n > 0, "bad sizes");
   B2U_REQUIRE(out || acc, "nothing to write: out and acc are both NULL");
   const long groups = static_cast<long>(d->h0) * d->w0;
-  const int grid = grid_for(groups * (d->c / 8), 256);
+  const int grid = grid_for((groups + kHeadPix - 1) / kHeadPix * (d->c / 8), 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (d->dtype == B2U_F32)
     head_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), reinterpret_cast<const float2*>(coef),

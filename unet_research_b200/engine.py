@@ -360,15 +360,15 @@ class UNetEngine:
             self.training_weights = True
             self.load_weights(self._sd_ref)
 
-    def _finalize(self, ws, sname, gkey, n, c, hw, masks: Optional[MaskPlan], site: Optional[int]):
+    def _finalize(self, ws, sname, gkey, n, c, hw, masks: Optional[MaskPlan], site: Optional[int], shared: bool = False):
         st = ws.stat[sname]
         count = float((c // self.num_groups) * hw)
         if masks is not None and site is not None:
             keep, ipc, numel = masks.keep_ptr(site), masks.ipc, masks.numel_per_call[site]
         else:
             keep, ipc, numel = None, 1, 0.0
-        call("b2u_gn_finalize", ptr(st.partials), st.rows, st.sgs, ptr(self.w[gkey + ".weight"]), ptr(self.w[gkey + ".bias"]),
-             ptr(st.coef), n, c, self.num_groups, count, GN_EPS, keep, ipc, numel, ptr(st.mr), stream_ptr())
+        call("b2u_gn_finalize_ex", ptr(st.partials), st.rows, st.sgs, ptr(self.w[gkey + ".weight"]), ptr(self.w[gkey + ".bias"]),
+             ptr(st.coef), n, c, self.num_groups, count, GN_EPS, keep, ipc, numel, ptr(st.mr), int(shared), stream_ptr())
 
     def _apply_desc(self, n, h, w, c, relu, out_cstride, out_coffset, masks, site2, m2_cstride=0, m2_coffset=0) -> ApplyDesc:
         a = ApplyDesc()
@@ -385,8 +385,11 @@ class UNetEngine:
 
     # ---- the forward schedule
     def forward(self, x: torch.Tensor, ws: Workspace, masks: Optional[MaskPlan] = None, *, head_out: bool = True,
-                want_logits: bool = False, mc: Optional[dict] = None, argmax: Optional[Dict[int, torch.Tensor]] = None):
+                want_logits: bool = False, mc: Optional[dict] = None, argmax: Optional[Dict[int, torch.Tensor]] = None,
+                shared_input: bool = False):
         """x: fp32 NCHW [n, Cin, h0, w0] on the engine's device (contiguous).  Launches only.
+        shared_input: the n images are the SAME image (Monte-Carlo iterations batched along n): the first conv and
+        its GroupNorm statistics are computed once and shared; only the DropBlock mask / rescale differ per image.
         mc = {"acc": double[2,h0,w0], "fov": float[h0,w0] | None, "samples": float[R,h0,w0] | None,
               "iter_base": int64[1], "return_num": R} switches the head to Monte-Carlo accumulation."""
         n, f, d, G = ws.n, self.filters, self.depth, self.num_groups
@@ -407,13 +410,15 @@ class UNetEngine:
             p = f"down_blocks.{lvl}.0"
             s1, s2, scat = 2 * lvl, 2 * lvl + 1, 2 * d + 2 + 3 * (d - 1 - lvl)
             # conv 1
+            shared = shared_input and lvl == 0
             if lvl == 0:
                 call("b2u_conv_first_fwd", ptr(x), ptr(self.w[p + ".0.weight"]), ptr(B["d0.raw1"]), ptr(ws.stat["d0.c1"].partials),
-                     n, self.init_channels, ws.h0, ws.w0, hh, ww, c, G, self.dtype, st)
+                     1 if shared else n, self.init_channels, ws.h0, ws.w0, hh, ww, c, G, self.dtype, st)
             else:
                 self._conv(ws, f"d{lvl - 1}.pact", p + ".0.weight", f"d{lvl}.raw1", f"d{lvl}.c1", n, hh, ww, c // 2, c)
-            self._finalize(ws, f"d{lvl}.c1", p + ".1", n, c, hh * ww, m, s1)
+            self._finalize(ws, f"d{lvl}.c1", p + ".1", n, c, hh * ww, m, s1, shared=shared)
             a = self._apply_desc(n, hh, ww, c, True, c, 0, None, None)
+            a.reserved[0] = 1 if shared else 0
             call("b2u_gn_apply", ptr(B[f"d{lvl}.raw1"]), ptr(ws.stat[f"d{lvl}.c1"].coef), mptr(s1), None, None,
                  ptr(B[f"d{lvl}.act1"]), C.byref(a), st)
             # conv 2 + pool + skip store

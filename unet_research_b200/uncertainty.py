@@ -108,7 +108,7 @@ class MCRunner:
     # ---- building blocks (all launch-only)
     def _forward(self, k: int):
         m = self.masks[k] if self.active else None
-        self.eng.forward(self.x, self.ws, m, head_out=False, mc=self.mc)
+        self.eng.forward(self.x, self.ws, m, head_out=False, mc=self.mc, shared_input=True)
         call("b2u_advance_counter", ptr(self.iter_base), self.nb, stream_ptr())
 
     def _generate(self, k: int, stride_blocks: int):
