@@ -46,6 +46,10 @@ int b2u_device_info(int* sm_count, int* max_threads_per_sm);
  * transpose_flip != 0 packs the data-gradient operand instead: [9][Cin][Cout] with taps rotated 180. */
 int b2u_pack_conv3x3_weight(const float* w, void* packed, int cout, int cin, int dtype, int transpose_flip,
                             void* stream);
+/* Both layouts in one pass over the fp32 weight (training repacks after every optimiser step); packed_dgrad may be
+ * NULL.  cout and cin must be multiples of 32. */
+int b2u_pack_conv3x3_weight_pair(const float* w, void* packed_fwd, void* packed_dgrad, int cout, int cin, int dtype,
+                                 void* stream);
 /* nn.ConvTranspose2d weight [Cin,Cout,2,2] fp32 -> [4][Cout][Cin] (tap = 2*i+j) in `dtype`. */
 int b2u_pack_convT2x2_weight(const float* w, void* packed, int cin, int cout, int dtype, void* stream);
 

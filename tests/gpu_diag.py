@@ -18,7 +18,7 @@ import traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["info", "conv", "convv1", "convv2", "wgrad", "bwdk", "convt", "first", "gn", "pool", "head", "dropblock", "rotate", "forward", "mc", "rot_ens", "tf32", "train"]
+SECTIONS = ["info", "conv", "convv1", "convv2", "wgrad", "bwdk", "convt", "first", "gn", "pool", "head", "dropblock", "rotate", "forward", "mc", "rot_ens", "tf32", "train", "traingraph"]
 
 
 def rel(a, b):
@@ -733,6 +733,55 @@ def _train_case(h, w, n, dropblock):
     print(f"  train n{n} {h}x{w} dropblock={dropblock}: loss {loss.item():.6f} vs {rloss.item():.6f}; all-grad rel {rel(allg, allr)[0]:.3e}; "
           f"median per-tensor rel {worst[len(worst) // 2][0]:.3e}; worst {[(round(a, 4), b) for a, b in worst[:4]]}")
     return {"loss": loss.item(), "loss_ref": rloss.item(), "grad_rel": rel(allg, allr)[0], "worst": worst[0][0], "median": worst[len(worst) // 2][0]}
+
+
+def _train_graph_case(h, w, n, steps=5):
+    """The CUDA-graph training step (captured after two eager warm-up steps) must reproduce the eager schedule
+    bit for bit: same DropBlock windows (torch generator offsets), same loss, same gradients, for a drop_prob that
+    changes every step (LinearScheduler ramp) and weights that change every step (SGD)."""
+    import torch
+    from torch import nn
+    import unet_research_b200 as U
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    x = synthetic.make_image(h, w, seed=1234, batch=n).to(dev)
+    gt = synthetic.make_gt(h, w, batch=n).to(dev)
+    fov = synthetic.make_fov_mask(h, w, batch=n).to(dev)
+    res = {}
+    for mode in (False, True):
+        m, _ = _build_model(dev, dropblock=True)
+        m.use_cuda_graph = mode
+        m.train()
+        tm = U.BaseUNetTraining(m, nn.BCELoss(), None)
+        opt = torch.optim.SGD(m.parameters(), lr=1e-2, momentum=0.9)
+        torch.manual_seed(777)
+        losses = []
+        for it in range(steps):
+            m._dropblock.drop_prob = 0.05 + 0.02 * it                 # what LinearScheduler.step() does
+            opt.zero_grad(set_to_none=True)
+            loss = tm.training_step((x.clone(), gt, fov), 0)
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        g = torch.cat([p.grad.flatten() for p in m.parameters()]).clone()
+        wv = torch.cat([p.detach().flatten() for p in m.parameters()]).clone()
+        res[mode] = (losses, g, wv, torch.cuda.default_generators[0].get_offset())
+        ws = list(m._engine._workspaces.values())[0]
+        captured = ws.train_step.fwd_graph is not None and ws.train_step.bwd_graphs is not None
+        if mode and not captured:
+            print("  train graph: NOT CAPTURED")
+            return {"ok": False}
+    (l0, g0, w0, o0), (l1, g1, w1, o1) = res[False], res[True]
+    dl = max(abs(a - b) for a, b in zip(l0, l1))
+    dg = float((g0 - g1).abs().max())
+    dw = float((w0 - w1).abs().max())
+    print(f"  train graph n{n} {h}x{w}: losses {['%.5f' % v for v in l1]} max|dloss| {dl:.2e} max|dgrad| {dg:.2e} max|dweight| {dw:.2e} "
+          f"generator offset {o0} vs {o1}")
+    return {"ok": dl == 0.0 and dg == 0.0 and dw == 0.0 and o0 == o1, "dl": dl, "dg": dg}
+
+
+def sec_traingraph():
+    return [_train_graph_case(120, 116, 2), _train_graph_case(584, 565, 1, steps=4)]
 
 
 def sec_train():

@@ -203,6 +203,13 @@ def test_train_step_vs_oracle():
         assert D.rel(dict(m.named_parameters())[k].grad, g_exact[k])[0] < 3e-2
 
 
+def test_train_step_cuda_graph_matches_eager():
+    """The captured training step (forward graph incl. weight repack + mask build, two backward graphs) reproduces
+    the eager launch sequence bit for bit while drop_prob and the weights change every step."""
+    r = D._train_graph_case(120, 116, 2)
+    assert r["ok"], r
+
+
 def test_training_reduces_loss_full_size():
     """BASELINE configs[1]: batch 1, 584x565, DropBlock bs 7 p .15, SGD(momentum .99) + clip .5: the loss goes down."""
     import unet_research_b200 as U

@@ -69,6 +69,7 @@ SIGNATURES = {
     "b2u_version": (_I, []),
     "b2u_device_info": (_I, [C.POINTER(_I), C.POINTER(_I)]),
     "b2u_pack_conv3x3_weight": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "b2u_pack_conv3x3_weight_pair": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "b2u_pack_convT2x2_weight": (_I, [_P, _P, _I, _I, _I, _P]),
     "b2u_conv3x3_stat_layout": (_I, [C.POINTER(ConvDesc), C.POINTER(_I), C.POINTER(_I)]),
     "b2u_convT2x2_stat_layout": (_I, [C.POINTER(ConvDesc), C.POINTER(_I), C.POINTER(_I)]),
@@ -106,7 +107,7 @@ _LAUNCHERS = {"b2u_conv3x3_fwd": 1, "b2u_convT2x2_fwd": 1, "b2u_conv_first_fwd":
               "b2u_gn_apply": 1, "b2u_gn_apply_pool": 1, "b2u_head_fwd": 1, "b2u_mc_finalize": 1,
               "b2u_mc_accumulate": 1, "b2u_advance_counter": 1, "b2u_dropblock_centers": 1,
               "b2u_dropblock_dilate": 1, "b2u_dropblock_centers_from_uniform": 1, "b2u_rotate_bilinear": 1,
-              "b2u_pack_conv3x3_weight": 1, "b2u_pack_convT2x2_weight": 1, "b2u_unit_bwd_stats": 1, "b2u_unit_bwd_finalize": 2,
+              "b2u_pack_conv3x3_weight": 1, "b2u_pack_conv3x3_weight_pair": 1, "b2u_pack_convT2x2_weight": 1, "b2u_unit_bwd_stats": 1, "b2u_unit_bwd_finalize": 2,
               "b2u_unit_bwd_apply": 1, "b2u_wgrad": 2, "b2u_wgrad_first": 2, "b2u_gemm1x1_fwd": 1,
               "b2u_pack_convT2x2_dgrad_weight": 1}
 

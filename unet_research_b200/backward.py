@@ -54,6 +54,32 @@ class TrainBuffers:
         self.wg_ws: Optional[torch.Tensor] = None
         self.reducer: Optional["GradReducer"] = None
         self.first_ws = torch.empty(n * 64 * f * eng.init_channels * 9, dtype=torch.float32, device=dev)
+        self.flat: Optional[torch.Tensor] = None        # all parameter gradients in ONE fp32 buffer (named_parameters order)
+        self.gviews: Dict[str, torch.Tensor] = {}
+        self.goffsets: Dict[str, int] = {}
+
+    def bind_parameters(self, named_shapes):
+        """Lay the gradients out in one flat buffer, `named_parameters()` order, every tensor 256-byte aligned:
+        one NCCL all-reduce (or two, split at the encoder/decoder boundary) and one fused optimiser pass cover them."""
+        if self.flat is not None and list(self.gviews.keys()) == [k for k, _ in named_shapes]:
+            return
+        off = 0
+        offs = []
+        for k, shape in named_shapes:
+            numel = 1
+            for v in shape:
+                numel *= int(v)
+            offs.append((k, tuple(shape), off, numel))
+            off += (numel + 63) // 64 * 64
+        self.flat = torch.zeros(off, dtype=torch.float32, device=self.gY[0].device)
+        self.gviews = {k: self.flat[o:o + nel].view(shape) for k, shape, o, nel in offs}
+        self.goffsets = {k: o for k, _, o, _ in offs}
+
+    def grad(self, key: str, shape) -> torch.Tensor:
+        v = self.gviews.get(key)
+        if v is not None:
+            return v.view(shape)
+        return torch.empty(shape, dtype=torch.float32, device=self.gY[0].device)
 
     def wgrad_workspace(self, floats: int, dev) -> torch.Tensor:
         if self.wg_ws is None or self.wg_ws.numel() < floats:
@@ -89,12 +115,12 @@ def _unit_bwd(eng: UNetEngine, ws: Workspace, tb: TrainBuffers, grads: Dict[str,
     if head is not None:
         go, out, whkey, h0, w0 = head
         d.grad_out, d.out, d.w_head, d.h0, d.w0 = ptr(go), ptr(out), ptr(eng.w[whkey]), h0, w0
-        dwh = torch.empty(c, dtype=torch.float32, device=eng.device)
+        dwh = tb.grad(whkey, (c,))
         grads[whkey] = dwh
     rows = C.c_int(0)
     call("b2u_unit_bwd_rows", h, w, c, C.byref(rows))
-    dgamma = torch.empty(c, dtype=torch.float32, device=eng.device)
-    dbeta = torch.empty(c, dtype=torch.float32, device=eng.device)
+    dgamma = tb.grad(gkey + ".weight", (c,))
+    dbeta = tb.grad(gkey + ".bias", (c,))
     grads[gkey + ".weight"], grads[gkey + ".bias"] = dgamma, dbeta
     sp = stream_ptr()
     call("b2u_unit_bwd_stats", C.byref(d), ptr(tb.partials), sp)
@@ -145,7 +171,7 @@ def _wgrad(eng, tb, grads, key, g: torch.Tensor, x: torch.Tensor, n, h, w, cg, c
     fl = C.c_longlong(0)
     call("b2u_wgrad_workspace_floats", C.byref(d), C.byref(fl))
     wsb = tb.wgrad_workspace(fl.value, eng.device)
-    dw = torch.empty(shape, dtype=torch.float32, device=eng.device)
+    dw = tb.grad(key, shape)
     call("b2u_wgrad", ptr(g), ptr(x), ptr(wsb), ptr(dw), C.byref(d), stream_ptr())
     grads[key] = dw
     if tb.reducer is not None:
@@ -160,9 +186,12 @@ def _dgrad3x3(eng, key, g: torch.Tensor, out: torch.Tensor, n, h, w, cout_fwd, c
 
 
 def unet_backward(eng: UNetEngine, ws: Workspace, tb: TrainBuffers, masks: Optional[MaskPlan], xin: torch.Tensor,
-                  out: torch.Tensor, grad_out: torch.Tensor, data_parallel: bool = False) -> Dict[str, torch.Tensor]:
+                  out: torch.Tensor, grad_out: torch.Tensor, data_parallel: bool = False,
+                  phase: Optional[int] = None) -> Dict[str, torch.Tensor]:
     """Returns {state-dict key: fp32 gradient in the PyTorch parameter layout}.  Launches only (plus, with
-    data_parallel, NCCL all-reduces overlapped with the remaining backward kernels)."""
+    data_parallel, NCCL all-reduces overlapped with the remaining backward kernels).
+    phase: None = everything; 0 = head + decoder + bottleneck; 1 = encoder (the two CUDA-graph segments of
+    training.TrainStep: the decoder-side gradients travel over NVLink while the encoder segment runs)."""
     tb.reducer = GradReducer() if data_parallel else None
     n, f, dpt = ws.n, eng.filters, eng.depth
     B = ws.buf
@@ -173,7 +202,7 @@ def unet_backward(eng: UNetEngine, ws: Workspace, tb: TrainBuffers, masks: Optio
 
     # ---------------- decoder, last level first
     c = f
-    for u in range(dpt - 1, -1, -1):
+    for u in (range(dpt - 1, -1, -1) if phase in (None, 0) else ()):
         lvl = dpt - 1 - u
         c = f << lvl
         hh, ww = ws.h >> lvl, ws.w >> lvl
@@ -207,17 +236,18 @@ def unet_backward(eng: UNetEngine, ws: Workspace, tb: TrainBuffers, masks: Optio
     # ---------------- bottleneck
     c = f << dpt
     hh, ww = ws.h >> dpt, ws.w >> dpt
-    _unit_bwd(eng, ws, tb, grads, n=n, h=hh, w=ww, c=c, yname="b.raw2", sname="b.c2", gkey="conn_block.5", relu=True, masks=m,
-              site=2 * dpt + 1, dy=tb.gY[dpt], grad_a=(tb.gA[dpt], c, 0))
-    _wgrad(eng, tb, grads, "conn_block.4.weight", tb.gY[dpt], B["b.act1"], n, hh, ww, c, c, c, 9, 0, (c, c, 3, 3))
-    _dgrad3x3(eng, "conn_block.4.weight", tb.gY[dpt], tb.gA[dpt], n, hh, ww, c, c)
-    _unit_bwd(eng, ws, tb, grads, n=n, h=hh, w=ww, c=c, yname="b.raw1", sname="b.c1", gkey="conn_block.1", relu=True, masks=m,
-              site=2 * dpt, dy=tb.gY[dpt], grad_a=(tb.gA[dpt], c, 0))
-    _wgrad(eng, tb, grads, "conn_block.0.weight", tb.gY[dpt], B[f"d{dpt - 1}.pact"], n, hh, ww, c, c // 2, c // 2, 9, 0, (c, c // 2, 3, 3))
-    _dgrad3x3(eng, "conn_block.0.weight", tb.gY[dpt], tb.gPA[dpt - 1], n, hh, ww, c, c // 2)
+    if phase in (None, 0):
+        _unit_bwd(eng, ws, tb, grads, n=n, h=hh, w=ww, c=c, yname="b.raw2", sname="b.c2", gkey="conn_block.5", relu=True, masks=m,
+                  site=2 * dpt + 1, dy=tb.gY[dpt], grad_a=(tb.gA[dpt], c, 0))
+        _wgrad(eng, tb, grads, "conn_block.4.weight", tb.gY[dpt], B["b.act1"], n, hh, ww, c, c, c, 9, 0, (c, c, 3, 3))
+        _dgrad3x3(eng, "conn_block.4.weight", tb.gY[dpt], tb.gA[dpt], n, hh, ww, c, c)
+        _unit_bwd(eng, ws, tb, grads, n=n, h=hh, w=ww, c=c, yname="b.raw1", sname="b.c1", gkey="conn_block.1", relu=True, masks=m,
+                  site=2 * dpt, dy=tb.gY[dpt], grad_a=(tb.gA[dpt], c, 0))
+        _wgrad(eng, tb, grads, "conn_block.0.weight", tb.gY[dpt], B[f"d{dpt - 1}.pact"], n, hh, ww, c, c // 2, c // 2, 9, 0, (c, c // 2, 3, 3))
+        _dgrad3x3(eng, "conn_block.0.weight", tb.gY[dpt], tb.gPA[dpt - 1], n, hh, ww, c, c // 2)
 
     # ---------------- encoder, deepest level first
-    for lvl in range(dpt - 1, -1, -1):
+    for lvl in (range(dpt - 1, -1, -1) if phase in (None, 1) else ()):
         c = f << lvl
         hh, ww = ws.h >> lvl, ws.w >> lvl
         s1, s2, scat = 2 * lvl, 2 * lvl + 1, 2 * dpt + 2 + 3 * (dpt - 1 - lvl)
@@ -238,11 +268,12 @@ def unet_backward(eng: UNetEngine, ws: Workspace, tb: TrainBuffers, masks: Optio
             _wgrad(eng, tb, grads, p + ".0.weight", tb.gY[lvl], B[f"d{lvl - 1}.pact"], n, hh, ww, c, c // 2, c // 2, 9, 0, (c, c // 2, 3, 3))
             _dgrad3x3(eng, p + ".0.weight", tb.gY[lvl], tb.gPA[lvl - 1], n, hh, ww, c, c // 2)
         else:
-            dw = torch.empty(c, eng.init_channels, 3, 3, dtype=torch.float32, device=eng.device)
+            dw = tb.grad(p + ".0.weight", (c, eng.init_channels, 3, 3))
             call("b2u_wgrad_first", ptr(tb.gY[0]), ptr(xin), ptr(tb.first_ws), ptr(dw), n, eng.init_channels, ws.h0, ws.w0, hh, ww, c,
                  eng.dtype, stream_ptr())
             grads[p + ".0.weight"] = dw
-    grads["output_conv.0.weight"] = grads["output_conv.0.weight"].view(1, f, 1, 1)
+    if "output_conv.0.weight" in grads:
+        grads["output_conv.0.weight"] = grads["output_conv.0.weight"].view(1, f, 1, 1)
     if tb.reducer is not None:
         tb.reducer.finish(grads)
         tb.last_allreduce_bytes = tb.reducer.bytes

@@ -68,7 +68,7 @@ __device__ __forceinline__ void load8f(const T* p, float (&f)[8]) {
 template <typename T>
 __device__ __forceinline__ void unit_grad8(const UnitBwdParams& p, const UnitBwdPtrs& q, int n, int hh, int ww, int cv,
                                            const float (&a)[8], const float (&b)[8], float mean, float rstd, float s1, float s2,
-                                           const float (&wh)[8], float (&dz)[8], float (&xhat)[8], float (&act)[8], float& dlogit) {
+                                           float (&dz)[8], float (&xhat)[8], float (&act)[8], float& dlogit) {
   const long pix = (static_cast<long>(n) * p.h + hh) * p.w + ww;
   float yv[8];
   load8f(reinterpret_cast<const T*>(q.y) + pix * p.c + cv * 8, yv);
@@ -105,8 +105,10 @@ __device__ __forceinline__ void unit_grad8(const UnitBwdParams& p, const UnitBwd
       const float o = q.out[op];
       dlogit = q.grad_out[op] * o * (1.f - o);
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] += dlogit * wh[i];
+    const float4 wa = __ldg(reinterpret_cast<const float4*>(q.w_head + cv * 8));
+    const float4 wb = __ldg(reinterpret_cast<const float4*>(q.w_head + cv * 8 + 4));
+    g[0] += dlogit * wa.x; g[1] += dlogit * wa.y; g[2] += dlogit * wa.z; g[3] += dlogit * wa.w;
+    g[4] += dlogit * wb.x; g[5] += dlogit * wb.y; g[6] += dlogit * wb.z; g[7] += dlogit * wb.w;
   }
   const uint32_t m1 = q.mask1 ? q.mask1[pix * (p.c >> 3) + cv] : 0xFFu;
 #pragma unroll
@@ -121,8 +123,10 @@ __device__ __forceinline__ void unit_grad8(const UnitBwdParams& p, const UnitBwd
 }
 
 // grid = (rows, n); thread owns channel vector t % cvs; deterministic block reduction to partials[n][row][c][3]
-template <typename T>
-__global__ void __launch_bounds__(256) unit_bwd_stats_kernel(UnitBwdParams p, UnitBwdPtrs q) {
+// GPV = GroupNorm groups per 8-channel vector (1 when the group size is >= 8, else 8 / group size): the per-group
+// (mean, rstd[, c1, c2]) live in GPV registers each instead of 8.
+template <typename T, int GPV>
+__global__ void __launch_bounds__(256, 3) unit_bwd_stats_kernel(UnitBwdParams p, UnitBwdPtrs q) {
   extern __shared__ float sm[];
   const int n = blockIdx.y;
   const int cvs = p.c >> 3;
@@ -130,7 +134,8 @@ __global__ void __launch_bounds__(256) unit_bwd_stats_kernel(UnitBwdParams p, Un
   const int slot = threadIdx.x / cvs;
   const int slots = blockDim.x / cvs;
   const int gsize = p.c / p.num_groups;
-  float a[8], b[8], wh[8];
+  constexpr int CPG = 8 / GPV;                                  // channels of the vector per group slot
+  float a[8], b[8];
   {
     const float4* cp = reinterpret_cast<const float4*>(q.coef + static_cast<size_t>(n) * p.c + cv * 8);
 #pragma unroll
@@ -138,17 +143,14 @@ __global__ void __launch_bounds__(256) unit_bwd_stats_kernel(UnitBwdParams p, Un
       const float4 t = __ldg(cp + i);
       a[2 * i] = t.x; b[2 * i] = t.y; a[2 * i + 1] = t.z; b[2 * i + 1] = t.w;
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) wh[i] = q.w_head ? __ldg(q.w_head + cv * 8 + i) : 0.f;
   }
-  // all 8 channels of a vector lie in one group when gsize >= 8; otherwise per-channel (mean, rstd)
   float s1 = 1.f, s2 = 1.f;
   if (q.keep1) s1 = static_cast<float>(p.numel_per_call1 / static_cast<double>(q.keep1[n / p.images_per_call1]));
   if (q.mask2) s2 = static_cast<float>(p.numel_per_call2 / static_cast<double>(q.keep2[n / p.images_per_call2]));
-  float mean8[8], rstd8[8];
+  float mean8[GPV], rstd8[GPV];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float2 t = __ldg(q.mr + static_cast<size_t>(n) * p.num_groups + (cv * 8 + i) / gsize);
+  for (int i = 0; i < GPV; ++i) {
+    const float2 t = __ldg(q.mr + static_cast<size_t>(n) * p.num_groups + (cv * 8 + i * CPG) / gsize);
     mean8[i] = t.x;
     rstd8[i] = t.y;
   }
@@ -160,10 +162,10 @@ __global__ void __launch_bounds__(256) unit_bwd_stats_kernel(UnitBwdParams p, Un
     const int hh = pix / p.w, ww = pix - hh * p.w;
     float dz[8], xhat[8], act[8], dlogit;
     // per-channel mean/rstd: pass channel 0's and fix up below (gsize < 8 only happens for C = 64, 128)
-    unit_grad8<T>(p, q, n, hh, ww, cv, a, b, 0.f, 1.f, s1, s2, wh, dz, xhat, act, dlogit);
+    unit_grad8<T>(p, q, n, hh, ww, cv, a, b, 0.f, 1.f, s1, s2, dz, xhat, act, dlogit);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float xh = (xhat[i] - mean8[i]) * rstd8[i];         // xhat[] holds raw y here (mean 0, rstd 1 above)
+      const float xh = (xhat[i] - mean8[i / CPG]) * rstd8[i / CPG];   // xhat[] holds raw y here (mean 0, rstd 1 above)
       acc1[i] += dz[i];
       acc2[i] += dz[i] * xh;
       acc3[i] += dlogit * act[i];
@@ -188,71 +190,88 @@ __global__ void __launch_bounds__(256) unit_bwd_stats_kernel(UnitBwdParams p, Un
   }
 }
 
-// grid = (num_groups, n) for the per-group coefficients, then a second launch shape for dgamma/dbeta; kept as two
-// kernels for clarity.
-__global__ void bwd_group_coef_kernel(const float* __restrict__ partials, int rows, int c, int num_groups,
-                                      const float* __restrict__ gamma, double count, float2* __restrict__ gcoef) {
-  const int g = blockIdx.x, n = blockIdx.y;
+// One block per GroupNorm group reduces the partial rows of every image (fp64, fixed order => deterministic):
+//   per (image, group):  c1 = sum_c gamma_c P1 / cnt,  c2 = sum_c gamma_c P2 / cnt     -> gcoef[n][g]
+//   per channel:         dbeta = sum_n P1, dgamma = sum_n P2, dw_head = sum_n P3
+// A partial row holds the group's gsize*3 floats contiguously; a warp covers 32/(gsize*3) rows per trip when the
+// group is narrow (C = 64: 6 floats per row) so the loads stay coalesced and every lane has work.
+constexpr int kBwdFinWarps = 16;
+__global__ void __launch_bounds__(kBwdFinWarps * 32) bwd_finalize_kernel(const float* __restrict__ partials, int n, int rows, int c,
+                                                                       int num_groups, const float* __restrict__ gamma, double count,
+                                                                       float2* __restrict__ gcoef, float* __restrict__ dgamma,
+                                                                       float* __restrict__ dbeta, float* __restrict__ dw_head) {
+  const int g = blockIdx.x;
   const int gsize = c / num_groups;
-  const float* base = partials + static_cast<size_t>(n) * rows * c * 3;
-  double s1 = 0.0, s2 = 0.0;
-  for (int i = threadIdx.x; i < rows * gsize; i += blockDim.x) {
-    const int r = i / gsize, k = i - r * gsize;
-    const int ch = g * gsize + k;
-    const float* pp = base + (static_cast<size_t>(r) * c + ch) * 3;
-    const double gm = static_cast<double>(gamma[ch]);
-    s1 += gm * static_cast<double>(pp[0]);
-    s2 += gm * static_cast<double>(pp[1]);
-  }
-  __shared__ double sh[2][128];
-  sh[0][threadIdx.x] = s1;
-  sh[1][threadIdx.x] = s2;
-  __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
-      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+  const int E = gsize * 3;                                   // floats of this group in one partial row
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rpw = E <= 32 ? 32 / E : 1;                      // rows per warp trip
+  const int nj = E <= 32 ? 1 : (E + 31) / 32;                // 32-float chunks per row (<= 3 for gsize <= 32)
+  const int rsub = E <= 32 ? lane / E : 0;
+  const int e0 = E <= 32 ? lane - rsub * E : lane;
+  const bool lane_on = E <= 32 ? (rsub < rpw) : true;
+  __shared__ double red[kBwdFinWarps][32][3];
+  __shared__ double tot[96];                                 // per (channel, stat) sums over the images
+  for (int i = threadIdx.x; i < 96; i += blockDim.x) tot[i] = 0.0;
+  for (int img = 0; img < n; ++img) {
+    const float* base = partials + (static_cast<size_t>(img) * rows * c + static_cast<size_t>(g) * gsize) * 3;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int r = warp * rpw + rsub; r < rows; r += kBwdFinWarps * rpw) {
+      if (lane_on) {
+        const float* rowp = base + static_cast<size_t>(r) * c * 3;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          if (j < nj && e0 + 32 * j < E) acc[j] += static_cast<double>(rowp[e0 + 32 * j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) red[warp][lane][j] = acc[j];
+    __syncthreads();
+    // element e of the row = (channel e / 3, stat e % 3)
+    if (threadIdx.x < E) {
+      const int e = threadIdx.x;
+      double sum = 0.0;
+      if (E <= 32) {
+        for (int w = 0; w < kBwdFinWarps; ++w)
+          for (int rs = 0; rs < rpw; ++rs) sum += red[w][rs * E + e][0];
+      } else {
+        for (int w = 0; w < kBwdFinWarps; ++w) sum += red[w][e & 31][e >> 5];
+      }
+      red[0][0][0] = red[0][0][0];                           // (keeps the compiler from hoisting across the barrier)
+      tot[e] += sum;
+      // stash this image's per-element sums for the group coefficients
+      reinterpret_cast<double*>(red)[kBwdFinWarps * 96 - 96 + e] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const double* cur = reinterpret_cast<double*>(red) + kBwdFinWarps * 96 - 96;
+      double s1 = 0.0, s2 = 0.0;
+      for (int k = 0; k < gsize; ++k) {
+        const double gm = static_cast<double>(gamma[g * gsize + k]);
+        s1 += gm * cur[k * 3];
+        s2 += gm * cur[k * 3 + 1];
+      }
+      gcoef[static_cast<size_t>(img) * num_groups + g] = make_float2(static_cast<float>(s1 / count), static_cast<float>(s2 / count));
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) gcoef[static_cast<size_t>(n) * num_groups + g] = make_float2(static_cast<float>(sh[0][0] / count), static_cast<float>(sh[1][0] / count));
-}
-
-// one block per channel: dgamma[c] = sum_{n,rows} P2, dbeta[c] = sum P1, dw_head[c] = sum P3
-__global__ void bwd_param_grad_kernel(const float* __restrict__ partials, int n, int rows, int c, float* __restrict__ dgamma,
-                                      float* __restrict__ dbeta, float* __restrict__ dw_head) {
-  const int ch = blockIdx.x;
-  double s[3] = {0.0, 0.0, 0.0};
-  for (int i = threadIdx.x; i < n * rows; i += blockDim.x) {
-    const float* pp = partials + (static_cast<size_t>(i) * c + ch) * 3;
-    s[0] += pp[0];
-    s[1] += pp[1];
-    s[2] += pp[2];
-  }
-  __shared__ double sh[3][128];
-  for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] = s[k];
-  __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (threadIdx.x < o)
-      for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    if (dbeta) dbeta[ch] = static_cast<float>(sh[0][0]);
-    if (dgamma) dgamma[ch] = static_cast<float>(sh[1][0]);
-    if (dw_head) dw_head[ch] = static_cast<float>(sh[2][0]);
+  if (threadIdx.x < gsize) {
+    const int ch = g * gsize + threadIdx.x;
+    if (dbeta) dbeta[ch] = static_cast<float>(tot[threadIdx.x * 3]);
+    if (dgamma) dgamma[ch] = static_cast<float>(tot[threadIdx.x * 3 + 1]);
+    if (dw_head) dw_head[ch] = static_cast<float>(tot[threadIdx.x * 3 + 2]);
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) unit_bwd_apply_kernel(UnitBwdParams p, UnitBwdPtrs q) {
+template <typename T, int GPV>
+__global__ void __launch_bounds__(256, 3) unit_bwd_apply_kernel(UnitBwdParams p, UnitBwdPtrs q) {
   const int n = blockIdx.y;
   const int cvs = p.c >> 3;
   const int cv = threadIdx.x % cvs;
   const int slot = threadIdx.x / cvs;
   const int slots = blockDim.x / cvs;
   const int gsize = p.c / p.num_groups;
-  float a[8], b[8], wh[8], gm[8];
+  constexpr int CPG = 8 / GPV;
+  float a[8], b[8], gm[8];
   {
     const float4* cp = reinterpret_cast<const float4*>(q.coef + static_cast<size_t>(n) * p.c + cv * 8);
 #pragma unroll
@@ -261,18 +280,15 @@ __global__ void __launch_bounds__(256) unit_bwd_apply_kernel(UnitBwdParams p, Un
       a[2 * i] = t.x; b[2 * i] = t.y; a[2 * i + 1] = t.z; b[2 * i + 1] = t.w;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      wh[i] = q.w_head ? __ldg(q.w_head + cv * 8 + i) : 0.f;
-      gm[i] = __ldg(q.gamma + cv * 8 + i);
-    }
+    for (int i = 0; i < 8; ++i) gm[i] = __ldg(q.gamma + cv * 8 + i);
   }
   float s1 = 1.f, s2 = 1.f;
   if (q.keep1) s1 = static_cast<float>(p.numel_per_call1 / static_cast<double>(q.keep1[n / p.images_per_call1]));
   if (q.mask2) s2 = static_cast<float>(p.numel_per_call2 / static_cast<double>(q.keep2[n / p.images_per_call2]));
-  float mean8[8], rstd8[8], c1[8], c2[8];
+  float mean8[GPV], rstd8[GPV], c1[GPV], c2[GPV];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int g = (cv * 8 + i) / gsize;
+  for (int i = 0; i < GPV; ++i) {
+    const int g = (cv * 8 + i * CPG) / gsize;
     const float2 t = __ldg(q.mr + static_cast<size_t>(n) * p.num_groups + g);
     const float2 u = __ldg(q.gcoef + static_cast<size_t>(n) * p.num_groups + g);
     mean8[i] = t.x; rstd8[i] = t.y; c1[i] = u.x; c2[i] = u.y;
@@ -282,12 +298,12 @@ __global__ void __launch_bounds__(256) unit_bwd_apply_kernel(UnitBwdParams p, Un
   for (int pix = blockIdx.x * slots + slot; pix < npix; pix += gridDim.x * slots) {
     const int hh = pix / p.w, ww = pix - hh * p.w;
     float dz[8], xhat[8], act[8], dlogit;
-    unit_grad8<T>(p, q, n, hh, ww, cv, a, b, 0.f, 1.f, s1, s2, wh, dz, xhat, act, dlogit);
+    unit_grad8<T>(p, q, n, hh, ww, cv, a, b, 0.f, 1.f, s1, s2, dz, xhat, act, dlogit);
     float o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float xh = (xhat[i] - mean8[i]) * rstd8[i];
-      o[i] = rstd8[i] * (gm[i] * dz[i] - c1[i] - xh * c2[i]);
+      const float xh = (xhat[i] - mean8[i / CPG]) * rstd8[i / CPG];
+      o[i] = rstd8[i / CPG] * (gm[i] * dz[i] - c1[i / CPG] - xh * c2[i / CPG]);
     }
     long dst;
     if (p.s2d) {
@@ -366,8 +382,18 @@ extern "C" int b2u_unit_bwd_stats(const b2u_unit_bwd_desc* d, float* partials, v
   dim3 grid(p.rows, d->n);
   const size_t smem = static_cast<size_t>(threads) * 24 * sizeof(float);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (d->dtype == B2U_F32) unit_bwd_stats_kernel<float><<<grid, threads, smem, st>>>(p, q);
-  else unit_bwd_stats_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(p, q);
+  const int gsize = d->c / d->num_groups;
+  const int gpv = gsize >= 8 ? 1 : 8 / gsize;
+  B2U_REQUIRE(gpv == 1 || gpv == 2 || gpv == 4, "group size %d must be 2, 4 or a multiple of 8", gsize);
+#define B2U_STATS(T)                                                                  \
+  do {                                                                                \
+    if (gpv == 1) unit_bwd_stats_kernel<T, 1><<<grid, threads, smem, st>>>(p, q);      \
+    else if (gpv == 2) unit_bwd_stats_kernel<T, 2><<<grid, threads, smem, st>>>(p, q); \
+    else unit_bwd_stats_kernel<T, 4><<<grid, threads, smem, st>>>(p, q);               \
+  } while (0)
+  if (d->dtype == B2U_F32) B2U_STATS(float);
+  else B2U_STATS(__nv_bfloat16);
+#undef B2U_STATS
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -375,14 +401,11 @@ extern "C" int b2u_unit_bwd_stats(const b2u_unit_bwd_desc* d, float* partials, v
 extern "C" int b2u_unit_bwd_finalize(const float* partials, int n, int rows_per_image, int c, int num_groups, const float* gamma,
                                      double count, float* group_coef, float* dgamma, float* dbeta, float* dw_head, void* stream) {
   B2U_REQUIRE(partials && gamma && group_coef && n > 0 && c > 0 && num_groups > 0 && c % num_groups == 0, "bad arguments");
+  B2U_REQUIRE(c / num_groups <= 32, "group size %d > 32 is not supported by the backward finalise", c / num_groups);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  bwd_group_coef_kernel<<<dim3(num_groups, n), 128, 0, st>>>(partials, rows_per_image, c, num_groups, gamma, count,
-                                                            reinterpret_cast<float2*>(group_coef));
+  bwd_finalize_kernel<<<num_groups, kBwdFinWarps * 32, 0, st>>>(partials, n, rows_per_image, c, num_groups, gamma, count,
+                                                              reinterpret_cast<float2*>(group_coef), dgamma, dbeta, dw_head);
   B2U_LAUNCH_CHECK();
-  if (dgamma || dbeta || dw_head) {
-    bwd_param_grad_kernel<<<c, 128, 0, st>>>(partials, n, rows_per_image, c, dgamma, dbeta, dw_head);
-    B2U_LAUNCH_CHECK();
-  }
   return B2U_OK;
 }
 
@@ -402,8 +425,18 @@ extern "C" int b2u_unit_bwd_apply(const b2u_unit_bwd_desc* d, const float* group
   if (bpi > cap) bpi = cap;
   dim3 grid(static_cast<unsigned>(bpi), d->n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (d->dtype == B2U_F32) unit_bwd_apply_kernel<float><<<grid, threads, 0, st>>>(p, q);
-  else unit_bwd_apply_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(p, q);
+  const int gsize = d->c / d->num_groups;
+  const int gpv = gsize >= 8 ? 1 : 8 / gsize;
+  B2U_REQUIRE(gpv == 1 || gpv == 2 || gpv == 4, "group size %d must be 2, 4 or a multiple of 8", gsize);
+#define B2U_APPLY(T)                                                               \
+  do {                                                                             \
+    if (gpv == 1) unit_bwd_apply_kernel<T, 1><<<grid, threads, 0, st>>>(p, q);      \
+    else if (gpv == 2) unit_bwd_apply_kernel<T, 2><<<grid, threads, 0, st>>>(p, q); \
+    else unit_bwd_apply_kernel<T, 4><<<grid, threads, 0, st>>>(p, q);               \
+  } while (0)
+  if (d->dtype == B2U_F32) B2U_APPLY(float);
+  else B2U_APPLY(__nv_bfloat16);
+#undef B2U_APPLY
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -444,6 +444,29 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, T* __restrict__
     out[i] = to_operand<T>(w[(static_cast<long>(co) * cin + ci) * 9 + src_tap]);
   }
 }
+// Both packed layouts of one 3x3 weight in a single pass (training: the weights change every optimiser step).
+// A block stages a 32 (co) x 32 (ci) x 9 tile through shared memory: the fp32 source is read once, fully
+// coalesced (288 contiguous floats per output channel), and both destinations are written as 64-byte runs:
+//   fwd  [tap][co][ci]      dgrad [8 - tap][ci][co]   (transposed, taps rotated by 180 degrees).
+template <typename T>
+__global__ void __launch_bounds__(256) pack_conv3x3_pair_kernel(const float* __restrict__ w, T* __restrict__ fwd, T* __restrict__ dgrad,
+                                                                int cout, int cin) {
+  __shared__ T tile[9][32][33];
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  for (int f = threadIdx.x; f < 32 * 288; f += 256) {
+    const int co_l = f / 288, rem = f - co_l * 288;
+    const int ci_l = rem / 9, tap = rem - ci_l * 9;
+    tile[tap][co_l][ci_l] = to_operand<T>(w[(static_cast<long>(co0 + co_l) * cin + ci0) * 9 + rem]);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  for (int r = wrp; r < 9 * 32; r += 8) {
+    const int tap = r >> 5, row = r & 31;
+    fwd[(static_cast<long>(tap) * cout + co0 + row) * cin + ci0 + lane] = tile[tap][row][lane];
+    if (dgrad) dgrad[(static_cast<long>(8 - tap) * cin + ci0 + row) * cout + co0 + lane] = tile[tap][lane][row];
+  }
+}
+
 template <typename T>
 __global__ void pack_convT_kernel(const float* __restrict__ w, T* __restrict__ out, int cin, int cout) {
   long total = 4L * cout * cin;     // out[tap][co][ci] = w[ci][co][tap]
@@ -502,6 +525,20 @@ extern "C" int b2u_pack_conv3x3_weight(const float* w, void* packed, int cout, i
   int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   if (dtype == B2U_F32) pack_conv3x3_kernel<float><<<blocks, 256, 0, st>>>(w, static_cast<float*>(packed), cout, cin, transpose_flip);
   else pack_conv3x3_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(packed), cout, cin, transpose_flip);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+extern "C" int b2u_pack_conv3x3_weight_pair(const float* w, void* packed_fwd, void* packed_dgrad, int cout, int cin, int dtype,
+                                            void* stream) {
+  B2U_REQUIRE(w && packed_fwd && cout > 0 && cin > 0, "bad arguments");
+  B2U_REQUIRE(cout % 32 == 0 && cin % 32 == 0, "pair packing needs cout and cin to be multiples of 32 (got %d, %d)", cout, cin);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(cin / 32, cout / 32);
+  if (dtype == B2U_F32)
+    pack_conv3x3_pair_kernel<float><<<grid, 256, 0, st>>>(w, static_cast<float*>(packed_fwd), static_cast<float*>(packed_dgrad), cout, cin);
+  else
+    pack_conv3x3_pair_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(packed_fwd),
+                                                                   static_cast<__nv_bfloat16*>(packed_dgrad), cout, cin);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

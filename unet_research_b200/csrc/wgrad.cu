@@ -186,6 +186,43 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
   }
 }
 
+// layout 0 with 9 taps: one thread per (cg, cx) pair sums the slices of all nine taps (reads coalesced along cx)
+// and writes its nine taps as one 36-byte run, so a warp writes 1152 contiguous bytes of the PyTorch layout.
+__global__ void __launch_bounds__(256) wgrad_reduce9_kernel(const float* __restrict__ ws, float* __restrict__ dw, int slices, int cg, int cx) {
+  // blockDim = (32 pairs, SG slice groups): slice group y sums slices y, y + SG, ...; the groups are then added in a
+  // fixed order through shared memory (deterministic), and thread (x, 0) writes the nine taps.
+  __shared__ float part[8][32][9];
+  const long pairs = static_cast<long>(cg) * cx;
+  const long total = 9 * pairs;
+  const long i = blockIdx.x * 32L + threadIdx.x;
+  const int sg = threadIdx.y, nsg = blockDim.y;
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  if (i < pairs) {
+    for (int s = sg; s < slices; s += nsg) {
+      const float* src = ws + static_cast<long>(s) * total + i;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[t] += src[t * pairs];
+    }
+  }
+  if (nsg > 1) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) part[sg][threadIdx.x][t] = acc[t];
+    __syncthreads();
+    if (sg == 0) {
+      for (int y = 1; y < nsg; ++y)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[t] += part[y][threadIdx.x][t];
+    }
+  }
+  if (sg == 0 && i < pairs) {
+    float* dst = dw + i * 9;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) dst[t] = acc[t];
+  }
+}
+
 // First layer: dW[co][ci][tap] = sum_p g[p][co] * x[p + tap][ci] on CUDA cores (K = 9*Cin <= 27 columns of output).
 // grid = (blocks, n): each block reduces a pixel range to ws[n][block][cout][cin*9]; a second kernel sums the rows.
 template <typename T, int CIN>
@@ -277,8 +314,11 @@ static int wg_plan(const b2u_wgrad_desc* d, WgPlan* pl) {
   pl->mblks = (d->cg + 127) / 128;
   pl->xchunks = d->cx / 64;
   pl->groups = d->taps == 9 ? 2 : 1;
-  const int pairs = pl->mblks * pl->xchunks * pl->groups;
-  int slices = (b2u_num_sms() * 2 + pairs - 1) / pairs;
+  // the second tap group (tap 8 alone) is 1/8 of the work of the first: size the split for the heavy CTAs only
+  const int pairs = pl->mblks * pl->xchunks;
+  // split the pixel tiles only as far as needed to occupy every SM once: each extra slice costs a full fp32 copy of
+  // the weight gradient in HBM (75 MB for the 1024 -> 1024 layer)
+  int slices = b2u_num_sms() / pairs;                       // floor: slices * pairs CTAs fit one wave
   if (slices > pl->total_tiles) slices = pl->total_tiles;
   if (slices < 1) slices = 1;
   pl->tiles_per_slice = (pl->total_tiles + slices - 1) / slices;
@@ -343,8 +383,14 @@ extern "C" int b2u_wgrad(const void* g, const void* x, float* workspace, float* 
   }
   B2U_LAUNCH_CHECK();
   const long total = static_cast<long>(d->taps) * d->cg * d->cx;
-  int blocks = static_cast<int>((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, dw, pl.slices, d->taps, d->cg, d->cx, d->layout, pl.slices);
+  if (d->taps == 9 && d->layout == 0) {
+    const long pairs = static_cast<long>(d->cg) * d->cx;
+    const int nsg = pl.slices >= 8 ? 8 : (pl.slices >= 4 ? 4 : (pl.slices >= 2 ? 2 : 1));
+    wgrad_reduce9_kernel<<<static_cast<unsigned>((pairs + 31) / 32), dim3(32, nsg), 0, st>>>(workspace, dw, pl.slices, d->cg, d->cx);
+  } else {
+    int blocks = static_cast<int>((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+    wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, dw, pl.slices, d->taps, d->cg, d->cx, d->layout, pl.slices);
+  }
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

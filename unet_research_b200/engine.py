@@ -72,6 +72,20 @@ def philox_thresholds(gamma: float) -> Tuple[int, int]:
     return min(lo, (1 << 32) - 1), min(wrap, (1 << 32) - 1)
 
 
+_THRESH_CACHE: Dict[Tuple[float, int, int, int], Tuple[int, int]] = {}
+
+
+def _thresholds_cached(drop_prob: float, block_size: int, h: int, w: int) -> Tuple[int, int]:
+    key = (float(drop_prob), block_size, h, w)
+    v = _THRESH_CACHE.get(key)
+    if v is None:
+        if len(_THRESH_CACHE) > 4096:
+            _THRESH_CACHE.clear()
+        v = philox_thresholds(dropblock_gamma(drop_prob, block_size, h, w))
+        _THRESH_CACHE[key] = v
+    return v
+
+
 def rand_grid(numel: int, sms: int, max_threads: int) -> int:
     return min(sms * (max_threads // 256), (numel + 255) // 256)
 
@@ -130,7 +144,7 @@ class MaskPlan:
             self.mask_site_off.append(mask_words)
             hc, wc = hh - block_size + 1, ww - block_size + 1
             numel = images_per_call * c * hc * wc
-            lo, hi = philox_thresholds(dropblock_gamma(drop_prob, block_size, hh, ww))
+            lo, hi = _thresholds_cached(drop_prob, block_size, hh, ww)
             self.numel_per_call.append(float(images_per_call * c * hh * ww))
             for b in range(n_calls):
                 d = calls[k]
@@ -153,6 +167,22 @@ class MaskPlan:
         self.mask_bits = torch.empty(mask_words, dtype=torch.int32, device=device)
         self.keep_counts = torch.zeros(self.n_sites * n_calls, dtype=torch.int64, device=device)
         self.offset_base = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def set_drop_prob(self, drop_prob: float):
+        """Re-threshold the call table for a new drop_prob (LinearScheduler ramps it every training step,
+        reference utils_unet.py:410-411): same buffers, same device pointers (captured CUDA graphs stay valid)."""
+        drop_prob = float(drop_prob)
+        if drop_prob == self.drop_prob:
+            return
+        self.drop_prob = drop_prob
+        k = 0
+        for s, (c, hh, ww) in enumerate(self.sites):
+            lo, hi = _thresholds_cached(drop_prob, self.block_size, hh, ww)
+            for b in range(self.n_calls):
+                self.host_table[k].thresh_lo, self.host_table[k].thresh_hi = lo, hi
+                k += 1
+        raw = np.frombuffer(bytes(self.host_table), dtype=np.uint8).copy()
+        self.table.copy_(torch.from_numpy(raw), non_blocking=False)
 
     def set_stream_position(self, philox_offset: int):
         self.offset_base.fill_(int(philox_offset))
@@ -274,47 +304,60 @@ class UNetEngine:
             raise NotImplementedError("first-layer kernel supports init_channels 1 or 3")
         self.init_channels, self.filters, self.depth, self.num_groups, self.dtype = init_channels, filters, depth, num_groups, dtype
         self.w: Dict[str, torch.Tensor] = {}
+        self._aliased = set()
         self._workspaces: Dict[Tuple[int, int, int], Workspace] = {}
         self.training_weights = False          # set by enable_training(): also keep the dgrad-packed weights
         self._sd_ref = state_dict
         self.load_weights(state_dict)
 
     # ---- weights
-    def load_weights(self, sd: Dict[str, torch.Tensor]):
+    def load_weights(self, sd: Dict[str, torch.Tensor], sync: bool = True):
         """(Re)pack the weights.  Existing packed buffers are overwritten IN PLACE so that device pointers
-        baked into captured CUDA graphs stay valid across optimiser steps / load_state_dict."""
+        baked into captured CUDA graphs stay valid across optimiser steps / load_state_dict.  Tensors the
+        kernels read in their PyTorch layout (GroupNorm gamma/beta, first conv, head) are ALIASED when they
+        already live on the device as contiguous fp32 (no copy; the optimiser updates them in place).
+        sync=False: launch-only (used inside CUDA-graph capture; the caller keeps `sd` alive)."""
         dev, dt = self.device, _torch_dtype(self.dtype)
         st = stream_ptr()
 
         def slot(key, shape, dtype):
             t = self.w.get(key)
-            if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or key in self._aliased:
                 t = torch.empty(shape, dtype=dtype, device=dev)
                 self.w[key] = t
+                self._aliased.discard(key)
             return t
+
+        def plain(key, v, v32, shape):
+            if v32.data_ptr() == v.data_ptr():
+                self.w[key] = v32.view(shape)
+                self._aliased.add(key)
+            else:
+                slot(key, shape, torch.float32).copy_(v32.view(shape))
 
         self._sd_ref = sd
         for k, v in sd.items():
             v32 = v.detach().to(device=dev, dtype=torch.float32).contiguous()
             if v32.dim() == 4 and k == "down_blocks.0.0.0.weight":
-                slot(k, v32.shape, torch.float32).copy_(v32)               # direct first-layer kernel reads fp32
+                plain(k, v, v32, tuple(v32.shape))                         # direct first-layer kernel reads fp32
             elif v32.dim() == 4 and k.startswith("output_conv"):
                 if v32.shape[0] != 1:
                     raise NotImplementedError("head kernel supports output_channels == 1")
-                slot(k, (v32.numel(),), torch.float32).copy_(v32.reshape(-1))
+                plain(k, v, v32, (v32.numel(),))
             elif v32.dim() == 4 and v32.shape[2] == 3:
                 cout, cin = v32.shape[0], v32.shape[1]
-                call("b2u_pack_conv3x3_weight", ptr(v32), ptr(slot(k, (9, cout, cin), dt)), cout, cin, self.dtype, 0, st)
-                if self.training_weights:                                  # data-gradient operand: transposed, taps rotated 180
-                    call("b2u_pack_conv3x3_weight", ptr(v32), ptr(slot(k + "#dgrad", (9, cin, cout), dt)), cout, cin, self.dtype, 1, st)
+                # forward operand [9][Cout][Cin] and (training) the data-gradient operand [9][Cin][Cout], taps rotated 180
+                dg = slot(k + "#dgrad", (9, cin, cout), dt) if self.training_weights else None
+                call("b2u_pack_conv3x3_weight_pair", ptr(v32), ptr(slot(k, (9, cout, cin), dt)), ptr(dg), cout, cin, self.dtype, st)
             elif v32.dim() == 4 and v32.shape[2] == 2:
                 cin, cout = v32.shape[0], v32.shape[1]
                 call("b2u_pack_convT2x2_weight", ptr(v32), ptr(slot(k, (4, cout, cin), dt)), cin, cout, self.dtype, st)
                 if self.training_weights:
                     call("b2u_pack_convT2x2_dgrad_weight", ptr(v32), ptr(slot(k + "#dgrad", (1, cin, 4 * cout), dt)), cin, cout, self.dtype, st)
             else:
-                slot(k, v32.shape, torch.float32).copy_(v32)
-        torch.cuda.current_stream().synchronize()      # v32 temporaries die here
+                plain(k, v, v32, tuple(v32.shape))
+        if sync:
+            torch.cuda.current_stream().synchronize()  # v32 temporaries die here
 
     # ---- layout queries
     def conv_stat_layout(self, n, h, w, cin, cout, conv_t: bool) -> Tuple[int, int]:

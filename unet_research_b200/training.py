@@ -10,48 +10,149 @@ from torch import nn
 from . import _lib
 
 
+def _dp_active(model) -> bool:
+    import torch.distributed as dist
+    return (bool(getattr(model, "data_parallel", False)) and dist.is_available() and dist.is_initialized()
+            and dist.get_world_size() > 1)
+
+
+class TrainStep:
+    """One training forward/backward of a fixed (batch, H, W) as three CUDA graphs (BASELINE configs[1]: batch 1
+    is launch-bound when ~290 kernels are issued one by one from Python):
+
+      forward  graph: repack the conv weights from the live parameters -> build the DropBlock masks -> forward schedule
+      backward graph 0: head + decoder + bottleneck          backward graph 1: encoder
+
+    Everything step-dependent lives in device memory the graphs read: the input copy, the upstream gradient copy,
+    the Philox offset and the DropBlock thresholds (the scheduler changes drop_prob every step).  With
+    data-parallel training the decoder-side gradients (85 % of the bytes, flat and contiguous) are all-reduced
+    over NCCL while graph 1 runs.  The first `WARMUP` calls run eagerly (kernel attributes, lazy workspaces)."""
+
+    WARMUP = 2
+
+    def __init__(self, model, eng, ws, tb):
+        self.eng, self.ws, self.tb = eng, ws, tb
+        dev = eng.device
+        self.x = torch.empty(ws.n, eng.init_channels, ws.h0, ws.w0, dtype=torch.float32, device=dev)
+        self.go = torch.empty(ws.n, 1, ws.h0, ws.w0, dtype=torch.float32, device=dev)
+        self.named = [(k, p) for k, p in model.named_parameters()]
+        self.keys = [k for k, _ in self.named]
+        self.sd = {k: p.detach() for k, p in self.named}
+        tb.bind_parameters([(k, tuple(p.shape)) for k, p in self.named])
+        offs = tb.goffsets
+        self.tail = min(o for k, o in offs.items() if not k.startswith("down_blocks"))
+        if any(o >= self.tail for k, o in offs.items() if k.startswith("down_blocks")):
+            self.tail = 0                                  # unexpected parameter order: one all-reduce over everything
+        self.sig = None
+        self.calls = 0
+        self.fwd_graph = None
+        self.bwd_graphs = None
+        self.masks = None
+        self.seed = 0
+
+    def _signature(self, active, bs, seed):
+        return (active, bs, seed if active else 0, tuple(p.data_ptr() for _, p in self.named))
+
+    def _fwd_body(self):
+        self.eng.load_weights(self.sd, sync=False)
+        if self.masks is not None:
+            self.masks.generate(self.seed)
+        self.eng.forward(self.x, self.ws, self.masks, argmax=self.tb.argmax)
+
+    def forward(self, model, xin: torch.Tensor) -> torch.Tensor:
+        eng, ws = self.eng, self.ws
+        active, p, bs = model._dropblock_state()
+        idx = xin.device.index if xin.device.index is not None else torch.cuda.current_device()
+        gen = torch.cuda.default_generators[idx]
+        seed = gen.initial_seed()
+        sig = self._signature(active, bs, seed)
+        if sig != self.sig:
+            self.sig, self.calls, self.fwd_graph, self.bwd_graphs = sig, 0, None, None
+            self.sd = {k: q.detach() for k, q in self.named}
+        self.masks, self.seed = None, seed
+        if active:
+            self.masks = model._mask_plan(eng, 1, ws.n, ws, p, bs)
+            self.masks.set_stream_position(gen.get_offset())
+            gen.set_offset(gen.get_offset() + self.masks.offset_per_call)
+        self.x.copy_(xin)
+        use_graph = bool(getattr(model, "use_cuda_graph", True))
+        if use_graph and self.calls >= self.WARMUP and self.fwd_graph is None:
+            torch.cuda.synchronize(eng.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._fwd_body()
+            self.fwd_graph = g
+        if use_graph and self.fwd_graph is not None:
+            self.fwd_graph.replay()
+        else:
+            self._fwd_body()
+        self.calls += 1
+        model._engine_key = model._engine_signature(eng.device)     # the packed weights now match the live parameters
+        return ws.out.clone()
+
+    def backward(self, model, grad_out: torch.Tensor):
+        from .backward import unet_backward
+        eng, ws, tb = self.eng, self.ws, self.tb
+        self.go.copy_(grad_out)
+        dp = _dp_active(model)
+        use_graph = bool(getattr(model, "use_cuda_graph", True)) and self.fwd_graph is not None
+        if not use_graph:
+            grads = unet_backward(eng, ws, tb, self.masks, self.x, ws.out, self.go, data_parallel=dp)
+            return tuple(grads[k] for k in self.keys)
+        if self.bwd_graphs is None:
+            torch.cuda.synchronize(eng.device)
+            g0, g1 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g0):
+                unet_backward(eng, ws, tb, self.masks, self.x, ws.out, self.go, phase=0)
+            with torch.cuda.graph(g1, pool=g0.pool()):
+                unet_backward(eng, ws, tb, self.masks, self.x, ws.out, self.go, phase=1)
+            self.bwd_graphs = (g0, g1)
+        g0, g1 = self.bwd_graphs
+        if dp:
+            import torch.distributed as dist
+            g0.replay()
+            h0 = dist.all_reduce(tb.flat[self.tail:], op=dist.ReduceOp.AVG, async_op=True) if self.tail > 0 else None
+            g1.replay()
+            h1 = dist.all_reduce(tb.flat[:self.tail] if self.tail > 0 else tb.flat, op=dist.ReduceOp.AVG, async_op=True)
+            if h0 is not None:
+                h0.wait()
+            h1.wait()
+            tb.last_allreduce_bytes = tb.flat.numel() * 4
+        else:
+            g0.replay()
+            g1.replay()
+        return tuple(tb.gviews[k] for k in self.keys)
+
+
 class _UNetFunction(torch.autograd.Function):
     """out = UNet(x); backward returns one gradient per parameter, in `model.parameters()` order."""
 
     @staticmethod
     def forward(ctx, model, x, *params):
         from .backward import TrainBuffers
-        eng = model._get_engine(x.device)
-        eng.enable_training()
         n, _, h0, w0 = x.shape
+        eng = model._get_engine(x.device, repack=False)
+        if not eng.training_weights:
+            eng.enable_training()
         model._original_size = (h0, w0)
         ws = eng.workspace(n, h0, w0)
         tb = getattr(ws, "train_buffers", None)
         if tb is None:
             tb = TrainBuffers(eng, ws)
             ws.train_buffers = tb
+        ts = getattr(ws, "train_step", None)
+        if ts is None or [id(p) for _, p in ts.named] != [id(p) for p in params]:
+            ts = TrainStep(model, eng, ws, tb)
+            ws.train_step = ts
         xin = x.detach().to(torch.float32).contiguous()
-        active, p, bs = model._dropblock_state()
-        masks = None
-        if active:
-            masks = model._mask_plan(eng, 1, n, ws, p, bs)
-            idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
-            gen = torch.cuda.default_generators[idx]
-            masks.set_stream_position(gen.get_offset())
-            masks.generate(gen.initial_seed())
-            gen.set_offset(gen.get_offset() + masks.offset_per_call)
-        out = eng.forward(xin, ws, masks, argmax=tb.argmax).clone()
-        ctx.model, ctx.eng, ctx.ws, ctx.tb, ctx.masks, ctx.xin = model, eng, ws, tb, masks, xin
-        ctx.keys = [k for k, _ in model.named_parameters()]
-        ctx.save_for_backward(out)
+        out = ts.forward(model, xin)
+        ctx.model, ctx.ts = model, ts
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        from .backward import unet_backward
-        (out,) = ctx.saved_tensors
-        import torch.distributed as dist
-        dp = bool(getattr(ctx.model, "data_parallel", False)) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        grads = unet_backward(ctx.eng, ctx.ws, ctx.tb, ctx.masks, ctx.xin, out, grad_out, data_parallel=dp)
-        missing = [k for k in ctx.keys if k not in grads]
-        if missing:
-            raise _lib.B2uError(f"backward produced no gradient for {missing[:3]}...")
-        return (None, None) + tuple(grads[k] for k in ctx.keys)
+        grads = ctx.ts.backward(ctx.model, grad_out)
+        return (None, None) + grads
 
 
 def unet_autograd_forward(model, x):

@@ -56,6 +56,7 @@ class UNet(nn.Module):
         self._checkpointing = checkpointing       # activation recompute is a memory trick; values are unchanged
         self.compute_dtype = "bf16"               # "bf16" (tcgen05 kind::f16) or "tf32" (fp32 storage, kind::tf32)
         self.data_parallel = False                # True: backward all-reduces (averages) the gradients over torch.distributed
+        self.use_cuda_graph = True                # training steps replay captured CUDA graphs after two eager warm-up steps
         self._engine: Optional[UNetEngine] = None
         self._engine_key = None
         self._mask_plans = {}
@@ -159,10 +160,18 @@ class UNet(nn.Module):
             return True, float(db.drop_prob), int(db.block_size)
         return False, 0.0, 7
 
-    def _get_engine(self, device) -> UNetEngine:
+    def _engine_signature(self, device):
         dtype = _lib.F32 if self.compute_dtype == "tf32" else _lib.BF16
         params = list(self.parameters())
-        key = (str(device), dtype, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        return (str(device), dtype, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+
+    def _get_engine(self, device, repack: bool = True) -> UNetEngine:
+        """repack=False: the caller (training.TrainStep) repacks the weights itself, inside its CUDA graph."""
+        key = self._engine_signature(device)
+        dtype = key[1]
+        if (not repack and self._engine is not None and self._engine_key is not None
+                and self._engine_key[:2] == key[:2] and self._engine_key[3] == key[3]):
+            return self._engine
         if self._engine is None or self._engine_key != key:
             sd = {k: v for k, v in self.state_dict().items()}
             if self._engine is None or self._engine_key[:2] != key[:2]:
@@ -175,13 +184,16 @@ class UNet(nn.Module):
         return self._engine
 
     def _mask_plan(self, eng, n_calls, ipc, ws, drop_prob, block_size) -> MaskPlan:
-        key = (n_calls, ipc, ws.h, ws.w, drop_prob, block_size)
+        """One plan (bitmaps, call table) per shape; drop_prob is re-thresholded in place because the scheduler
+        ramps it every training step (reference :410-411)."""
+        key = (n_calls, ipc, ws.h, ws.w, block_size)
         mp = self._mask_plans.get(key)
         if mp is None:
-            if len(self._mask_plans) > 4:          # scheduler ramps drop_prob every step: keep the cache small
+            if len(self._mask_plans) > 4:
                 self._mask_plans.clear()
             mp = MaskPlan(n_calls, ipc, ws.h, ws.w, self._base_filters, self._model_depth, drop_prob, block_size, eng.device)
             self._mask_plans[key] = mp
+        mp.set_drop_prob(drop_prob)
         return mp
 
     # ------------------------------------------------------------------ forward (reference :408-449)
