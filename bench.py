@@ -42,6 +42,17 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
+def load_traffic():
+    """DRAM bytes (read + write) of the conv family per step from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -234,9 +245,19 @@ def run_gpu(args):
     # ---- roofline of the dominant kernel family (conv_gemm_kernel): per-launch CUDA-event timing, eager mode
     conv_ms, other = time_conv_kernels(runner, dev, reps=max(3, min(K, 10)))
     conv_tflops = CONV_FLOP_PER_FORWARD * NB / (conv_ms / 1000.0) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (18 conv3x3 + 4 convT launches per step)",
+    eb = elementwise_bytes_per_step(NB)
+    hbm = {}
+    for name, nbytes in eb.items():
+        key = name if name in other else name.replace("b2u_gn_finalize", "b2u_gn_finalize_ex")
+        if key in other and other[key] > 0:
+            gbs = nbytes / (other[key] / 1000.0) / 1e9
+            hbm[name] = {"algorithmic_mb_per_step": nbytes / 1e6, "ms_per_step": other[key], "achieved_gbs": gbs,
+                         "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
+    traffic = load_traffic()
+    roofline = {"bound": "tensor", "kernel": "conv3x3_v2_kernel + convT_v2_kernel (17 conv3x3 + 4 convT launches per step)",
                 "achieved": conv_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": conv_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+                "frac": conv_tflops / peaks["bf16_tflops_sustained"], "traffic": traffic,
+                "hbm_bound_kernels": hbm, "hbm_peak_gbs": peaks["hbm_gbs"],
                 "peak_source": peaks["src"] + " bf16_tflops_sustained (kernels timed inside a long step)",
                 "conv_ms_per_step": conv_ms, "step_ms": ms_max / K, "conv_share_of_step": conv_ms / (ms_max / K),
                 "other_kernels_ms_per_step": other}
@@ -278,6 +299,10 @@ def run_gpu(args):
                "step": f"DropBlockEval.predict_step, {T_e2e} iterations per call (sharded over ranks), pinned host in/out",
                "mc_1000_iter_projected_s": 1000.0 / (reps * T_e2e / float(tt.item()))}
 
+    train = None
+    if not args.no_train:
+        train = bench_train(dev, rank, world, args.train_steps, 4)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         val, k, w, cores = oracle_mc_forward_timer(2, 0, budget_s=25.0)
@@ -295,7 +320,7 @@ def run_gpu(args):
                        "parallelism": f"mc-iteration sharding x{world}", "cuda_graph": True,
                        "mask_build": "side stream, overlapped with the forward of the previous step"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "train": train,
             "tflops_whole_step": FLOP_PER_FORWARD * NB * world * K / (ms_max / 1000.0) / 1e12,
             "mc_1000_iter_projected_s": 1000.0 / value, "allreduce_ms": allreduce_ms,
         }
@@ -303,6 +328,96 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def elementwise_bytes_per_step(nb, filters=64, depth=4, h=592, w=576, h0=H0, w0=W0):
+    """ALGORITHMIC HBM bytes of one Monte-Carlo step (nb batched iterations, bf16 activations) per fused kernel
+    family, from the tensor shapes alone: every activation read once / written once, bit masks
+    1 bit per element, statistics and coefficients ignored."""
+    out = {"b2u_gn_apply": 0.0, "b2u_gn_apply_pool": 0.0, "b2u_head_fwd": 0.0, "b2u_conv_first_fwd": 0.0,
+           "b2u_dropblock_dilate": 0.0}
+    c = filters
+    bits = 0.0
+    for lvl in range(depth + 1):
+        e = float(h >> lvl) * (w >> lvl) * c                     # elements of one conv output at this level
+        if lvl < depth:
+            # encoder: unit 1 apply (first level reads the SHARED raw tensor once), unit 2 apply+pool, pooled-GN apply
+            out["b2u_gn_apply"] += (2.0 * e * (1 if lvl == 0 else nb) + 2.0 * e * nb + e * nb / 8.0)
+            out["b2u_gn_apply_pool"] += nb * (2.0 * e + 2.0 * e + 0.5 * e + e / 8.0 + e / 8.0)
+            out["b2u_gn_apply"] += nb * (2.0 * e / 4 + 2.0 * e / 4)
+            # decoder at the same resolution: up-conv apply (with concat mask), unit 1 apply, unit 2 apply (not the last level)
+            out["b2u_gn_apply"] += nb * (4.0 * e + e / 8.0)
+            out["b2u_gn_apply"] += nb * (4.0 * e + e / 8.0)
+            if lvl > 0:
+                out["b2u_gn_apply"] += nb * (4.0 * e + e / 8.0)
+            bits += nb * (2 * e + 2 * e + 2 * e)                 # sites: 2 encoder units, concat (2c), 2 decoder units
+        else:
+            out["b2u_gn_apply"] += nb * 2 * (4.0 * e + e / 8.0)
+            bits += nb * 2 * e
+        c *= 2
+    e0 = float(h) * w * filters
+    out["b2u_head_fwd"] = nb * (2.0 * e0 + e0 / 8.0) + 16.0 * h0 * w0 * 2
+    out["b2u_conv_first_fwd"] = 2.0 * e0 + 4.0 * h0 * w0
+    out["b2u_dropblock_dilate"] = 2.0 * bits / 8.0                # centre bitmap in, keep bitmap out
+    return out
+
+
+def bench_train(dev, rank, world, steps, warmup):
+    """BASELINE configs[1] (+ configs[4] data-parallel part): fwd + bwd + clip + SGD, batch 1 per GPU, 584x565,
+    DropBlock bs 7 p .15, bf16; with N > 1 every rank trains on its own image and the gradients are averaged over
+    NCCL inside backward (decoder-side bucket overlapped with the encoder backward).  Returns the `train` object."""
+    import torch
+    import torch.distributed as dist
+    from torch import nn
+    import unet_research_b200 as U
+    from unet_research_b200 import synthetic
+    from unet_research_b200.smoke_test import build_canonical
+    model, _ = build_canonical(dev, dropblock=True, compute="bf16")
+    model.train()
+    model.data_parallel = world > 1
+    x = synthetic.make_image(H0, W0, seed=1234 + rank).to(dev)
+    gt = synthetic.make_gt(H0, W0, seed=1234 + rank).to(dev)
+    fov = synthetic.make_fov_mask(H0, W0).to(dev)
+    tm = U.BaseUNetTraining(model, nn.BCELoss(), None)
+    opt = U.FusedSGD(model.parameters(), lr=1e-3, momentum=0.99, max_grad_norm=0.5) if hasattr(U, "FusedSGD") else \
+        torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.99)
+    fused = hasattr(U, "FusedSGD")
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = tm.training_step((x.clone(), gt, fov), 0)
+        loss.backward()
+        if not fused:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 0.5)
+        opt.step()
+        return loss
+
+    for _ in range(max(warmup, 4)):
+        l0 = step()
+    first = float(l0.item())
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    ws = list(model._engine._workspaces.values())[0]
+    graphs = ws.train_step.fwd_graph is not None and ws.train_step.bwd_graphs is not None
+    return {"metric": "train imgs/s (fwd + bwd + clip + SGD, batch 1 per GPU, 584x565, DropBlock bs7 p0.15, bf16)",
+            "value": world / (ms / 1000.0), "unit": "imgs/s", "ms_per_step": ms, "steps": steps, "global_batch": world,
+            "tflops": 1501.4e9 * world / (ms / 1000.0) / 1e12, "flop_per_image": 1501.4e9, "cuda_graphs": graphs,
+            "optimizer": "fused SGD-momentum + global-norm clip (one multi-tensor kernel pair)" if fused else "torch.optim.SGD + clip_grad_norm_",
+            "gradient_allreduce_bytes": (124.16e6 if world > 1 else 0), "allreduce": "NCCL AVG, 2 buckets, decoder bucket overlapped with the encoder backward" if world > 1 else None,
+            "loss_first": first, "loss_last": float(loss.item())}
 
 
 def time_conv_kernels(runner, dev, reps):
@@ -327,6 +442,9 @@ def time_conv_kernels(runner, dev, reps):
     E.call = timed_call
     try:
         for _ in range(reps):
+            # a ~10 ms spin kernel first: the whole step is enqueued while it runs, so every event pair below
+            # brackets back-to-back GPU execution and never the host's launch latency
+            torch.cuda._sleep(20_000_000)
             runner.masks[0].generate(runner.seed)
             runner.eng.forward(runner.x, runner.ws, runner.masks[0], head_out=False, mc=runner.mc, shared_input=True)
         torch.cuda.synchronize(dev)
@@ -350,6 +468,8 @@ def main():
     ap.add_argument("--e2e-iters", type=int, default=100)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=30)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

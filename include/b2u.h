@@ -261,6 +261,22 @@ int b2u_pack_convT2x2_dgrad_weight(const float* w, void* packed, int cin, int co
 int b2u_rotate_bilinear(const float* x, float* out, int n, int c, int h, int w, const double* angles_deg,
                         int x_batch_stride_is_zero, void* stream);
 
+/* ------------------------------------------------------------------ fused optimiser step
+ * torch.optim.SGD(lr, momentum) (base_model_tests/training.py:32) + Lightning's gradient_clip_val (global L2 norm,
+ * torch.nn.utils.clip_grad_norm_ semantics: clip = min(1, max_norm / (norm + 1e-6)); grads are scaled in place).
+ * tensors_dev: device array of b2u_sgd_tensor; chunks_dev: device array of {int32 tensor, int32 count, int64 start}
+ * covering every tensor in pieces of at most b2u_sgd_chunk_elems() elements; partial_dev: n_chunks doubles.
+ * max_grad_norm <= 0 disables clipping; first_step != 0 initialises the momentum buffers with the gradient. */
+typedef struct {
+  float* param;
+  float* grad;
+  float* momentum;
+  long long numel;
+} b2u_sgd_tensor;
+long long b2u_sgd_chunk_elems(void);
+int b2u_sgd_step(const b2u_sgd_tensor* tensors_dev, const void* chunks_dev, int n_chunks, double* partial_dev, float lr,
+                 float momentum, float max_grad_norm, int first_step, float* grad_norm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -210,6 +210,46 @@ def test_train_step_cuda_graph_matches_eager():
     assert r["ok"], r
 
 
+def test_fused_sgd_matches_torch():
+    """FusedSGD (clip + momentum SGD in two launches) against torch.nn.utils.clip_grad_norm_ + torch.optim.SGD
+    (reference training.py:32 + Lightning gradient_clip_val) over several steps, ragged tensor sizes included."""
+    import unet_research_b200 as U
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(5)
+    shapes = [(64, 1, 3, 3), (64,), (1024, 1024, 3, 3), (7,), (65537,), (128, 64, 2, 2), (1, 64, 1, 1)]
+    pa = [torch.randn(s, generator=g).to(dev).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa = U.FusedSGD(pa, lr=0.05, momentum=0.99, max_grad_norm=0.5)
+    ob = torch.optim.SGD(pb, lr=0.05, momentum=0.99)
+    for it in range(4):
+        scale = 10.0 if it % 2 == 0 else 1e-3                      # alternately clipped and not clipped
+        gs = [(torch.randn(s, generator=g) * scale).to(dev) for s in shapes]
+        for p, q, gr in zip(pa, pb, gs):
+            p.grad = gr.clone()
+            q.grad = gr.clone()
+        oa.step()
+        norm_ref = torch.nn.utils.clip_grad_norm_(pb, 0.5)
+        ob.step()
+        assert abs(float(oa.last_grad_norm) - float(norm_ref)) <= 1e-5 * float(norm_ref)
+        for p, q in zip(pa, pb):
+            assert D.rel(p.detach(), q.detach())[0] < 1e-6
+            assert D.rel(p.grad, q.grad)[0] < 1e-5                # grads are scaled in place like clip_grad_norm_
+    assert pa[0]._version > 0                                      # version counters were bumped
+    # no clipping, no momentum
+    pc = [torch.randn(1000, generator=g).to(dev).requires_grad_(True)]
+    pd = [pc[0].detach().clone().requires_grad_(True)]
+    oc, od = U.FusedSGD(pc, lr=0.1), torch.optim.SGD(pd, lr=0.1)
+    pc[0].grad = torch.ones(1000, device=dev)
+    pd[0].grad = torch.ones(1000, device=dev)
+    oc.step()
+    od.step()
+    assert torch.equal(pc[0].detach(), pd[0].detach())
+    cpu_p = torch.zeros(3, requires_grad=True)
+    cpu_p.grad = torch.ones(3)
+    with pytest.raises(Exception):
+        U.FusedSGD([cpu_p], lr=0.1).step()                         # no CPU path
+
+
 def test_training_reduces_loss_full_size():
     """BASELINE configs[1]: batch 1, 584x565, DropBlock bs 7 p .15, SGD(momentum .99) + clip .5: the loss goes down."""
     import unet_research_b200 as U
@@ -222,13 +262,12 @@ def test_training_reduces_loss_full_size():
     gt = synthetic.make_gt(584, 565).to(dev)
     fov = synthetic.make_fov_mask(584, 565).to(dev)
     tm = U.BaseUNetTraining(m, nn.BCELoss(), None)
-    opt = torch.optim.SGD(m.parameters(), lr=1e-3, momentum=0.99)
+    opt = U.FusedSGD(m.parameters(), lr=1e-3, momentum=0.99, max_grad_norm=0.5)
     losses = []
     for _ in range(12):
         opt.zero_grad(set_to_none=True)
         loss = tm.training_step((x.clone(), gt, fov), 0)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(m.parameters(), 0.5)
         opt.step()
         losses.append(loss.item())
     assert all(l == l for l in losses) and losses[-1] < losses[0] - 0.05, losses

@@ -151,8 +151,19 @@ class _UNetFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        grads = ctx.ts.backward(ctx.model, grad_out)
-        return (None, None) + grads
+        """The parameter gradients live in ONE flat fp32 buffer owned by the workspace (TrainBuffers.flat).  They are
+        delivered by aliasing: `p.grad` becomes a view of that buffer (no 124 MB accumulate-copy per step, stable
+        pointers for the fused optimiser and the NCCL buckets).  A gradient that already exists and is NOT that view
+        (another loss term, another workspace) is accumulated into, as autograd would.  Like every framework that
+        owns its gradient buffers this assumes `zero_grad()` between steps (Lightning and the reference's loops do)."""
+        ts = ctx.ts
+        grads = ts.backward(ctx.model, grad_out)
+        for (_, p), g in zip(ts.named, grads):
+            if p.grad is None:
+                p.grad = g
+            elif p.grad.data_ptr() != g.data_ptr():
+                p.grad.add_(g)
+        return (None, None) + (None,) * len(grads)
 
 
 def unet_autograd_forward(model, x):
