@@ -34,6 +34,7 @@ extern "C" {
 
 #define B2U_BF16 0
 #define B2U_F32 1
+#define B2U_F16 2   /* fp16 storage and operands (kind::f16, F16 format), fp32 accumulate: inference only */
 
 const char* b2u_last_error(void);
 int b2u_version(void);
@@ -62,7 +63,7 @@ int b2u_pack_convT2x2_weight(const float* w, void* packed, int cin, int cout, in
 typedef struct {
   int32_t n, h, w;          /* input batch / height / width (pixels)                               */
   int32_t cin, cout;        /* channels; cin % (128/sizeof(elt)) == 0, cout % 64 == 0              */
-  int32_t dtype;            /* B2U_BF16 | B2U_F32                                                  */
+  int32_t dtype;            /* B2U_BF16 | B2U_F32 | B2U_F16                                        */
   int32_t num_groups;       /* GroupNorm groups of the FOLLOWING norm; 0 = no statistics           */
   int32_t x_cstride;        /* channel count of the tensor x lives in (>= cin; concat buffers)     */
   int32_t reserved[4];

@@ -18,7 +18,7 @@ import traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["info", "conv", "convv1", "convv2", "wgrad", "bwdk", "convt", "first", "gn", "pool", "head", "dropblock", "rotate", "forward", "mc", "rot_ens", "tf32", "train", "traingraph"]
+SECTIONS = ["info", "conv", "convv1", "convv2", "wgrad", "bwdk", "convt", "first", "gn", "pool", "head", "dropblock", "rotate", "forward", "mc", "rot_ens", "tf32", "train", "traingraph", "precision"]
 
 
 def rel(a, b):
@@ -646,6 +646,56 @@ def _forward_case(h, w, n, compute):
         rr, _ = rel(B[bname].float().permute(0, 3, 1, 2), taps[tname])
         print(f"     {tname:12s} rel {rr:.3e}")
     return {"out_rel": r, "out_max": mx, "logits_rel": rl, "logits_max": ml}
+
+
+def sec_precision():
+    """How far does the REFERENCE algorithm itself move when PyTorch runs it at reduced precision on this GPU?
+    The oracle forward (torch ops, same weights, 584x565) under (a) torch.autocast(bfloat16) and (b) allow_tf32=True is
+    compared with its own fp64 result, next to our bf16 / tf32 kernels: the measured floor that the 1e-2 / 1e-3
+    logit bars of the north star have to be read against."""
+    import torch
+    from oracle import unet_oracle as O
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    h, w = 584, 565
+    x = synthetic.make_image(h, w, seed=1234).to(dev)
+    sd = {k: v.to(dev) for k, v in synthetic.make_state_dict(seed=1234).items()}
+    res = {}
+    with torch.no_grad():
+        t64 = {}
+        O.unet_forward({k: v.double() for k, v in sd.items()}, x.double(), taps=t64)
+        ref_lg, ref_out = t64["logits"][:, :, :h, :w], torch.sigmoid(t64["logits"][:, :, :h, :w])
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        t = {}
+        O.unet_forward(sd, x, taps=t)
+        res["torch fp32"] = (rel(t["logits"][:, :, :h, :w], ref_lg)[0], rel(torch.sigmoid(t["logits"][:, :, :h, :w]), ref_out)[0])
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+        t = {}
+        O.unet_forward(sd, x, taps=t)
+        res["torch tf32 (cudnn.allow_tf32)"] = (rel(t["logits"][:, :, :h, :w], ref_lg)[0], rel(torch.sigmoid(t["logits"][:, :, :h, :w]), ref_out)[0])
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        t = {}
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            O.unet_forward(sd, x, taps=t)
+        lg = t["logits"][:, :, :h, :w].float()
+        res["torch autocast bf16"] = (rel(lg, ref_lg)[0], rel(torch.sigmoid(lg), ref_out)[0])
+        t = {}
+        with torch.autocast("cuda", dtype=torch.float16):
+            O.unet_forward(sd, x, taps=t)
+        lg = t["logits"][:, :, :h, :w].float()
+        res["torch autocast fp16"] = (rel(lg, ref_lg)[0], rel(torch.sigmoid(lg), ref_out)[0])
+        for compute in ("bf16", "fp16", "tf32"):
+            m, _ = _build_model(dev, compute=compute)
+            eng = m._get_engine(dev)
+            ws = eng.workspace(1, h, w)
+            out = eng.forward(x, ws, None, want_logits=True).clone()
+            res[f"b200 kernels {compute}"] = (rel(ws.logits, ref_lg)[0], rel(out, ref_out)[0])
+    for k, (a, b) in res.items():
+        print(f"  {k:34s} logits rel L2 {a:.3e}   probabilities rel L2 {b:.3e}   (vs the fp64 oracle)")
+    return res
 
 
 def sec_forward():

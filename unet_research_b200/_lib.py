@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libb2u.so")
 
-BF16, F32 = 0, 1
+BF16, F32, F16 = 0, 1, 2
 
 
 class B2uError(RuntimeError):

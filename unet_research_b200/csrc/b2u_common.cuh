@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -210,6 +211,56 @@ __device__ __forceinline__ float round_tf32(float x) {   // round-to-nearest (ti
 template <typename T> __device__ __forceinline__ T to_operand(float x);
 template <> __device__ __forceinline__ __nv_bfloat16 to_operand<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
 template <> __device__ __forceinline__ float to_operand<float>(float x) { return round_tf32(x); }
+// fp16 operands (kind::f16 with the F16 format): 11-bit mantissa at bf16 speed; values are saturated to the finite
+// range instead of overflowing to inf (post-GroupNorm activations and kaiming-scale weights are O(1))
+__device__ __forceinline__ float sat_f16(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
+template <> __device__ __forceinline__ __half to_operand<__half>(float x) { return __float2half_rn(sat_f16(x)); }
+
+// Storage format of a tensor-core kernel: 0 = bf16, 1 = fp32 storage / tf32 math, 2 = fp16 (== the B2U_* dtype codes)
+template <int F> struct FmtTraits;
+template <> struct FmtTraits<0> { using T = __nv_bfloat16; static constexpr int kIdescFmt = 1; };
+template <> struct FmtTraits<1> { using T = float; static constexpr int kIdescFmt = 2; };
+template <> struct FmtTraits<2> { using T = __half; static constexpr int kIdescFmt = 0; };
+
+// 32 consecutive accumulator columns of one row -> global memory in the storage type
+template <typename T> __device__ __forceinline__ void store_chunk32(T* dst, const float (&x)[32]);
+template <> __device__ __forceinline__ void store_chunk32<float>(float* dst, const float (&x)[32]) {
+  float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d4[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+}
+template <> __device__ __forceinline__ void store_chunk32<__nv_bfloat16>(__nv_bfloat16* dst, const float (&x)[32]) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(x[8 * i], x[8 * i + 1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(x[8 * i + 2], x[8 * i + 3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(x[8 * i + 4], x[8 * i + 5]);
+    __nv_bfloat162 d = __floats2bfloat162_rn(x[8 * i + 6], x[8 * i + 7]);
+    uint4 v;
+    v.x = *reinterpret_cast<uint32_t*>(&a);
+    v.y = *reinterpret_cast<uint32_t*>(&b);
+    v.z = *reinterpret_cast<uint32_t*>(&c);
+    v.w = *reinterpret_cast<uint32_t*>(&d);
+    d4[i] = v;
+  }
+}
+template <> __device__ __forceinline__ void store_chunk32<__half>(__half* dst, const float (&x)[32]) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 a = __floats2half2_rn(sat_f16(x[8 * i]), sat_f16(x[8 * i + 1]));
+    __half2 b = __floats2half2_rn(sat_f16(x[8 * i + 2]), sat_f16(x[8 * i + 3]));
+    __half2 c = __floats2half2_rn(sat_f16(x[8 * i + 4]), sat_f16(x[8 * i + 5]));
+    __half2 d = __floats2half2_rn(sat_f16(x[8 * i + 6]), sat_f16(x[8 * i + 7]));
+    uint4 v;
+    v.x = *reinterpret_cast<uint32_t*>(&a);
+    v.y = *reinterpret_cast<uint32_t*>(&b);
+    v.z = *reinterpret_cast<uint32_t*>(&c);
+    v.w = *reinterpret_cast<uint32_t*>(&d);
+    d4[i] = v;
+  }
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -260,6 +311,25 @@ template <> struct Vec8<__nv_bfloat16> {
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
 #pragma unroll
     for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  }
+};
+template <> struct Vec8<__half> {
+  uint4 raw;
+  __device__ __forceinline__ void load(const __half* p) { raw = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(__half* p) const { *reinterpret_cast<uint4*>(p) = raw; }
+  __device__ __forceinline__ void to_float(float (&f)[8]) const {
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __half22float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ __forceinline__ void from_float(const float (&f)[8]) {
+    __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(sat_f16(f[2 * i]), sat_f16(f[2 * i + 1]));
   }
 };
 template <> struct Vec8<float> {

@@ -63,14 +63,15 @@ __device__ __forceinline__ void v2_epilogue_stats(const float (&x)[32], bool val
   if (lane % LPV == 0) scratch[lane / LPV] = v[0];
 }
 
-template <int BLOCK_N, int MT, bool kTf32>
+template <int BLOCK_N, int MT, int kFmt>
 __global__ void __launch_bounds__(kV2Threads, 1)
 conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvV2Params p) {
-  using OutT = typename std::conditional<kTf32, float, __nv_bfloat16>::type;
+  constexpr bool kTf32 = kFmt == 1;
+  using OutT = typename FmtTraits<kFmt>::T;
   constexpr int kBBytes = BLOCK_N * 128;
   constexpr int kKElems = kTf32 ? 32 : 64;
   constexpr int kUmmaK = kTf32 ? 8 : 16;
-  constexpr uint32_t kIdesc = umma_idesc(128, BLOCK_N, kTf32 ? 2 : 1);
+  constexpr uint32_t kIdesc = umma_idesc(128, BLOCK_N, FmtTraits<kFmt>::kIdescFmt);
   constexpr int kAccCols = MT * BLOCK_N;                       // TMEM columns of one accumulator buffer
   constexpr int kNumBuf = (2 * kAccCols <= 512) ? 2 : 1;
   constexpr int kTmemCols = (kNumBuf * kAccCols <= 64) ? 64 : (kNumBuf * kAccCols <= 128) ? 128 : (kNumBuf * kAccCols <= 256) ? 256 : 512;
@@ -242,26 +243,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
           if (valid) {
-            if constexpr (kTf32) {
-              float4* dst = reinterpret_cast<float4*>(yrow + chunk * 32);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) dst[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-            } else {
-              uint4* dst = reinterpret_cast<uint4*>(yrow + chunk * 32);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                __nv_bfloat162 a = __floats2bfloat162_rn(x[8 * i], x[8 * i + 1]);
-                __nv_bfloat162 b = __floats2bfloat162_rn(x[8 * i + 2], x[8 * i + 3]);
-                __nv_bfloat162 c = __floats2bfloat162_rn(x[8 * i + 4], x[8 * i + 5]);
-                __nv_bfloat162 d = __floats2bfloat162_rn(x[8 * i + 6], x[8 * i + 7]);
-                uint4 v;
-                v.x = *reinterpret_cast<uint32_t*>(&a);
-                v.y = *reinterpret_cast<uint32_t*>(&b);
-                v.z = *reinterpret_cast<uint32_t*>(&c);
-                v.w = *reinterpret_cast<uint32_t*>(&d);
-                dst[i] = v;
-              }
-            }
+            store_chunk32<OutT>(yrow + chunk * 32, x);
           }
         }
         if (p.sgs_log2 >= 0) {
@@ -324,7 +306,7 @@ static int v2_make_plan(const b2u_conv_desc* d, V2Plan* pl) {
   return B2U_OK;
 }
 
-template <int BN, int MT, bool TF>
+template <int BN, int MT, int TF>
 static int v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Params& gp, int grid, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -389,10 +371,12 @@ int conv3x3_v2_run(const void* x, const void* wpacked, void* y, float* partials,
   int grid = b2u_num_sms();
   if (grid > gp.num_items) grid = gp.num_items;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool tf = d->dtype == B2U_F32;
-#define B2U_V2_CASE(BN, MTV)                                                                                        \
-  if (pl.block_n == BN && pl.mt == MTV)                                                                              \
-    return tf ? v2_launch<BN, MTV, true>(ta, tb, gp, grid, pl.smem, st) : v2_launch<BN, MTV, false>(ta, tb, gp, grid, pl.smem, st);
+#define B2U_V2_CASE(BN, MTV)                                                                        \
+  if (pl.block_n == BN && pl.mt == MTV) {                                                            \
+    if (d->dtype == B2U_F32) return v2_launch<BN, MTV, 1>(ta, tb, gp, grid, pl.smem, st);            \
+    if (d->dtype == B2U_F16) return v2_launch<BN, MTV, 2>(ta, tb, gp, grid, pl.smem, st);            \
+    return v2_launch<BN, MTV, 0>(ta, tb, gp, grid, pl.smem, st);                                     \
+  }
   B2U_V2_CASE(64, 1) B2U_V2_CASE(64, 2) B2U_V2_CASE(128, 1) B2U_V2_CASE(128, 2) B2U_V2_CASE(256, 1) B2U_V2_CASE(256, 2)
 #undef B2U_V2_CASE
   b2u_set_error("conv3x3 v2: no kernel for BLOCK_N %d MT %d", pl.block_n, pl.mt);

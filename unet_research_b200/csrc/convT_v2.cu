@@ -60,13 +60,14 @@ __device__ __forceinline__ void convT_epilogue_stats(const float (&x)[32], bool 
   if (lane % LPV == 0) scratch[lane / LPV] = v[0];
 }
 
-template <bool kTf32>
+template <int kFmt>
 __global__ void __launch_bounds__(kTThreads, 1)
 convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTParams p) {
-  using OutT = typename std::conditional<kTf32, float, __nv_bfloat16>::type;
+  constexpr bool kTf32 = kFmt == 1;
+  using OutT = typename FmtTraits<kFmt>::T;
   constexpr int kKElems = kTf32 ? 32 : 64;
   constexpr int kUmmaK = kTf32 ? 8 : 16;
-  constexpr uint32_t kIdesc = umma_idesc(128, kTBlockN, kTf32 ? 2 : 1);
+  constexpr uint32_t kIdesc = umma_idesc(128, kTBlockN, FmtTraits<kFmt>::kIdescFmt);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -191,26 +192,7 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int co0 = gcol - tap * p.cout;
           const size_t opix = (static_cast<size_t>(img) * (2 * p.h) + (2 * hh + (tap >> 1))) * out_w + (2 * ww + (tap & 1));
           OutT* yrow = reinterpret_cast<OutT*>(p.y) + opix * p.cout + co0;
-          if constexpr (kTf32) {
-            float4* dst = reinterpret_cast<float4*>(yrow);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-          } else {
-            uint4* dst = reinterpret_cast<uint4*>(yrow);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              __nv_bfloat162 a = __floats2bfloat162_rn(x[8 * i], x[8 * i + 1]);
-              __nv_bfloat162 b = __floats2bfloat162_rn(x[8 * i + 2], x[8 * i + 3]);
-              __nv_bfloat162 c = __floats2bfloat162_rn(x[8 * i + 4], x[8 * i + 5]);
-              __nv_bfloat162 d = __floats2bfloat162_rn(x[8 * i + 6], x[8 * i + 7]);
-              uint4 v;
-              v.x = *reinterpret_cast<uint32_t*>(&a);
-              v.y = *reinterpret_cast<uint32_t*>(&b);
-              v.z = *reinterpret_cast<uint32_t*>(&c);
-              v.w = *reinterpret_cast<uint32_t*>(&d);
-              dst[i] = v;
-            }
-          }
+          store_chunk32<OutT>(yrow, x);
         }
       }
       // the accumulator has been read: release it before the (shared-memory only) statistics reduction
@@ -256,7 +238,7 @@ int convT_v2_stat_layout(const b2u_conv_desc* d, int* rows_per_image, int* subgr
   return B2U_OK;
 }
 
-template <bool TF>
+template <int TF>
 static int convT_v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvTParams& gp, int grid, size_t smem, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -309,7 +291,9 @@ int convT_v2_run(const void* x, const void* wpacked, void* y, float* partials, c
   int grid = b2u_num_sms();
   if (grid > gp.num_items) grid = gp.num_items;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return d->dtype == B2U_F32 ? convT_v2_launch<true>(ta, tb, gp, grid, smem, st) : convT_v2_launch<false>(ta, tb, gp, grid, smem, st);
+  if (d->dtype == B2U_F32) return convT_v2_launch<1>(ta, tb, gp, grid, smem, st);
+  if (d->dtype == B2U_F16) return convT_v2_launch<2>(ta, tb, gp, grid, smem, st);
+  return convT_v2_launch<0>(ta, tb, gp, grid, smem, st);
 }
 
 }  // namespace b2u

@@ -65,15 +65,16 @@ __device__ __forceinline__ void epilogue_stats(const float (&x)[32], bool valid,
   if (lane % LPV == 0) scratch[lane / LPV] = v[0];
 }
 
-template <int BLOCK_N, bool kTf32>
+template <int BLOCK_N, int kFmt>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
-  using OutT = typename std::conditional<kTf32, float, __nv_bfloat16>::type;
+  constexpr bool kTf32 = kFmt == 1;
+  using OutT = typename FmtTraits<kFmt>::T;
   constexpr int kBBytes = BLOCK_N * 128;
   constexpr int kKElems = kTf32 ? 32 : 64;       // K elements per 128-byte row
   constexpr int kUmmaK = kTf32 ? 8 : 16;         // 32 bytes of K per tcgen05.mma
-  constexpr uint32_t kIdesc = umma_idesc(kBlockM, BLOCK_N, kTf32 ? 2 : 1);
+  constexpr uint32_t kIdesc = umma_idesc(kBlockM, BLOCK_N, FmtTraits<kFmt>::kIdescFmt);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -202,26 +203,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       if (valid) {
-        if constexpr (kTf32) {
-          float4* dst = reinterpret_cast<float4*>(yrow + chunk * 32);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dst[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-        } else {
-          uint4* dst = reinterpret_cast<uint4*>(yrow + chunk * 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 a = __floats2bfloat162_rn(x[8 * i], x[8 * i + 1]);
-            __nv_bfloat162 b = __floats2bfloat162_rn(x[8 * i + 2], x[8 * i + 3]);
-            __nv_bfloat162 c = __floats2bfloat162_rn(x[8 * i + 4], x[8 * i + 5]);
-            __nv_bfloat162 d = __floats2bfloat162_rn(x[8 * i + 6], x[8 * i + 7]);
-            uint4 v;
-            v.x = *reinterpret_cast<uint32_t*>(&a);
-            v.y = *reinterpret_cast<uint32_t*>(&b);
-            v.z = *reinterpret_cast<uint32_t*>(&c);
-            v.w = *reinterpret_cast<uint32_t*>(&d);
-            dst[i] = v;
-          }
-        }
+        store_chunk32<OutT>(yrow + chunk * 32, x);
       }
     }
     if (p.sgs_log2 >= 0) {
@@ -273,7 +255,7 @@ int conv_encode_map(CUtensorMap* map, int dtype, int rank, const void* base, con
     return B2U_ERR_CUDA;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(map, dtype == B2U_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+  CUresult r = fn(map, dtype == B2U_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (dtype == B2U_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), rank,
                   const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -317,7 +299,7 @@ struct Plan {
 
 int conv_validate_desc(const b2u_conv_desc* d) {
   B2U_REQUIRE(d != nullptr, "null descriptor");
-  B2U_REQUIRE(d->dtype == B2U_BF16 || d->dtype == B2U_F32, "dtype must be B2U_BF16 or B2U_F32");
+  B2U_REQUIRE(d->dtype == B2U_BF16 || d->dtype == B2U_F32 || d->dtype == B2U_F16, "dtype must be B2U_BF16, B2U_F16 or B2U_F32");
   const int ke = d->dtype == B2U_F32 ? 32 : 64;
   B2U_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0, "empty tensor (n=%d h=%d w=%d)", d->n, d->h, d->w);
   B2U_REQUIRE(d->cin > 0 && d->cin % ke == 0, "cin=%d must be a positive multiple of %d", d->cin, ke);
@@ -355,7 +337,7 @@ static int make_plan(const b2u_conv_desc* d, bool conv_t, Plan* pl) {
   return B2U_OK;
 }
 
-template <int BN, bool TF>
+template <int BN, int TF>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& gp, dim3 grid, size_t smem,
                        cudaStream_t st) {
   static bool attr_set = false;       // per instantiation; the value only ever grows to the device max
@@ -421,12 +403,16 @@ static int run_gemm(const void* x, const void* wpacked, void* y, float* partials
 
   dim3 grid(static_cast<unsigned>(d->n) * pl.tiles_w * pl.tiles_h, gp.n_tiles_per_tap * (conv_t ? 4 : 1));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool tf = d->dtype == B2U_F32;
+#define B2U_V1_CASE(BN)                                                                   \
+  if (d->dtype == B2U_F32) return launch_gemm<BN, 1>(ta, tb, gp, grid, pl.smem, st);         \
+  if (d->dtype == B2U_F16) return launch_gemm<BN, 2>(ta, tb, gp, grid, pl.smem, st);         \
+  return launch_gemm<BN, 0>(ta, tb, gp, grid, pl.smem, st);
   switch (pl.block_n) {
-    case 64: return tf ? launch_gemm<64, true>(ta, tb, gp, grid, pl.smem, st) : launch_gemm<64, false>(ta, tb, gp, grid, pl.smem, st);
-    case 128: return tf ? launch_gemm<128, true>(ta, tb, gp, grid, pl.smem, st) : launch_gemm<128, false>(ta, tb, gp, grid, pl.smem, st);
-    default: return tf ? launch_gemm<256, true>(ta, tb, gp, grid, pl.smem, st) : launch_gemm<256, false>(ta, tb, gp, grid, pl.smem, st);
+    case 64: B2U_V1_CASE(64)
+    case 128: B2U_V1_CASE(128)
+    default: B2U_V1_CASE(256)
   }
+#undef B2U_V1_CASE
 }
 
 // ----------------------------------------------------------------------------- weight packing
@@ -524,6 +510,7 @@ extern "C" int b2u_pack_conv3x3_weight(const float* w, void* packed, int cout, i
   long total = 9L * cout * cin;
   int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   if (dtype == B2U_F32) pack_conv3x3_kernel<float><<<blocks, 256, 0, st>>>(w, static_cast<float*>(packed), cout, cin, transpose_flip);
+  else if (dtype == B2U_F16) pack_conv3x3_kernel<__half><<<blocks, 256, 0, st>>>(w, static_cast<__half*>(packed), cout, cin, transpose_flip);
   else pack_conv3x3_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(packed), cout, cin, transpose_flip);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
@@ -536,6 +523,8 @@ extern "C" int b2u_pack_conv3x3_weight_pair(const float* w, void* packed_fwd, vo
   dim3 grid(cin / 32, cout / 32);
   if (dtype == B2U_F32)
     pack_conv3x3_pair_kernel<float><<<grid, 256, 0, st>>>(w, static_cast<float*>(packed_fwd), static_cast<float*>(packed_dgrad), cout, cin);
+  else if (dtype == B2U_F16)
+    pack_conv3x3_pair_kernel<__half><<<grid, 256, 0, st>>>(w, static_cast<__half*>(packed_fwd), static_cast<__half*>(packed_dgrad), cout, cin);
   else
     pack_conv3x3_pair_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(packed_fwd),
                                                                    static_cast<__nv_bfloat16*>(packed_dgrad), cout, cin);
@@ -548,6 +537,7 @@ extern "C" int b2u_pack_convT2x2_weight(const float* w, void* packed, int cin, i
   long total = 4L * cout * cin;
   int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   if (dtype == B2U_F32) pack_convT_kernel<float><<<blocks, 256, 0, st>>>(w, static_cast<float*>(packed), cin, cout);
+  else if (dtype == B2U_F16) pack_convT_kernel<__half><<<blocks, 256, 0, st>>>(w, static_cast<__half*>(packed), cin, cout);
   else pack_convT_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(packed), cin, cout);
   B2U_LAUNCH_CHECK();
   return B2U_OK;

@@ -616,6 +616,8 @@ extern "C" int b2u_conv_first_fwd(const float* x_nchw, const float* w, void* y, 
   } while (0)
   if (dtype == B2U_F32) {
     if (cin == 1) B2U_LAUNCH_FIRST(float, 1); else B2U_LAUNCH_FIRST(float, 3);
+  } else if (dtype == B2U_F16) {
+    if (cin == 1) B2U_LAUNCH_FIRST(__half, 1); else B2U_LAUNCH_FIRST(__half, 3);
   } else {
     if (cin == 1) B2U_LAUNCH_FIRST(__nv_bfloat16, 1); else B2U_LAUNCH_FIRST(__nv_bfloat16, 3);
   }
@@ -680,14 +682,14 @@ extern "C" int b2u_gn_apply(const void* x, const float* coef, const uint32_t* ma
   if (bpi < 1) bpi = 1;
   dim3 grid(static_cast<unsigned>(bpi), d->n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (d->dtype == B2U_F32)
-    gn_apply_kernel<float><<<grid, threads, 0, st>>>(static_cast<const float*>(x), reinterpret_cast<const float2*>(coef),
-                                                 reinterpret_cast<const uint8_t*>(mask1), reinterpret_cast<const uint8_t*>(mask2),
-                                                 keep_counts2, static_cast<float*>(out), p);
-  else
-    gn_apply_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(x), reinterpret_cast<const float2*>(coef),
-                                                         reinterpret_cast<const uint8_t*>(mask1), reinterpret_cast<const uint8_t*>(mask2),
-                                                         keep_counts2, static_cast<__nv_bfloat16*>(out), p);
+#define B2U_APPLY_T(T)                                                                                                  \
+  gn_apply_kernel<T><<<grid, threads, 0, st>>>(static_cast<const T*>(x), reinterpret_cast<const float2*>(coef),            \
+                                               reinterpret_cast<const uint8_t*>(mask1), reinterpret_cast<const uint8_t*>(mask2), \
+                                               keep_counts2, static_cast<T*>(out), p)
+  if (d->dtype == B2U_F32) B2U_APPLY_T(float);
+  else if (d->dtype == B2U_F16) B2U_APPLY_T(__half);
+  else B2U_APPLY_T(__nv_bfloat16);
+#undef B2U_APPLY_T
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -721,16 +723,15 @@ extern "C" int b2u_gn_apply_pool(const void* x, const float* coef, const uint32_
   dim3 grid(rows, d->n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* parts = pool_num_groups > 0 ? pool_partials : nullptr;
-  if (d->dtype == B2U_F32)
-    gn_apply_pool_kernel<float><<<grid, threads, smem, st>>>(
-        static_cast<const float*>(x), reinterpret_cast<const float2*>(coef), reinterpret_cast<const uint8_t*>(mask1),
-        reinterpret_cast<const uint8_t*>(mask2), keep_counts2, static_cast<float*>(skip_out), static_cast<float*>(pooled),
-        parts, argmax, sgs, p);
-  else
-    gn_apply_pool_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(
-        static_cast<const __nv_bfloat16*>(x), reinterpret_cast<const float2*>(coef), reinterpret_cast<const uint8_t*>(mask1),
-        reinterpret_cast<const uint8_t*>(mask2), keep_counts2, static_cast<__nv_bfloat16*>(skip_out),
-        static_cast<__nv_bfloat16*>(pooled), parts, argmax, sgs, p);
+#define B2U_POOL_T(T)                                                                                                   \
+  gn_apply_pool_kernel<T><<<grid, threads, smem, st>>>(                                                                   \
+      static_cast<const T*>(x), reinterpret_cast<const float2*>(coef), reinterpret_cast<const uint8_t*>(mask1),            \
+      reinterpret_cast<const uint8_t*>(mask2), keep_counts2, static_cast<T*>(skip_out), static_cast<T*>(pooled), parts,    \
+      argmax, sgs, p)
+  if (d->dtype == B2U_F32) B2U_POOL_T(float);
+  else if (d->dtype == B2U_F16) B2U_POOL_T(__half);
+  else B2U_POOL_T(__nv_bfloat16);
+#undef B2U_POOL_T
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -746,14 +747,14 @@ extern "C" int b2u_head_fwd(const void* x, const float* coef, const uint32_t* ma
   const long groups = static_cast<long>(d->h0) * d->w0;
   const int grid = grid_for((groups + kHeadPix - 1) / kHeadPix * (d->c / 8), 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (d->dtype == B2U_F32)
-    head_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), reinterpret_cast<const float2*>(coef),
-                                             reinterpret_cast<const uint8_t*>(mask1), w_head, out, logits, fov, acc, samples,
-                                             iter_base, *d);
-  else
-    head_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), reinterpret_cast<const float2*>(coef),
-                                                     reinterpret_cast<const uint8_t*>(mask1), w_head, out, logits, fov, acc,
-                                                     samples, iter_base, *d);
+#define B2U_HEAD_T(T)                                                                                                   \
+  head_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), reinterpret_cast<const float2*>(coef),                    \
+                                       reinterpret_cast<const uint8_t*>(mask1), w_head, out, logits, fov, acc, samples,    \
+                                       iter_base, *d)
+  if (d->dtype == B2U_F32) B2U_HEAD_T(float);
+  else if (d->dtype == B2U_F16) B2U_HEAD_T(__half);
+  else B2U_HEAD_T(__nv_bfloat16);
+#undef B2U_HEAD_T
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

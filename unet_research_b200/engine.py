@@ -30,7 +30,7 @@ GN_EPS = 1e-5
 
 
 def _torch_dtype(dtype: int):
-    return torch.float32 if dtype == _lib.F32 else torch.bfloat16
+    return {_lib.F32: torch.float32, _lib.F16: torch.float16}.get(dtype, torch.bfloat16)
 
 
 def device_rand_geometry() -> Tuple[int, int]:
