@@ -187,6 +187,14 @@ typedef struct {
  * philox_offset (lets a captured CUDA graph advance the stream between replays); may be NULL. */
 int b2u_dropblock_centers(const b2u_dropblock_call* table, int n_calls, uint64_t seed,
                           const unsigned long long* offset_base, uint32_t* center_bits, void* stream);
+/* Dropblock2d_ichan (utils_modules.py:86-139): centres = torch.bernoulli(p = gamma) over the full [N,C,H,W] tensor
+ * (ATen bernoulli_tensor_cuda_kernel: thread idx draws one curand_uniform4 for elements 4*idx..4*idx+3, `u <= p`),
+ * border of bs/2 zeroed; written into the same compact centre bitmap, so b2u_dropblock_dilate follows unchanged.
+ * call.numel = n_img*c*h*w, call.thresh_lo = largest raw Philox word whose uniform is <= float(gamma).
+ * center_words_total: size of center_bits in uint32 words (zeroed by this call). */
+int b2u_dropblock_centers_ichan(const b2u_dropblock_call* table, int n_calls, const b2u_dropblock_call* host_table,
+                                uint64_t seed, const unsigned long long* offset_base, uint32_t* center_bits,
+                                long long center_words_total, void* stream);
 int b2u_dropblock_dilate(const b2u_dropblock_call* table, int n_calls, const b2u_dropblock_call* host_table,
                          const uint32_t* center_bits, uint32_t* mask_bits, unsigned long long* keep_counts,
                          void* stream);

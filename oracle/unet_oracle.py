@@ -60,6 +60,36 @@ def dropblock2d(x: Tensor, drop_prob: float, block_size: int, training: bool = T
     return out
 
 
+def dropblock2d_ichan(x: Tensor, drop_prob: float, block_size: int, training: bool = True,
+                      bernoulli_fn: Callable = torch.bernoulli, record: Optional[list] = None) -> Tensor:
+    """R/utils/utils_modules.py:106-139 (`Dropblock2d_ichan.forward`), out of place.  `bernoulli_fn` is the draw
+    (`torch.bernoulli(torch.ones_like(tensor) * gamma)`, :113-114)."""
+    if not training or drop_prob == 0.:
+        return x
+    fx, fy = x.shape[2], x.shape[3]
+    keep_prob = 1 - drop_prob
+    gamma = (1 - keep_prob) / (block_size ** 2) * (fx * fy) / ((fx - block_size + 1) * (fy - block_size + 1))   # :96-99
+    gamma = min(gamma, 1)
+    mask = bernoulli_fn(torch.ones_like(x) * gamma).clone()
+    ex = block_size // 2                                                                    # :116-121
+    mask[:, :, :ex] = 0
+    mask[:, :, :, :ex] = 0
+    mask[:, :, fx - ex:] = 0
+    mask[:, :, :, fy - ex:] = 0
+    shp = mask.shape
+    mp = F.max_pool2d(mask.view(-1, 1, shp[2], shp[3]), kernel_size=(block_size, block_size), stride=(1, 1),
+                      padding=block_size // 2).view(shp)                                      # :123-127
+    mask = 1 - mp
+    if record is not None:
+        record.append(mask)
+    out = x * mask
+    total = mask.numel()
+    den = 1. - torch.true_divide(total - torch.sum(mask), total)                            # :133-137
+    if den != 0:
+        out = out * (1. / den)
+    return out
+
+
 def linear_scheduler_values(start_value: float, stop_value: float, nr_steps: int) -> np.ndarray:
     """`dropblock==0.3.0` `LinearScheduler.__init__`: `np.linspace(start, stop, int(nr_steps))`;
     `step()` assigns `drop_values[i]` to `dropblock.drop_prob` while `i < len` and increments i.
@@ -73,11 +103,14 @@ class DropBlockCfg:
     (drop_prob, block_size) pair used at all 22 sites, each site drawing its own mask."""
 
     def __init__(self, drop_prob: float = 0.0, block_size: int = 7, training: bool = True,
-                 rand_fn: Callable = torch.rand):
+                 rand_fn: Callable = torch.rand, mode: str = "dropblock2d", bernoulli_fn: Callable = torch.bernoulli):
         self.drop_prob, self.block_size, self.training, self.rand_fn = drop_prob, block_size, training, rand_fn
+        self.mode, self.bernoulli_fn = mode, bernoulli_fn          # "ichan": Dropblock2d_ichan (utils_modules.py:86-139)
         self.masks: Optional[list] = None      # set to [] to record block masks in call order
 
     def __call__(self, x: Tensor) -> Tensor:
+        if self.mode == "ichan":
+            return dropblock2d_ichan(x, self.drop_prob, self.block_size, self.training, self.bernoulli_fn, self.masks)
         return dropblock2d(x, self.drop_prob, self.block_size, self.training, self.rand_fn, self.masks)
 
 

@@ -18,7 +18,7 @@ import traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["info", "conv", "convv1", "convv2", "wgrad", "bwdk", "convt", "first", "gn", "pool", "head", "dropblock", "rotate", "forward", "mc", "rot_ens", "tf32", "train", "traingraph", "precision"]
+SECTIONS = ["info", "conv", "convv1", "convv2", "wgrad", "bwdk", "convt", "first", "gn", "pool", "head", "dropblock", "rotate", "forward", "mc", "rot_ens", "tf32", "train", "traingraph", "precision", "ichan"]
 
 
 def rel(a, b):
@@ -574,6 +574,77 @@ def sec_dropblock():
         exact_keep = int(rec[0].double().sum())
         res.append({"mismatches": mism, "keep": int(keep), "keep_ref": exact_keep, "offset": off_got, "offset_ref": off_ref, "out_rel": r})
     return res
+
+
+def sec_ichan():
+    """Dropblock2d_ichan: masks bit-exact against torch.bernoulli on the same device / seed / offset, then the U-Net
+    forward and the Monte-Carlo loop with the ichan layer at all 22 sites against the oracle."""
+    import torch
+    from torch import nn
+    from oracle import unet_oracle as O
+    import unet_research_b200 as U
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    ok = True
+    for shape in [(1, 64, 128, 128), (2, 32, 37, 36), (1, 64, 592, 576), (1, 1024, 37, 36), (3, 96, 9, 50)]:
+        x = torch.randn(*shape, device=dev)
+        layer = U.Dropblock2d_ichan(0.15, 7)
+        layer.train()
+        torch.manual_seed(4242)
+        torch.rand(5, device=dev)                                  # move the generator off offset 0
+        off0 = torch.cuda.default_generators[0].get_offset()
+        m, keep = layer.block_mask(x)
+        off1 = torch.cuda.default_generators[0].get_offset()
+        torch.manual_seed(4242)
+        torch.rand(5, device=dev)
+        rec = []
+        yref = O.dropblock2d_ichan(x, 0.15, 7, True, record=rec)
+        off1r = torch.cuda.default_generators[0].get_offset()
+        mism = int((m != rec[0]).sum())
+        torch.manual_seed(4242)
+        torch.rand(5, device=dev)
+        y = layer(x.clone())
+        rr = rel(y, yref)[0]
+        good = mism == 0 and int(keep.item()) == int(rec[0].sum().item()) and off1 == off1r and rr < 1e-6
+        ok &= good
+        print(f"  ichan {shape}: mask mismatches {mism} / {m.numel()}  keep {int(keep.item())} vs {int(rec[0].sum().item())}  "
+              f"offset {off1 - off0} vs {off1r - off0}  out rel {rr:.2e}")
+    # U-Net forward, ichan at all sites
+    h, w = 120, 116
+    x = synthetic.make_image(h, w, seed=1234).to(dev)
+    fov = synthetic.make_fov_mask(h, w).to(dev)
+    m = U.UNet(init_channels=1, filters=64, output_channels=1, model_depth=4)
+    m.set_activation_function(nn.ReLU())
+    m.set_dropblock(U.Dropblock2d_ichan, block_size=7, drop_prob=0.15, use_scheduler=False)
+    m.set_normalization(nn.GroupNorm, params={"num_groups": 32, "num_channels": "fill"})
+    m.create_model()
+    sd = synthetic.make_state_dict(seed=1234)
+    m.load_state_dict(sd)
+    m.to(dev).eval()
+    m.apply(U.set_dropblock_on)
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    with torch.no_grad():
+        torch.manual_seed(99)
+        y = m(x)
+        o1 = torch.cuda.default_generators[0].get_offset()
+        torch.manual_seed(99)
+        yr = O.unet_forward(sdd, x, dropblock=O.DropBlockCfg(0.15, 7, True, mode="ichan"))
+        o2 = torch.cuda.default_generators[0].get_offset()
+    r1 = rel(y, yr)[0]
+    ev = U.DropBlockEval(m, num_iterations=6, return_num=3, iter_batch=2)
+    torch.manual_seed(1234)
+    _, (mean, std, tens) = ev.predict_step((x, None, fov), 0)
+    torch.manual_seed(1234)
+    outs = []
+    with torch.no_grad():
+        for _ in range(6):
+            outs.append(O.unet_forward(sdd, x, dropblock=O.DropBlockCfg(0.15, 7, True, mode="ichan")) * fov)
+    st = torch.stack(outs)
+    r2, r3 = rel(tens, st[:3].unsqueeze(1))[0], rel(mean, st.mean(0))[0]
+    ds = float((std - st.std(0)).abs().max())
+    print(f"  ichan unet forward rel {r1:.3e} (offset {o1} vs {o2}); mc samples rel {r2:.3e} mean rel {r3:.3e} max|dstd| {ds:.2e}")
+    ok &= r1 < 1e-2 and o1 == o2 and r2 < 1e-2 and r3 < 5e-3 and ds < 1.5e-2
+    return {"ok": bool(ok)}
 
 
 def sec_rotate():

@@ -244,6 +244,12 @@ def test_mc_dropblock_fp16_mode():
     assert float((std - rstd).abs().max()) < 5e-3
 
 
+def test_dropblock2d_ichan():
+    """`Dropblock2d_ichan` masks bit-exact vs torch.bernoulli on the same device/seed/offset (incl.
+    the generator bookkeeping), and the U-Net forward / MC loop with it against the oracle."""
+    assert D.sec_ichan()["ok"]
+
+
 def test_fused_sgd_matches_torch():
     """FusedSGD (clip + momentum SGD in two launches) against torch.nn.utils.clip_grad_norm_ + torch.optim.SGD
     (reference training.py:32 + Lightning gradient_clip_val) over several steps, ragged tensor sizes included."""

@@ -165,3 +165,34 @@ def test_offset_increment_formula():
     assert P.torch_rand_grid(64 * 586 * 570) == 1184
     assert P.torch_rand_offset_increment(64 * 586 * 570) == ((64 * 586 * 570 - 1) // (1184 * 256 * 4) + 1) * 4
     assert P.torch_rand_offset_increment(100) == 4
+
+
+def test_dropblock_ichan_layer_matches_reference(golden_dir):
+    """Dropblock2d_ichan (utils_modules.py:86-139) with the reference's own bernoulli draw fed back in."""
+    g = _load(golden_dir, "dropblock_ichan_layer.npz")
+    draw = torch.from_numpy(g["draw"])
+    y = O.dropblock2d_ichan(torch.from_numpy(g["x"]), 0.15, 7, True, bernoulli_fn=lambda p: draw.clone())
+    np.testing.assert_allclose(y.numpy(), g["y"], rtol=1e-6, atol=1e-7)
+    # inactive in eval mode / at drop_prob 0 (:107-108)
+    x = torch.from_numpy(g["x"])
+    assert O.dropblock2d_ichan(x, 0.15, 7, False) is x and O.dropblock2d_ichan(x, 0.0, 7, True) is x
+
+
+def test_unet_forward_ichan_matches_reference(golden_dir, sd):
+    """U-Net forward with Dropblock2d_ichan at all 22 sites, the reference's 22 bernoulli draws replayed in call order."""
+    g = _load(golden_dir, "unet_ichan_fwd_120x116.npz")
+    shapes = g["shapes"]
+    assert len(shapes) == 22
+    it = iter(range(22))
+
+    def replay(p):
+        i = next(it)
+        shp = tuple(int(v) for v in shapes[i])
+        assert tuple(p.shape) == shp
+        n = int(np.prod(shp))
+        return torch.from_numpy(np.unpackbits(g[f"draw{i:02d}"])[:n].reshape(shp).astype(np.float32))
+
+    x = synthetic.make_image(H, W, seed=1234)
+    with torch.no_grad():
+        y = O.unet_forward(sd, x, dropblock=O.DropBlockCfg(0.15, 7, True, mode="ichan", bernoulli_fn=replay))
+    np.testing.assert_allclose(y.numpy(), g["output"], rtol=0, atol=5e-6)

@@ -74,6 +74,47 @@ __global__ void __launch_bounds__(256) dropblock_centers_kernel(const b2u_dropbl
   }
 }
 
+// Dropblock2d_ichan (reference utils_modules.py:86-139) draws `torch.bernoulli(ones_like(x) * gamma)` over the FULL
+// [N,C,H,W] tensor and then zeroes a border of bs/2 (:117-121).  ATen's bernoulli_tensor_cuda_kernel
+// (DistributionTemplates.h:608-650) runs CUDA_tensor_apply2 with step 4 and 512-thread blocks, grid =
+// ceil(numel / 2048): thread idx owns elements 4*idx .. 4*idx+3 and draws ONE curand_uniform4 after
+// curand_init(seed, idx, offset), i.e. Philox counter (offset/4, 0, idx, 0); element k is 1 iff uniform_k <= p.
+// The surviving (interior) centres are written into the same compact (H-bs+1) x (W-bs+1) bitmap the DropBlock2D
+// path uses, so the dilate kernel is shared.  Centres are sparse (gamma ~ 0.3 %): set bits go through atomicOr
+// onto a zeroed bitmap.  call.numel = n_img*c*h*w, call.thresh_lo = largest raw word whose uniform is <= p.
+__global__ void __launch_bounds__(256) dropblock_centers_ichan_kernel(const b2u_dropblock_call* __restrict__ table, uint64_t seed,
+                                               const unsigned long long* __restrict__ offset_base,
+                                               uint32_t* __restrict__ center_bits) {
+  const b2u_dropblock_call c = table[blockIdx.y];
+  const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+  const uint64_t e0 = static_cast<uint64_t>(idx) * 4ull;
+  if (e0 >= c.numel) return;
+  const uint64_t off = c.philox_offset + (offset_base ? *offset_base : 0ull);
+  const uint64_t ctr = off >> 2;
+  uint32_t r[4];
+  philox4x32_10(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), idx, 0u, static_cast<uint32_t>(seed),
+                static_cast<uint32_t>(seed >> 32), r);
+  const uint32_t t = c.thresh_lo;
+  if (!(r[0] <= t || r[1] <= t || r[2] <= t || r[3] <= t)) return;
+  const int ex = c.block_size >> 1;
+  const int hc = c.h - c.block_size + 1, wc = c.w - c.block_size + 1;
+  uint32_t* out = center_bits + c.center_word_off;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t e = e0 + k;
+    if (r[k] <= t && e < c.numel) {
+      const uint32_t x = static_cast<uint32_t>(e % c.w);
+      const uint64_t q = e / c.w;
+      const uint32_t y = static_cast<uint32_t>(q % c.h);
+      const uint32_t plane = static_cast<uint32_t>(q / c.h);
+      if (static_cast<int>(y) >= ex && static_cast<int>(y) < c.h - ex && static_cast<int>(x) >= ex && static_cast<int>(x) < c.w - ex) {
+        const uint32_t bit = (plane * hc + (y - ex)) * wc + (x - ex);
+        atomicOr(out + (bit >> 5), 1u << (bit & 31u));
+      }
+    }
+  }
+}
+
 __global__ void dropblock_centers_from_uniform_kernel(const float* __restrict__ u, uint32_t* __restrict__ bits,
                                                       long long numel, float gamma) {
   const long long nwords = (numel + 31) / 32;
@@ -213,6 +254,24 @@ extern "C" int b2u_dropblock_centers(const b2u_dropblock_call* table, int n_call
   // torch's grid.x never exceeds SMs * (maxThreadsPerSM / 256); calls with a smaller grid exit early
   dim3 grid(sms * (mt / 256), n_calls);
   dropblock_centers_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, seed, offset_base, center_bits);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_dropblock_centers_ichan(const b2u_dropblock_call* table, int n_calls, const b2u_dropblock_call* host_table,
+                                           uint64_t seed, const unsigned long long* offset_base, uint32_t* center_bits,
+                                           long long center_words_total, void* stream) {
+  B2U_REQUIRE(table && host_table && center_bits && n_calls > 0 && center_words_total > 0, "bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint32_t max_numel = 0;
+  for (int i = 0; i < n_calls; ++i) {
+    B2U_REQUIRE(host_table[i].block_size >= 1 && (host_table[i].block_size & 1), "block_size must be odd");
+    if (host_table[i].numel > max_numel) max_numel = host_table[i].numel;
+  }
+  B2U_CHECK_CUDA(cudaMemsetAsync(center_bits, 0, static_cast<size_t>(center_words_total) * 4, st));
+  const unsigned threads_needed = (max_numel + 3u) / 4u;
+  dim3 grid((threads_needed + 255u) / 256u, n_calls);
+  dropblock_centers_ichan_kernel<<<grid, 256, 0, st>>>(table, seed, offset_base, center_bits);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -75,15 +75,36 @@ def philox_thresholds(gamma: float) -> Tuple[int, int]:
 _THRESH_CACHE: Dict[Tuple[float, int, int, int], Tuple[int, int]] = {}
 
 
-def _thresholds_cached(drop_prob: float, block_size: int, h: int, w: int) -> Tuple[int, int]:
-    key = (float(drop_prob), block_size, h, w)
+def _thresholds_cached(drop_prob: float, block_size: int, h: int, w: int, mode: str = "dropblock2d") -> Tuple[int, int]:
+    key = (float(drop_prob), block_size, h, w, mode)
     v = _THRESH_CACHE.get(key)
     if v is None:
         if len(_THRESH_CACHE) > 4096:
             _THRESH_CACHE.clear()
-        v = philox_thresholds(dropblock_gamma(drop_prob, block_size, h, w))
+        if mode == "ichan":                      # utils_modules.py:98-102: min(gamma, 1), compared with `<=`
+            t = philox_threshold_le(min(dropblock_gamma(drop_prob, block_size, h, w), 1.0))
+            v = (max(t, 0), 0) if t >= 0 else (0, 0)
+        else:
+            v = philox_thresholds(dropblock_gamma(drop_prob, block_size, h, w))
         _THRESH_CACHE[key] = v
     return v
+
+
+def philox_threshold_le(p: float) -> int:
+    """Largest raw Philox word whose `curand_uniform` value is <= float32(p) (torch.bernoulli's `rand <= p`,
+    DistributionTemplates.h:622-641); -1 when no word qualifies.  Bisection on the exact fp32 arithmetic."""
+    pf = np.float32(p)
+    lo, hi = 0, 1 << 32                      # first word with uniform > p
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if _uniform_f32(np.array([mid], dtype=np.uint32))[0] <= pf:
+            lo = mid + 1
+        else:
+            hi = mid
+    return lo - 1
+
+
+BERNOULLI_OFFSET_INCREMENT = 12              # gen->philox_cuda_state(10), rounded up to a multiple of 4
 
 
 def rand_grid(numel: int, sms: int, max_threads: int) -> int:
@@ -116,9 +137,14 @@ class MaskPlan:
     one call covering the whole batch).  Holds the call table, bitmaps and keep counters."""
 
     def __init__(self, n_calls: int, images_per_call: int, h: int, w: int, filters: int, depth: int,
-                 drop_prob: float, block_size: int, device):
+                 drop_prob: float, block_size: int, device, mode: str = "dropblock2d"):
+        """mode "dropblock2d": DropBlock2D (torch.rand over the interior grid, utils_modules.py:49);
+        mode "ichan": Dropblock2d_ichan (torch.bernoulli over the full tensor, border zeroed, :113-121)."""
         if block_size % 2 == 0 or block_size > 31:
             raise NotImplementedError("CUDA DropBlock supports odd block_size <= 31 (reference default 7)")
+        if mode not in ("dropblock2d", "ichan"):
+            raise ValueError(f"unknown DropBlock mode {mode!r}")
+        self.mode = mode
         self.n_calls, self.ipc = n_calls, images_per_call
         self.drop_prob, self.block_size = float(drop_prob), int(block_size)
         self.sites = site_shapes(h, w, filters, depth)
@@ -137,14 +163,20 @@ class MaskPlan:
                 raise ValueError(f"feature map {hh}x{ww} smaller than block_size {block_size} "
                                  "(the reference fails here too: negative dimension)")
             site_prefix.append(per_iter)
-            per_iter += rand_offset_increment(images_per_call * c * (hh - block_size + 1) * (ww - block_size + 1), sms, mt)
+            if mode == "ichan":
+                per_iter += BERNOULLI_OFFSET_INCREMENT
+            else:
+                per_iter += rand_offset_increment(images_per_call * c * (hh - block_size + 1) * (ww - block_size + 1), sms, mt)
         self.offset_per_call = per_iter
         k = 0
         for s, (c, hh, ww) in enumerate(self.sites):
             self.mask_site_off.append(mask_words)
             hc, wc = hh - block_size + 1, ww - block_size + 1
-            numel = images_per_call * c * hc * wc
-            lo, hi = _thresholds_cached(drop_prob, block_size, hh, ww)
+            numel = images_per_call * c * hc * wc                  # bits of the compact centre bitmap
+            draws = images_per_call * c * hh * ww if mode == "ichan" else numel
+            if draws >= 2 ** 32:
+                raise NotImplementedError("one DropBlock call is limited to 2^32 - 1 random draws")
+            lo, hi = _thresholds_cached(drop_prob, block_size, hh, ww, mode)
             self.numel_per_call.append(float(images_per_call * c * hh * ww))
             for b in range(n_calls):
                 d = calls[k]
@@ -152,7 +184,7 @@ class MaskPlan:
                 d.philox_offset = b * per_iter + site_prefix[s]
                 d.center_word_off = center_words
                 d.mask_word_off = mask_words + b * images_per_call * hh * ww * (c // 32)
-                d.numel = numel
+                d.numel = draws
                 d.grid = rand_grid(numel, sms, mt)
                 d.thresh_lo, d.thresh_hi = lo, hi
                 d.n_img, d.c, d.h, d.w = images_per_call, c, hh, ww
@@ -163,6 +195,7 @@ class MaskPlan:
         self.host_table = calls
         raw = np.frombuffer(bytes(calls), dtype=np.uint8).copy()
         self.table = torch.from_numpy(raw).to(device)
+        self.center_words = center_words + 4
         self.center_bits = torch.zeros(center_words + 4, dtype=torch.int32, device=device)
         self.mask_bits = torch.empty(mask_words, dtype=torch.int32, device=device)
         self.keep_counts = torch.zeros(self.n_sites * n_calls, dtype=torch.int64, device=device)
@@ -177,7 +210,7 @@ class MaskPlan:
         self.drop_prob = drop_prob
         k = 0
         for s, (c, hh, ww) in enumerate(self.sites):
-            lo, hi = _thresholds_cached(drop_prob, self.block_size, hh, ww)
+            lo, hi = _thresholds_cached(drop_prob, self.block_size, hh, ww, self.mode)
             for b in range(self.n_calls):
                 self.host_table[k].thresh_lo, self.host_table[k].thresh_hi = lo, hi
                 k += 1
@@ -191,8 +224,12 @@ class MaskPlan:
         """Launch both mask phases for the whole table (reads the stream position from `offset_base`)."""
         self.keep_counts.zero_()
         n = self.n_calls * self.n_sites
-        call("b2u_dropblock_centers", ptr(self.table), n, C.c_uint64(seed & (2 ** 64 - 1)), ptr(self.offset_base),
-             ptr(self.center_bits), stream_ptr())
+        if self.mode == "ichan":
+            call("b2u_dropblock_centers_ichan", ptr(self.table), n, self.host_table, C.c_uint64(seed & (2 ** 64 - 1)),
+                 ptr(self.offset_base), ptr(self.center_bits), self.center_words, stream_ptr())
+        else:
+            call("b2u_dropblock_centers", ptr(self.table), n, C.c_uint64(seed & (2 ** 64 - 1)), ptr(self.offset_base),
+                 ptr(self.center_bits), stream_ptr())
         call("b2u_dropblock_dilate", ptr(self.table), n, self.host_table, ptr(self.center_bits), ptr(self.mask_bits),
              ptr(self.keep_counts), stream_ptr())
 

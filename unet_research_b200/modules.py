@@ -70,6 +70,97 @@ class DropBlock2D(nn.Module):
         return out
 
 
+class Dropblock2d_ichan(nn.Module):
+    """`Dropblock2d_ichan(drop_prob=0.5, block_size=3)` (reference utils_modules.py:86-139), the variant the six
+    multi-fidelity scripts train with (MF-training-UNI.py:244): centres are `torch.bernoulli(gamma)` draws over the
+    full feature map with a border of block_size//2 zeroed, gamma is clamped to 1, and the rescale is skipped when
+    everything was dropped.  Same setters/getters as the reference; inside a `UNet` the masks come from the fused CUDA
+    kernels (bit-exact with torch.bernoulli's CUDA stream), stand-alone `forward` applies them with the reference's
+    arithmetic."""
+
+    def __init__(self, drop_prob=0.5, block_size=3):
+        super().__init__()
+        self.drop_prob = drop_prob
+        self.block_size = block_size
+
+    def set_drop_prob(self, p):
+        self.drop_prob = p
+
+    def get_drop_prob(self):
+        return self.drop_prob
+
+    def get_gamma(self, feat_x, feat_y):
+        keep_prob = 1 - self.drop_prob
+        gamma = (1 - keep_prob) / (self.block_size ** 2) * (feat_x * feat_y) / ((feat_x - self.block_size + 1) * (feat_y - self.block_size + 1))
+        return min(gamma, 1)
+
+    def extra_repr(self):
+        return f"drop_prob={self.drop_prob}, block_size={self.block_size}"
+
+    def block_mask(self, x: torch.Tensor):
+        """(keep mask [N,C,H,W] float 0/1, keep_count int64[1]) for the current CUDA generator state; advances the
+        generator exactly like the reference's single torch.bernoulli call."""
+        from .engine import MaskPlan, BERNOULLI_OFFSET_INCREMENT
+        if not x.is_cuda:
+            raise _lib.B2uError("Dropblock2d_ichan needs a CUDA tensor: there is no CPU path")
+        n, c, h, w = x.shape
+        if c % 32 != 0:
+            raise NotImplementedError("CUDA DropBlock needs channels to be a multiple of 32")
+        plan = _SingleSitePlan(n, c, h, w, float(self.drop_prob), int(self.block_size), x.device, "ichan")
+        gen = torch.cuda.default_generators[x.device.index if x.device.index is not None else torch.cuda.current_device()]
+        plan.run(gen.initial_seed(), gen.get_offset())
+        gen.set_offset(gen.get_offset() + BERNOULLI_OFFSET_INCREMENT)
+        return plan.mask_nchw(x.dtype), plan.keep
+
+    def forward(self, tensor):
+        if not self.training or self.drop_prob == 0.:
+            return tensor
+        mask, _ = self.block_mask(tensor)
+        tensor *= mask                                             # in place, as the reference (:128)
+        total = mask.numel()
+        scale_denominator = 1. - torch.true_divide(total - torch.sum(mask), total)
+        if scale_denominator != 0:
+            tensor *= 1. / scale_denominator
+        return tensor
+
+
+class _SingleSitePlan:
+    """One DropBlock call outside a U-Net (stand-alone layer use): table of one entry + its bitmaps."""
+
+    def __init__(self, n, c, h, w, drop_prob, block_size, device, mode):
+        from .engine import _thresholds_cached
+        if block_size % 2 == 0 or block_size > 31:
+            raise NotImplementedError("CUDA DropBlock supports odd block_size <= 31")
+        self.n, self.c, self.h, self.w, self.mode = n, c, h, w, mode
+        hc, wc = h - block_size + 1, w - block_size + 1
+        if hc <= 0 or wc <= 0:
+            raise ValueError(f"feature map {h}x{w} smaller than block_size {block_size}")
+        d = DropblockCall()
+        d.philox_offset, d.center_word_off, d.mask_word_off = 0, 0, 0
+        d.numel = n * c * h * w if mode == "ichan" else n * c * hc * wc
+        d.thresh_lo, d.thresh_hi = _thresholds_cached(drop_prob, block_size, h, w, mode)
+        d.n_img, d.c, d.h, d.w, d.block_size, d.count_index = n, c, h, w, block_size, 0
+        self.d = d
+        self.words = (n * c * hc * wc + 31) // 32 + 4
+        self.centers = torch.zeros(self.words, dtype=torch.int32, device=device)
+        self.bits = torch.empty(n * h * w * (c // 32), dtype=torch.int32, device=device)
+        self.keep = torch.zeros(1, dtype=torch.int64, device=device)
+        self.device = device
+
+    def run(self, seed: int, offset: int):
+        self.d.philox_offset = offset
+        table = torch.from_numpy(np.frombuffer(bytes(self.d), dtype=np.uint8).copy()).to(self.device)
+        self.keep.zero_()
+        call("b2u_dropblock_centers_ichan", ptr(table), 1, C.byref(self.d), C.c_uint64(seed & (2 ** 64 - 1)), None,
+             ptr(self.centers), self.words, stream_ptr())
+        call("b2u_dropblock_dilate", ptr(table), 1, C.byref(self.d), ptr(self.centers), ptr(self.bits), ptr(self.keep), stream_ptr())
+
+    def mask_nchw(self, dtype):
+        shifts = torch.arange(32, device=self.device, dtype=torch.int32)
+        m = ((self.bits.view(self.n, self.h, self.w, self.c // 32, 1) >> shifts) & 1).reshape(self.n, self.h, self.w, self.c)
+        return m.permute(0, 3, 1, 2).to(dtype)
+
+
 class LinearScheduler(nn.Module):
     """`dropblock==0.3.0` LinearScheduler (third-party; imported by the reference at
     utils_modules.py:1 and used at utils_unet.py:128-132, 410-411).  Same attribute names

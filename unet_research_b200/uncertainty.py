@@ -21,12 +21,13 @@ from torch import nn
 from . import _lib
 from ._lib import call, ptr, stream_ptr
 from .engine import MaskPlan, UNetEngine
-from .modules import DropBlock2D
+from .modules import DropBlock2D, Dropblock2d_ichan
 
 
 def set_dropblock_on(layer):
-    """Dropblock_Uncertainty.py:22-25."""
-    if type(layer) == DropBlock2D:
+    """Dropblock_Uncertainty.py:22-25 (exact type check, as the reference); the `dropblock_i` runs submitted by
+    uncertainty_script.py:26 do the same for `Dropblock2d_ichan`."""
+    if type(layer) == DropBlock2D or type(layer) == Dropblock2d_ichan:
         layer.training = True
 
 
@@ -82,7 +83,9 @@ class MCRunner:
         self.overlap = overlap and active
         cin = self.eng.init_channels
         if active:
-            mk = lambda: MaskPlan(nb, 1, self.ws.h, self.ws.w, self.eng.filters, self.eng.depth, drop_prob, block_size, device)
+            mode = model._dropblock_mode()
+            mk = lambda: MaskPlan(nb, 1, self.ws.h, self.ws.w, self.eng.filters, self.eng.depth, drop_prob, block_size, device,
+                                  mode=mode)
             self.masks = [mk(), mk()] if self.overlap else [mk()]
             self.per_iter = self.masks[0].offset_per_call
         else:
@@ -206,7 +209,7 @@ class DropBlockEval(_MCBase):
 
     def _runner(self, nb, h0, w0, dev, active, p, bs) -> MCRunner:
         eng = self._model._get_engine(dev)              # re-packs weights if the parameters changed
-        key = (nb, h0, w0, str(dev), active, p, bs, self.return_num, id(eng))
+        key = (nb, h0, w0, str(dev), active, p, bs, self.return_num, id(eng), self._model._dropblock_mode())
         r = self._runners.get(key)
         if r is None:
             r = MCRunner(self._model, nb, h0, w0, dev, active, p, bs, self.return_num, self.use_cuda_graph, self.overlap_masks)

@@ -20,7 +20,7 @@ from torch import nn
 
 from . import _lib
 from .engine import MaskPlan, UNetEngine
-from .modules import DropBlock2D, LinearScheduler
+from .modules import DropBlock2D, Dropblock2d_ichan, LinearScheduler
 
 
 class UNet(nn.Module):
@@ -107,7 +107,7 @@ class UNet(nn.Module):
         if self._output_channels != 1:
             bad.append(f"output_channels={self._output_channels}")
         inner = self._dropblock.dropblock if isinstance(self._dropblock, LinearScheduler) else self._dropblock
-        if not isinstance(inner, (nn.Identity, DropBlock2D)):
+        if not isinstance(inner, (nn.Identity, DropBlock2D, Dropblock2d_ichan)):
             bad.append(f"dropblock class {type(inner).__name__}")
         if bad:
             raise NotImplementedError("the B200 path implements the reference scripts' canonical configuration only; "
@@ -158,9 +158,15 @@ class UNet(nn.Module):
         db = self._dropblock
         if isinstance(db, LinearScheduler):
             db = db.dropblock
-        if isinstance(db, DropBlock2D) and db.training and db.drop_prob != 0.:
+        if isinstance(db, (DropBlock2D, Dropblock2d_ichan)) and db.training and db.drop_prob != 0.:
             return True, float(db.drop_prob), int(db.block_size)
         return False, 0.0, 7
+
+    def _dropblock_mode(self) -> str:
+        db = self._dropblock
+        if isinstance(db, LinearScheduler):
+            db = db.dropblock
+        return "ichan" if isinstance(db, Dropblock2d_ichan) else "dropblock2d"
 
     def _engine_signature(self, device):
         if self.compute_dtype not in ("bf16", "tf32", "fp16"):
@@ -190,12 +196,14 @@ class UNet(nn.Module):
     def _mask_plan(self, eng, n_calls, ipc, ws, drop_prob, block_size) -> MaskPlan:
         """One plan (bitmaps, call table) per shape; drop_prob is re-thresholded in place because the scheduler
         ramps it every training step (reference :410-411)."""
-        key = (n_calls, ipc, ws.h, ws.w, block_size)
+        mode = self._dropblock_mode()
+        key = (n_calls, ipc, ws.h, ws.w, block_size, mode)
         mp = self._mask_plans.get(key)
         if mp is None:
             if len(self._mask_plans) > 4:
                 self._mask_plans.clear()
-            mp = MaskPlan(n_calls, ipc, ws.h, ws.w, self._base_filters, self._model_depth, drop_prob, block_size, eng.device)
+            mp = MaskPlan(n_calls, ipc, ws.h, ws.w, self._base_filters, self._model_depth, drop_prob, block_size, eng.device,
+                          mode=mode)
             self._mask_plans[key] = mp
         mp.set_drop_prob(drop_prob)
         return mp
