@@ -270,6 +270,20 @@ int b2u_pack_convT2x2_dgrad_weight(const float* w, void* packed, int cin, int co
 int b2u_rotate_bilinear(const float* x, float* out, int n, int c, int h, int w, const double* angles_deg,
                         int x_batch_stride_is_zero, void* stream);
 
+/* ------------------------------------------------------------------ fused square_pad + TF.resize
+ * (utils_general.py:32-43 + torchvision TF.resize on tensors = bilinear, align_corners=False, antialias=True; used by
+ * the multi-fidelity steps MF-training-UNI.py:54-73 and DropBlockEval(resize=...) Dropblock_Uncertainty.py:52-61).
+ * x: [planes][h][w] fp32 -> out: [planes][oh][ow]; square_pad != 0 first zero-pads (virtually) to max(h,w) with the
+ * reference's split (top = d/2, left = d - d/2).  ATen's anti-aliased triangle filter, fp32. */
+int b2u_square_pad_resize(const float* x, float* out, int planes, int h, int w, int square_pad, int oh, int ow,
+                          void* stream);
+
+/* ------------------------------------------------------------------ evaluation metrics (utils_metrics.py:157-173)
+ * TP, FP, FN, TN of round(seg) against (long)gt over the pixels with (long)mask != 0 (the FOV), in one pass on the
+ * device: F1 (Dice) = 2TP / (2TP + FP + FN), accuracy = (TP + TN) / N.  counts4: 4 x uint64 (zeroed by the call). */
+int b2u_confusion_counts(const float* seg, const float* gt, const float* mask, long long n,
+                         unsigned long long* counts4, void* stream);
+
 /* ------------------------------------------------------------------ fused optimiser step
  * torch.optim.SGD(lr, momentum) (base_model_tests/training.py:32) + Lightning's gradient_clip_val (global L2 norm,
  * torch.nn.utils.clip_grad_norm_ semantics: clip = min(1, max_norm / (norm + 1e-6)); grads are scaled in place).

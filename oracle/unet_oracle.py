@@ -90,6 +90,25 @@ def dropblock2d_ichan(x: Tensor, drop_prob: float, block_size: int, training: bo
     return out
 
 
+def square_pad(tensor: Tensor) -> Tensor:
+    """R/utils/utils_general.py:32-43, restated with F.pad: rows (top = d//2, bottom = d - d//2); columns get
+    LEFT = d - d//2 and right = d//2 (TF.pad's padding tuple is (left, top, right, bottom) and the reference passes its
+    variable named `left` = total - total//2 first)."""
+    size = max(tensor.shape[-2], tensor.shape[-1])
+    tp = size - tensor.shape[-2]
+    top, bot = tp // 2, tp - tp // 2
+    tw = size - tensor.shape[-1]
+    right = tw // 2
+    left = tw - right
+    return F.pad(tensor, (left, right, top, bot))
+
+
+def square_pad_resize(tensor: Tensor, size: int) -> Tensor:
+    """`TF.resize(square_pad(x), size=(s, s))` as called at Dropblock_Uncertainty.py:52-61 / MF-training-UNI.py:54-66:
+    torchvision on tensors = F.interpolate(bilinear, align_corners=False, antialias=True) (torchvision 0.26)."""
+    return F.interpolate(square_pad(tensor), size=(size, size), mode="bilinear", align_corners=False, antialias=True)
+
+
 def linear_scheduler_values(start_value: float, stop_value: float, nr_steps: int) -> np.ndarray:
     """`dropblock==0.3.0` `LinearScheduler.__init__`: `np.linspace(start, stop, int(nr_steps))`;
     `step()` assigns `drop_values[i]` to `dropblock.drop_prob` while `i < len` and increments i.

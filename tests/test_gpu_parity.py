@@ -250,6 +250,86 @@ def test_dropblock2d_ichan():
     assert D.sec_ichan()["ok"]
 
 
+def test_accuracy_metrics_match_sklearn():
+    """on-device F1 / AUROC / accuracy == the reference recipe (masked numpy round + scikit-learn,
+    utils_metrics.py:157-173), including tied scores and exact 0.5 values; plus the Dice parity the north star names:
+    Dice of OUR MC mean vs Dice of the ORACLE's MC mean against the same ground truth."""
+    from sklearn import metrics as skm
+    import unet_research_b200 as U
+    from oracle import unet_oracle as O
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(11)
+    h, w = 120, 116
+    seg = torch.rand(1, 1, h, w, generator=g)
+    seg[0, 0, :10] = 0.5                                            # exact halves round to even (0)
+    seg[0, 0, 10:30] = (seg[0, 0, 10:30] * 8).round() / 8           # heavy ties
+    gt = (torch.rand(1, 1, h, w, generator=g) < 0.3).float()
+    fov = synthetic.make_fov_mask(h, w)
+
+    def ref_metrics(segmentation, gt_, mask):
+        # the reference builds np.ma arrays with mask = FOV and keeps `arr[arr.mask]`, i.e. the in-FOV elements
+        # (plain boolean indexing here: scikit-learn >= 1.6 rejects the all-masked MaskedArray it would receive)
+        sel = mask.long().numpy().astype(bool)
+        sc = segmentation.numpy()[sel]
+        rs = np.round(sc)
+        lg = gt_.long().numpy()[sel]
+        return (skm.f1_score(y_true=lg, y_pred=rs), skm.roc_auc_score(y_true=lg, y_score=sc),
+                skm.accuracy_score(y_true=lg, y_pred=rs))
+
+    f1, au, acc = U.get_accuracy_metrics(seg.to(dev), gt.to(dev), fov.to(dev))
+    rf1, rau, racc = ref_metrics(seg, gt, fov)
+    assert abs(f1 - rf1) < 1e-12 and abs(acc - racc) < 1e-12 and abs(au - rau) < 1e-9, (f1, rf1, au, rau, acc, racc)
+    # Dice of the MC-DropBlock mean: ours vs the oracle's, same Philox stream
+    x = synthetic.make_image(h, w, seed=1234).to(dev)
+    gts = synthetic.make_gt(h, w).to(dev)
+    m, sd = D._build_model(dev, dropblock=True)
+    ev = U.DropBlockEval(m, num_iterations=8, return_num=2, iter_batch=4)
+    torch.manual_seed(1234)
+    _, (mean, _, _) = ev.predict_step((x, None, fov.to(dev)), 0)
+    torch.manual_seed(1234)
+    rmean, _, _ = O.mc_dropblock(sd, x, fov.to(dev), 8, 2, 0.15, 7)
+    # random weights: threshold at the median so both classes are predicted
+    thr = rmean[fov.to(dev) != 0].median()
+    d_ours = U.get_accuracy_metrics((mean > thr).float(), gts, fov.to(dev))
+    d_ref = ref_metrics((rmean > thr).float().cpu(), gts.cpu(), fov)
+    assert abs(d_ours[0] - d_ref[0]) < 5e-3 and abs(d_ours[2] - d_ref[2]) < 5e-3, (d_ours, d_ref)
+    a_ours = U.get_accuracy_metrics(mean, gts, fov.to(dev))[1]
+    a_ref = ref_metrics(rmean.cpu(), gts.cpu(), fov)[1]
+    assert abs(a_ours - a_ref) < 5e-3, (a_ours, a_ref)
+
+
+def test_square_pad_resize_matches_torchvision():
+    """fused square_pad + antialiased bilinear TF.resize vs the oracle restatement (torch
+    F.interpolate antialias=True on the zero-padded square), down- and up-scaling, and DropBlockEval(resize=...)."""
+    import unet_research_b200 as U
+    from oracle import unet_oracle as O
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    for (h, w, s) in [(584, 565, 128), (584, 565, 256), (584, 565, 584), (120, 116, 64), (37, 50, 111), (64, 64, 584)]:
+        x = synthetic.make_image(h, w, seed=h + s, batch=2).to(dev)
+        got = U.square_pad_resize(x, s)
+        ref = O.square_pad_resize(x, s)
+        assert got.shape == ref.shape
+        assert float((got - ref).abs().max()) < 5e-6, (h, w, s, float((got - ref).abs().max()))   # fp32 sums of <= 100 taps, order differs from ATen
+    # plain resize (no pad), non-square target
+    x = synthetic.make_image(100, 80, seed=5).to(dev)
+    ref = torch.nn.functional.interpolate(x, size=(33, 77), mode="bilinear", align_corners=False, antialias=True)
+    assert float((U.square_pad_resize(x, (33, 77), square_pad=False) - ref).abs().max()) < 5e-6
+    # the -resize Monte-Carlo run (Dropblock_Uncertainty.py:52-61)
+    h, w = 200, 180
+    im = synthetic.make_image(h, w, seed=1234).to(dev)
+    fov = synthetic.make_fov_mask(h, w).to(dev)
+    m, sd = D._build_model(dev, dropblock=True)
+    ev = U.DropBlockEval(m, num_iterations=4, return_num=2, resize=128, iter_batch=2)
+    torch.manual_seed(7)
+    _, (mean, std, tens) = ev.predict_step((im, None, fov), 0)
+    torch.manual_seed(7)
+    rmean, rstd, rtens = O.mc_dropblock(sd, O.square_pad_resize(im, 128), O.square_pad_resize(fov, 128), 4, 2, 0.15, 7)
+    assert mean.shape == (1, 1, 128, 128)
+    assert D.rel(tens, rtens)[0] < 1e-2 and D.rel(mean, rmean)[0] < 5e-3
+
+
 def test_fused_sgd_matches_torch():
     """FusedSGD (clip + momentum SGD in two launches) against torch.nn.utils.clip_grad_norm_ + torch.optim.SGD
     (reference training.py:32 + Lightning gradient_clip_val) over several steps, ragged tensor sizes included."""

@@ -196,3 +196,19 @@ def test_unet_forward_ichan_matches_reference(golden_dir, sd):
     with torch.no_grad():
         y = O.unet_forward(sd, x, dropblock=O.DropBlockCfg(0.15, 7, True, mode="ichan", bernoulli_fn=replay))
     np.testing.assert_allclose(y.numpy(), g["output"], rtol=0, atol=5e-6)
+
+
+def test_square_pad_resize_restatement_matches_torchvision():
+    """The oracle's square_pad / resize restatement against the functions the reference actually calls
+    (utils_general.square_pad via the reference import when present, torchvision TF.resize)."""
+    import torchvision.transforms.functional as TF
+    from oracle import ref_shims
+    x = synthetic.make_image(584, 565, seed=3)
+    if ref_shims.reference_available():
+        ref_shims.load_reference()
+        from utils import utils_general  # type: ignore
+        assert torch.equal(O.square_pad(x), utils_general.square_pad(x))
+    sp = O.square_pad(x)
+    assert sp.shape[-2:] == (584, 584) and float(sp[..., :, :10].abs().max()) == 0.0 and float(sp[..., :, -9:].abs().max()) == 0.0
+    for s in (128, 256, 584):
+        np.testing.assert_allclose(O.square_pad_resize(x, s).numpy(), TF.resize(sp, size=(s, s)).numpy(), rtol=0, atol=1e-6)

@@ -13,6 +13,8 @@ from .unet import UNet
 from .uncertainty import DropBlockEval, RotationEval, set_dropblock_on, shard_range
 from .training import BaseUNetTraining
 from .optim import FusedSGD
+from .metrics import get_accuracy_metrics
+from .resize import square_pad_resize
 
 __all__ = ["UNet", "DropBlock2D", "Dropblock2d_ichan", "LinearScheduler", "DropBlockEval", "RotationEval", "set_dropblock_on",
-           "shard_range", "BaseUNetTraining", "FusedSGD"]
+           "shard_range", "BaseUNetTraining", "FusedSGD", "get_accuracy_metrics", "square_pad_resize"]

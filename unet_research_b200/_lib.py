@@ -100,6 +100,8 @@ SIGNATURES = {
     "b2u_dropblock_dilate": (_I, [_P, _I, C.POINTER(DropblockCall), _P, _P, _P, _P]),
     "b2u_dropblock_centers_from_uniform": (_I, [_P, _P, _LL, _F, _P]),
     "b2u_rotate_bilinear": (_I, [_P, _P, _I, _I, _I, _I, C.POINTER(_D), _I, _P]),
+    "b2u_square_pad_resize": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "b2u_confusion_counts": (_I, [_P, _P, _P, _LL, _P, _P]),
     "b2u_sgd_step": (_I, [_P, _P, _I, _P, _F, _F, _F, _I, _P, _P]),
     "b2u_sgd_chunk_elems": (_LL, []),
 }
@@ -112,7 +114,7 @@ _LAUNCHERS = {"b2u_conv3x3_fwd": 1, "b2u_convT2x2_fwd": 1, "b2u_conv_first_fwd":
               "b2u_dropblock_dilate": 1, "b2u_dropblock_centers_ichan": 1, "b2u_dropblock_centers_from_uniform": 1, "b2u_rotate_bilinear": 1,
               "b2u_pack_conv3x3_weight": 1, "b2u_pack_conv3x3_weight_pair": 1, "b2u_pack_convT2x2_weight": 1, "b2u_unit_bwd_stats": 1, "b2u_unit_bwd_finalize": 2,
               "b2u_unit_bwd_apply": 1, "b2u_wgrad": 2, "b2u_wgrad_first": 2, "b2u_gemm1x1_fwd": 1,
-              "b2u_pack_convT2x2_dgrad_weight": 1, "b2u_sgd_step": 2}
+              "b2u_pack_convT2x2_dgrad_weight": 1, "b2u_sgd_step": 2, "b2u_confusion_counts": 1, "b2u_square_pad_resize": 1}
 
 
 def load() -> C.CDLL:

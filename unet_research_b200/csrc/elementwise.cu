@@ -497,6 +497,34 @@ __global__ void mc_accumulate_kernel(const float* __restrict__ x, const float* _
 
 __global__ void advance_counter_kernel(long long* c, long long delta) { *c += delta; }
 
+// Confusion counts of a probability map against a binary ground truth inside the field-of-view mask
+// (utils_metrics.py:157-173: masked round() -> sklearn f1 / accuracy): counts[0..3] = TP, FP, FN, TN.
+// pred = rint(seg) == 1 (numpy rounds half to even: 0.5 -> 0), truth = (long)gt == 1, pixel used iff (long)mask != 0.
+__global__ void __launch_bounds__(256) confusion_kernel(const float* __restrict__ seg, const float* __restrict__ gt, const float* __restrict__ mask,
+                                                        long long n, unsigned long long* __restrict__ counts) {
+  unsigned int c[4] = {0u, 0u, 0u, 0u};
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    if (static_cast<long long>(mask[i]) != 0) {
+      const bool p = rintf(seg[i]) == 1.f;
+      const bool t = static_cast<long long>(gt[i]) == 1;
+      c[p ? (t ? 0 : 1) : (t ? 2 : 3)]++;
+    }
+  }
+  __shared__ unsigned int sh[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    unsigned int v = c[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    unsigned long long tot = 0;
+    for (int w = 0; w < 8; ++w) tot += sh[threadIdx.x][w];
+    if (tot) atomicAdd(counts + threadIdx.x, tot);      // integer atomics: order-independent, deterministic
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // torchvision TF.rotate(BILINEAR, fill=0) restated in one gather kernel (see include/b2u.h).
 struct RotParams {
@@ -771,6 +799,16 @@ extern "C" int b2u_mc_accumulate(const float* x, const float* fov, double* acc, 
   B2U_REQUIRE(x && acc && n > 0 && npix > 0, "bad arguments");
   mc_accumulate_kernel<<<grid_for(npix, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, fov, acc, samples, iter_base, n,
                                                                                               npix, return_num);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_confusion_counts(const float* seg, const float* gt, const float* mask, long long n,
+                                    unsigned long long* counts4, void* stream) {
+  B2U_REQUIRE(seg && gt && mask && counts4 && n > 0, "bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  B2U_CHECK_CUDA(cudaMemsetAsync(counts4, 0, 4 * sizeof(unsigned long long), st));
+  confusion_kernel<<<grid_for(n, 256), 256, 0, st>>>(seg, gt, mask, n, counts4);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

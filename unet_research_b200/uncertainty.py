@@ -278,7 +278,11 @@ class DropBlockEval(_MCBase):
         im, gt, mask = batch
         self._model.apply(set_dropblock_on)            # Dropblock_Uncertainty.py:50
         if self.resize != -1:
-            raise NotImplementedError("on-the-fly resize (Dropblock_Uncertainty.py:52-61) is a 'next' row (SURVEY 8f)")
+            # Dropblock_Uncertainty.py:52-61: pad to square, resize im / gt / mask on the fly (one fused kernel each)
+            from .resize import square_pad_resize
+            im = square_pad_resize(im, self.resize)
+            gt = square_pad_resize(gt, self.resize) if gt is not None else None
+            mask = square_pad_resize(mask, self.resize)
         mean, std, tensors = self.mc_statistics(im, mask)
         if self.mode == 'save':
             return batch_idx, (mean, std, tensors)
