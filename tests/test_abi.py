@@ -155,3 +155,31 @@ def test_shard_range_partitions():
         sizes = [b - a for a, b in spans]
         assert max(sizes) - min(sizes) <= 1
     assert [U.shard_range(359, r, 8)[1] - U.shard_range(359, r, 8)[0] for r in range(8)].count(45) == 7
+
+
+def test_io_formats_roundtrip(tmp_path):
+    """mean.pt / std.pt / tensors.pt layout (Dropblock_Uncertainty.py:157-165) and `_model.`-prefixed checkpoints."""
+    import torch
+    from torch import nn
+    import unet_research_b200 as U
+    from unet_research_b200 import io as bio
+    mean, std, tens = torch.rand(1, 1, 8, 9), torch.rand(1, 1, 8, 9), torch.rand(3, 1, 1, 8, 9)
+    d = bio.save_mc_outputs(str(tmp_path), 7, mean, std, tens)
+    assert d.endswith("tensors/image_7") and sorted(os.listdir(d)) == ["mean.pt", "std.pt", "tensors.pt"]
+    back = bio.load_mc_outputs(d)
+    assert torch.equal(back["mean"], mean) and torch.equal(back["tensors"], tens) and back["std"].dtype == torch.float32
+    m = U.UNet(init_channels=1, filters=64, output_channels=1, model_depth=4)
+    m.set_activation_function(nn.ReLU())
+    m.set_normalization(nn.GroupNorm, params={"num_groups": 32, "num_channels": "fill"})
+    m.create_model()
+    tm = U.BaseUNetTraining(m, nn.BCELoss(), None)
+    p = str(tmp_path / "last.ckpt")
+    bio.save_checkpoint(p, tm, epoch=3)
+    ck = torch.load(p)
+    assert len(ck["state_dict"]) == 75 and all(k.startswith("_model.") for k in ck["state_dict"]) and ck["epoch"] == 3
+    m2 = U.UNet(init_channels=1, filters=64, output_channels=1, model_depth=4)
+    m2.set_activation_function(nn.ReLU())
+    m2.set_normalization(nn.GroupNorm, params={"num_groups": 32, "num_channels": "fill"})
+    m2.create_model()
+    bio.load_checkpoint_into(m2, p)
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
