@@ -466,7 +466,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--iter-batch", type=int, default=5)
+    ap.add_argument("--iter-batch", type=int, default=10)
     ap.add_argument("--e2e-iters", type=int, default=100)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

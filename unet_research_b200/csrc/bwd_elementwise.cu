@@ -64,69 +64,100 @@ __device__ __forceinline__ void load8f(const T* p, float (&f)[8]) {
   v.to_float(f);
 }
 
-// upstream gradient g[8] and dZ[8], xhat[8] for one (pixel, channel vector)
+// Everything one (pixel, channel vector) needs from global memory, loaded in ONE phase: the three gradient
+// sources and the masks are independent loads, and issuing them back to back (before the first use) is what keeps a
+// latency-bound pass like this one near the HBM roofline -- the first version interleaved load and use and spent
+// 60 % of its cycles in three serialised long-scoreboard waits (profiles/r01_bwd_stats_source.md).
 template <typename T>
-__device__ __forceinline__ void unit_grad8(const UnitBwdParams& p, const UnitBwdPtrs& q, int n, int hh, int ww, int cv,
-                                           const float (&a)[8], const float (&b)[8], float mean, float rstd, float s1, float s2,
-                                           float (&dz)[8], float (&xhat)[8], float (&act)[8], float& dlogit) {
+struct UnitRaw {
+  Vec8<T> y, ga, gp;
+  uint2 am;
+  uint32_t m1, m2;
+  float o, go;
+  bool inside;
+};
+
+template <typename T>
+__device__ __forceinline__ void unit_load(const UnitBwdParams& p, const UnitBwdPtrs& q, int n, int hh, int ww, int cv, UnitRaw<T>& r) {
   const long pix = (static_cast<long>(n) * p.h + hh) * p.w + ww;
+  r.y.load(reinterpret_cast<const T*>(q.y) + pix * p.c + cv * 8);
+  r.m1 = q.mask1 ? q.mask1[pix * (p.c >> 3) + cv] : 0xFFu;
+  r.m2 = 0xFFu;
+  if (q.ga) {
+    r.ga.load(reinterpret_cast<const T*>(q.ga) + pix * p.a_cstride + p.a_coffset + cv * 8);
+    if (q.mask2) r.m2 = q.mask2[pix * (p.mask2_cstride >> 3) + (p.mask2_coffset >> 3) + cv];
+  }
+  if (q.gp) {
+    const long pp = (static_cast<long>(n) * (p.h >> 1) + (hh >> 1)) * (p.w >> 1) + (ww >> 1);
+    r.gp.load(reinterpret_cast<const T*>(q.gp) + pp * p.c + cv * 8);
+    r.am = *reinterpret_cast<const uint2*>(q.argmax + pp * p.c + cv * 8);
+  }
+  r.inside = false;
+  r.o = r.go = 0.f;
+  if (q.grad_out && hh < p.h0 && ww < p.w0) {
+    const long op = (static_cast<long>(n) * p.h0 + hh) * p.w0 + ww;
+    r.o = q.out[op];
+    r.go = q.grad_out[op];
+    r.inside = true;
+  }
+}
+
+// upstream gradient g[8] -> dZ[8], raw y[8] (returned in xhat) and the activation for one (pixel, channel vector)
+template <typename T>
+__device__ __forceinline__ void unit_grad8(const UnitBwdParams& p, const UnitBwdPtrs& q, const UnitRaw<T>& r, int hh, int ww, int cv,
+                                           const float (&a)[8], const float (&b)[8], float s1, float s2,
+                                           float (&dz)[8], float (&xhat)[8], float (&act)[8], float& dlogit) {
   float yv[8];
-  load8f(reinterpret_cast<const T*>(q.y) + pix * p.c + cv * 8, yv);
+  r.y.to_float(yv);
   float g[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) g[i] = 0.f;
   if (q.ga) {
     float t[8];
-    load8f(reinterpret_cast<const T*>(q.ga) + pix * p.a_cstride + p.a_coffset + cv * 8, t);
+    r.ga.to_float(t);
     if (q.mask2) {
-      const uint32_t m2 = q.mask2[pix * (p.mask2_cstride >> 3) + (p.mask2_coffset >> 3) + cv];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) t[i] = ((m2 >> i) & 1u) ? t[i] * s2 : 0.f;
+      for (int i = 0; i < 8; ++i) t[i] = ((r.m2 >> i) & 1u) ? t[i] * s2 : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] += t[i];
   }
   if (q.gp) {
-    const long pp = (static_cast<long>(n) * (p.h >> 1) + (hh >> 1)) * (p.w >> 1) + (ww >> 1);
     float t[8];
-    load8f(reinterpret_cast<const T*>(q.gp) + pp * p.c + cv * 8, t);
-    const uint2 am = *reinterpret_cast<const uint2*>(q.argmax + pp * p.c + cv * 8);
+    r.gp.to_float(t);
     const uint32_t code = ((hh & 1) << 1) | (ww & 1);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const uint32_t a8 = ((i < 4 ? am.x : am.y) >> (8 * (i & 3))) & 0xFFu;
+      const uint32_t a8 = ((i < 4 ? r.am.x : r.am.y) >> (8 * (i & 3))) & 0xFFu;
       if (a8 == code) g[i] += t[i];
     }
   }
   dlogit = 0.f;
   if (q.grad_out) {
-    if (hh < p.h0 && ww < p.w0) {
-      const long op = (static_cast<long>(n) * p.h0 + hh) * p.w0 + ww;
-      const float o = q.out[op];
-      dlogit = q.grad_out[op] * o * (1.f - o);
-    }
+    if (r.inside) dlogit = r.go * r.o * (1.f - r.o);
     const float4 wa = __ldg(reinterpret_cast<const float4*>(q.w_head + cv * 8));
     const float4 wb = __ldg(reinterpret_cast<const float4*>(q.w_head + cv * 8 + 4));
     g[0] += dlogit * wa.x; g[1] += dlogit * wa.y; g[2] += dlogit * wa.z; g[3] += dlogit * wa.w;
     g[4] += dlogit * wb.x; g[5] += dlogit * wb.y; g[6] += dlogit * wb.z; g[7] += dlogit * wb.w;
   }
-  const uint32_t m1 = q.mask1 ? q.mask1[pix * (p.c >> 3) + cv] : 0xFFu;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float z = fmaf(yv[i], a[i], b[i]);                    // s1 * (gamma * xhat + beta): same sign as the pre-activation
-    const bool keep = (m1 >> i) & 1u;
+    const bool keep = (r.m1 >> i) & 1u;
     const bool pass = keep && (!p.relu || z > 0.f);
     act[i] = keep ? (p.relu ? fmaxf(z, 0.f) : z) : 0.f;
     dz[i] = pass ? g[i] * s1 : 0.f;
-    xhat[i] = (yv[i] - mean) * rstd;
+    xhat[i] = yv[i];
   }
 }
+
+constexpr int kBwdUnroll = 2;       // pixels per thread per trip (all loads of both issued before the first use)
 
 // grid = (rows, n); thread owns channel vector t % cvs; deterministic block reduction to partials[n][row][c][3]
 // GPV = GroupNorm groups per 8-channel vector (1 when the group size is >= 8, else 8 / group size): the per-group
 // (mean, rstd[, c1, c2]) live in GPV registers each instead of 8.
 template <typename T, int GPV>
-__global__ void __launch_bounds__(256, 3) unit_bwd_stats_kernel(UnitBwdParams p, UnitBwdPtrs q) {
+__global__ void __launch_bounds__(256, 2) unit_bwd_stats_kernel(UnitBwdParams p, UnitBwdPtrs q) {
   extern __shared__ float sm[];
   const int n = blockIdx.y;
   const int cvs = p.c >> 3;
@@ -158,17 +189,30 @@ __global__ void __launch_bounds__(256, 3) unit_bwd_stats_kernel(UnitBwdParams p,
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc1[i] = acc2[i] = acc3[i] = 0.f;
   const int npix = p.h * p.w;
-  for (int pix = blockIdx.x * slots + slot; pix < npix; pix += gridDim.x * slots) {
-    const int hh = pix / p.w, ww = pix - hh * p.w;
-    float dz[8], xhat[8], act[8], dlogit;
-    // per-channel mean/rstd: pass channel 0's and fix up below (gsize < 8 only happens for C = 64, 128)
-    unit_grad8<T>(p, q, n, hh, ww, cv, a, b, 0.f, 1.f, s1, s2, dz, xhat, act, dlogit);
+  const int stride = gridDim.x * slots * kBwdUnroll;
+  for (int base = blockIdx.x * slots * kBwdUnroll + slot; base < npix; base += stride) {
+    UnitRaw<T> raw[kBwdUnroll];
+    int hh[kBwdUnroll], ww[kBwdUnroll];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float xh = (xhat[i] - mean8[i / CPG]) * rstd8[i / CPG];   // xhat[] holds raw y here (mean 0, rstd 1 above)
-      acc1[i] += dz[i];
-      acc2[i] += dz[i] * xh;
-      acc3[i] += dlogit * act[i];
+    for (int u = 0; u < kBwdUnroll; ++u) {
+      const int pix = base + u * slots;
+      hh[u] = pix / p.w;
+      ww[u] = pix - hh[u] * p.w;
+      if (pix < npix) unit_load<T>(p, q, n, hh[u], ww[u], cv, raw[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kBwdUnroll; ++u) {
+      if (base + u * slots < npix) {
+        float dz[8], xhat[8], act[8], dlogit;
+        unit_grad8<T>(p, q, raw[u], hh[u], ww[u], cv, a, b, s1, s2, dz, xhat, act, dlogit);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (xhat[i] - mean8[i / CPG]) * rstd8[i / CPG];   // xhat[] holds the raw conv output
+          acc1[i] += dz[i];
+          acc2[i] += dz[i] * xh;
+          acc3[i] += dlogit * act[i];
+        }
+      }
     }
   }
   // block reduction: [thread][24] -> [c][3]
@@ -263,7 +307,7 @@ __global__ void __launch_bounds__(kBwdFinWarps * 32) bwd_finalize_kernel(const f
 }
 
 template <typename T, int GPV>
-__global__ void __launch_bounds__(256, 3) unit_bwd_apply_kernel(UnitBwdParams p, UnitBwdPtrs q) {
+__global__ void __launch_bounds__(256, 2) unit_bwd_apply_kernel(UnitBwdParams p, UnitBwdPtrs q) {
   const int n = blockIdx.y;
   const int cvs = p.c >> 3;
   const int cv = threadIdx.x % cvs;
@@ -295,26 +339,40 @@ __global__ void __launch_bounds__(256, 3) unit_bwd_apply_kernel(UnitBwdParams p,
   }
   const int npix = p.h * p.w;
   T* dy = reinterpret_cast<T*>(q.dy);
-  for (int pix = blockIdx.x * slots + slot; pix < npix; pix += gridDim.x * slots) {
-    const int hh = pix / p.w, ww = pix - hh * p.w;
-    float dz[8], xhat[8], act[8], dlogit;
-    unit_grad8<T>(p, q, n, hh, ww, cv, a, b, 0.f, 1.f, s1, s2, dz, xhat, act, dlogit);
-    float o[8];
+  const int stride = gridDim.x * slots * kBwdUnroll;
+  for (int base = blockIdx.x * slots * kBwdUnroll + slot; base < npix; base += stride) {
+    UnitRaw<T> raw[kBwdUnroll];
+    int hh[kBwdUnroll], ww[kBwdUnroll];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float xh = (xhat[i] - mean8[i / CPG]) * rstd8[i / CPG];
-      o[i] = rstd8[i / CPG] * (gm[i] * dz[i] - c1[i / CPG] - xh * c2[i / CPG]);
+    for (int u = 0; u < kBwdUnroll; ++u) {
+      const int pix = base + u * slots;
+      hh[u] = pix / p.w;
+      ww[u] = pix - hh[u] * p.w;
+      if (pix < npix) unit_load<T>(p, q, n, hh[u], ww[u], cv, raw[u]);
     }
-    long dst;
-    if (p.s2d) {
-      const long pp = (static_cast<long>(n) * (p.h >> 1) + (hh >> 1)) * (p.w >> 1) + (ww >> 1);
-      dst = (pp * 4 + (((hh & 1) << 1) | (ww & 1))) * p.c + cv * 8;
-    } else {
-      dst = ((static_cast<long>(n) * p.h + hh) * p.w + ww) * p.c + cv * 8;
+#pragma unroll
+    for (int u = 0; u < kBwdUnroll; ++u) {
+      if (base + u * slots < npix) {
+        float dz[8], xhat[8], act[8], dlogit;
+        unit_grad8<T>(p, q, raw[u], hh[u], ww[u], cv, a, b, s1, s2, dz, xhat, act, dlogit);
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (xhat[i] - mean8[i / CPG]) * rstd8[i / CPG];
+          o[i] = rstd8[i / CPG] * (gm[i] * dz[i] - c1[i / CPG] - xh * c2[i / CPG]);
+        }
+        long dst;
+        if (p.s2d) {
+          const long pp = (static_cast<long>(n) * (p.h >> 1) + (hh[u] >> 1)) * (p.w >> 1) + (ww[u] >> 1);
+          dst = (pp * 4 + (((hh[u] & 1) << 1) | (ww[u] & 1))) * p.c + cv * 8;
+        } else {
+          dst = ((static_cast<long>(n) * p.h + hh[u]) * p.w + ww[u]) * p.c + cv * 8;
+        }
+        Vec8<T> v;
+        v.from_float(o);
+        v.store(dy + dst);
+      }
     }
-    Vec8<T> v;
-    v.from_float(o);
-    v.store(dy + dst);
   }
 }
 
@@ -323,8 +381,8 @@ static int bwd_pick_threads(int cvs) { return cvs > 256 ? 0 : (256 / cvs) * cvs;
 static int bwd_rows(int h, int w, int c) {
   const int threads = bwd_pick_threads(c / 8);
   const int slots = threads / (c / 8);
-  long b = (static_cast<long>(h) * w + slots - 1) / slots;
-  long cap = static_cast<long>(b2u_num_sms()) * 4;
+  long b = (static_cast<long>(h) * w + slots * kBwdUnroll - 1) / (slots * kBwdUnroll);
+  long cap = static_cast<long>(b2u_num_sms()) * 2;            // exactly one wave at 2 resident blocks per SM
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return static_cast<int>(b);
@@ -420,8 +478,8 @@ extern "C" int b2u_unit_bwd_apply(const b2u_unit_bwd_desc* d, const float* group
   q.dy = dy;
   const int threads = bwd_pick_threads(d->c / 8);
   const int slots = threads / (d->c / 8);
-  long bpi = (static_cast<long>(d->h) * d->w + slots - 1) / slots;
-  const long cap = (static_cast<long>(b2u_num_sms()) * 16 + d->n - 1) / d->n;
+  long bpi = (static_cast<long>(d->h) * d->w + slots * kBwdUnroll - 1) / (slots * kBwdUnroll);
+  const long cap = (static_cast<long>(b2u_num_sms()) * 8 + d->n - 1) / d->n;
   if (bpi > cap) bpi = cap;
   dim3 grid(static_cast<unsigned>(bpi), d->n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

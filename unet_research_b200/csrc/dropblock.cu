@@ -18,7 +18,12 @@ namespace b2u {
 // 32x32 -> 64 multiply as ONE IMAD.WIDE.U32 (the C++ uint64 product makes ptxas add a zero high-word
 // correction: 2 wasted adds per round, 20 per call)
 __device__ __forceinline__ void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#ifdef B2U_PHILOX_SPLIT_MUL
+  hi = __umulhi(a, b);
+  lo = a * b;
+#else
   asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+#endif
 }
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,

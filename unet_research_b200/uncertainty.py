@@ -191,7 +191,7 @@ class MCRunner:
 
 
 class DropBlockEval(_MCBase):
-    def __init__(self, model, num_iterations=1000, return_num=25, mode='save', resize=-1, iter_batch: int = 5,
+    def __init__(self, model, num_iterations=1000, return_num=25, mode='save', resize=-1, iter_batch: int = 10,
                  use_cuda_graph: bool = True, overlap_masks: bool = True):
         super().__init__(model)
         self.num_iterations = num_iterations
