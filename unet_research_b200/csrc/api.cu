@@ -2,6 +2,7 @@
 #include "b2u_common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 static thread_local char g_err[1024] = "";
@@ -23,6 +24,15 @@ int b2u_num_sms() {
     cached[dev] = v;
   }
   return cached[dev];
+}
+
+int b2u_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2U_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
 }
 
 extern "C" const char* b2u_last_error(void) { return g_err; }

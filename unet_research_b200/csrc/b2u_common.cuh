@@ -7,6 +7,9 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#ifdef __cplusplus
+#include <utility>
+#endif
 
 #include "../../include/b2u.h"
 
@@ -37,6 +40,27 @@ void b2u_set_error(const char* fmt, ...);
   } while (0)
 
 int b2u_num_sms();
+int b2u_pdl_enabled();      // 1 unless the environment sets B2U_PDL=0
+
+#ifdef __CUDACC__
+// Launch `kernel` with the programmatic-stream-serialization attribute (see pdl_wait / pdl_trigger below).  Every
+// kernel launched through this helper calls pdl_wait() before its first dependent global-memory access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t b2u_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = b2u_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#define B2U_PDL_LAUNCH(kernel, grid, block, smem, st, ...) (void)b2u_launch_pdl((kernel), (grid), (block), (smem), (st), __VA_ARGS__)
+#endif
 
 // ----------------------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
@@ -117,6 +141,15 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, uint64_
       "r"(c3)
       : "memory");
 }
+
+// ---- programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// be scheduled while its predecessor in the stream is still running; `pdl_wait()` (griddepcontrol.wait) blocks until the
+// predecessor grid has completed and its memory is visible, so everything a kernel does BEFORE the wait (barrier
+// init, TMEM allocation, descriptor prefetch, index arithmetic) and its launch latency overlap the predecessor's
+// tail.  `pdl_trigger()` (griddepcontrol.launch_dependents) lets the successor be scheduled once every CTA of this grid
+// has issued it or exited.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {

@@ -158,6 +158,8 @@ constexpr int kBwdUnroll = 2;       // pixels per thread per trip (all loads of 
 // (mean, rstd[, c1, c2]) live in GPV registers each instead of 8.
 template <typename T, int GPV>
 __global__ void __launch_bounds__(256, 2) unit_bwd_stats_kernel(UnitBwdParams p, UnitBwdPtrs q) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   extern __shared__ float sm[];
   const int n = blockIdx.y;
   const int cvs = p.c >> 3;
@@ -244,6 +246,8 @@ __global__ void __launch_bounds__(kBwdFinWarps * 32) bwd_finalize_kernel(const f
                                                                        int num_groups, const float* __restrict__ gamma, double count,
                                                                        float2* __restrict__ gcoef, float* __restrict__ dgamma,
                                                                        float* __restrict__ dbeta, float* __restrict__ dw_head) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   const int g = blockIdx.x;
   const int gsize = c / num_groups;
   const int E = gsize * 3;                                   // floats of this group in one partial row
@@ -308,6 +312,8 @@ __global__ void __launch_bounds__(kBwdFinWarps * 32) bwd_finalize_kernel(const f
 
 template <typename T, int GPV>
 __global__ void __launch_bounds__(256, 2) unit_bwd_apply_kernel(UnitBwdParams p, UnitBwdPtrs q) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   const int n = blockIdx.y;
   const int cvs = p.c >> 3;
   const int cv = threadIdx.x % cvs;
@@ -445,9 +451,9 @@ extern "C" int b2u_unit_bwd_stats(const b2u_unit_bwd_desc* d, float* partials, v
   B2U_REQUIRE(gpv == 1 || gpv == 2 || gpv == 4, "group size %d must be 2, 4 or a multiple of 8", gsize);
 #define B2U_STATS(T)                                                                  \
   do {                                                                                \
-    if (gpv == 1) unit_bwd_stats_kernel<T, 1><<<grid, threads, smem, st>>>(p, q);      \
-    else if (gpv == 2) unit_bwd_stats_kernel<T, 2><<<grid, threads, smem, st>>>(p, q); \
-    else unit_bwd_stats_kernel<T, 4><<<grid, threads, smem, st>>>(p, q);               \
+    if (gpv == 1) B2U_PDL_LAUNCH((unit_bwd_stats_kernel<T, 1>), grid, threads, smem, st, p, q);      \
+    else if (gpv == 2) B2U_PDL_LAUNCH((unit_bwd_stats_kernel<T, 2>), grid, threads, smem, st, p, q); \
+    else B2U_PDL_LAUNCH((unit_bwd_stats_kernel<T, 4>), grid, threads, smem, st, p, q);               \
   } while (0)
   if (d->dtype == B2U_F32) B2U_STATS(float);
   else B2U_STATS(__nv_bfloat16);
@@ -461,8 +467,7 @@ extern "C" int b2u_unit_bwd_finalize(const float* partials, int n, int rows_per_
   B2U_REQUIRE(partials && gamma && group_coef && n > 0 && c > 0 && num_groups > 0 && c % num_groups == 0, "bad arguments");
   B2U_REQUIRE(c / num_groups <= 32, "group size %d > 32 is not supported by the backward finalise", c / num_groups);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  bwd_finalize_kernel<<<num_groups, kBwdFinWarps * 32, 0, st>>>(partials, n, rows_per_image, c, num_groups, gamma, count,
-                                                              reinterpret_cast<float2*>(group_coef), dgamma, dbeta, dw_head);
+  B2U_PDL_LAUNCH((bwd_finalize_kernel), num_groups, kBwdFinWarps * 32, 0, st, partials, n, rows_per_image, c, num_groups, gamma, count, reinterpret_cast<float2*>(group_coef), dgamma, dbeta, dw_head);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -488,9 +493,9 @@ extern "C" int b2u_unit_bwd_apply(const b2u_unit_bwd_desc* d, const float* group
   B2U_REQUIRE(gpv == 1 || gpv == 2 || gpv == 4, "group size %d must be 2, 4 or a multiple of 8", gsize);
 #define B2U_APPLY(T)                                                               \
   do {                                                                             \
-    if (gpv == 1) unit_bwd_apply_kernel<T, 1><<<grid, threads, 0, st>>>(p, q);      \
-    else if (gpv == 2) unit_bwd_apply_kernel<T, 2><<<grid, threads, 0, st>>>(p, q); \
-    else unit_bwd_apply_kernel<T, 4><<<grid, threads, 0, st>>>(p, q);               \
+    if (gpv == 1) B2U_PDL_LAUNCH((unit_bwd_apply_kernel<T, 1>), grid, threads, 0, st, p, q);      \
+    else if (gpv == 2) B2U_PDL_LAUNCH((unit_bwd_apply_kernel<T, 2>), grid, threads, 0, st, p, q); \
+    else B2U_PDL_LAUNCH((unit_bwd_apply_kernel<T, 4>), grid, threads, 0, st, p, q);               \
   } while (0)
   if (d->dtype == B2U_F32) B2U_APPLY(float);
   else B2U_APPLY(__nv_bfloat16);

@@ -110,6 +110,9 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: barrier init, TMEM allocation and descriptor prefetch above overlapped the predecessor's tail; from here on the
+  // kernel touches tensors the predecessor wrote (or still reads)
+  pdl_wait();
 
   // All three single-thread role loops below keep (stage, phase) pairs that advance by compare-and-wrap:
   // no runtime division / modulo on the issue path (a single thread issues every TMA / MMA of the CTA, so
@@ -120,6 +123,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int s = 0;
       uint32_t ph = 1;                                          // first pass over a fresh barrier: wait(1) returns
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        if (item + static_cast<int>(gridDim.x) >= p.num_items) pdl_trigger();   // last item of this CTA: let the successor launch
         const int mg = item % p.num_mgroups;
         int cw[MT], ch[MT], cn[MT];
 #pragma unroll
@@ -313,7 +317,7 @@ static int v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2P
     B2U_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_v2_kernel<BN, MT, TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv3x3_v2_kernel<BN, MT, TF><<<grid, kV2Threads, smem, st>>>(ta, tb, gp);
+  B2U_PDL_LAUNCH((conv3x3_v2_kernel<BN, MT, TF>), grid, kV2Threads, smem, st, ta, tb, gp);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -100,6 +100,9 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: barrier init, TMEM allocation and descriptor prefetch above overlapped the predecessor's tail; from here on the
+  // kernel touches tensors the predecessor wrote (or still reads)
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -107,6 +110,7 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int s = 0;
       uint32_t ph = 1;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        if (item + static_cast<int>(gridDim.x) >= p.num_items) pdl_trigger();   // last item of this CTA: let the successor launch
         const int nt = item / p.total_tiles;
         const int tile = item - nt * p.total_tiles;
         const int img = tile / tiles_per_image;
@@ -245,7 +249,7 @@ static int convT_v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const C
     B2U_CHECK_CUDA(cudaFuncSetAttribute(convT_v2_kernel<TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  convT_v2_kernel<TF><<<grid, kTThreads, smem, st>>>(ta, tb, gp);
+  B2U_PDL_LAUNCH((convT_v2_kernel<TF>), grid, kTThreads, smem, st, ta, tb, gp);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -122,6 +122,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: barrier init, TMEM allocation and descriptor prefetch above overlapped the predecessor's tail; from here on the
+  // kernel touches tensors the predecessor wrote (or still reads)
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -346,7 +350,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
                                         227 * 1024));
     attr_set = true;
   }
-  conv_gemm_kernel<BN, TF><<<grid, kNumThreads, smem, st>>>(ta, tb, gp);
+  B2U_PDL_LAUNCH((conv_gemm_kernel<BN, TF>), grid, kNumThreads, smem, st, ta, tb, gp);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -437,6 +441,8 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, T* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256) pack_conv3x3_pair_kernel(const float* __restrict__ w, T* __restrict__ fwd, T* __restrict__ dgrad,
                                                                 int cout, int cin) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   __shared__ T tile[9][32][33];
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
   for (int f = threadIdx.x; f < 32 * 288; f += 256) {
@@ -455,6 +461,8 @@ __global__ void __launch_bounds__(256) pack_conv3x3_pair_kernel(const float* __r
 
 template <typename T>
 __global__ void pack_convT_kernel(const float* __restrict__ w, T* __restrict__ out, int cin, int cout) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   long total = 4L * cout * cin;     // out[tap][co][ci] = w[ci][co][tap]
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     int ci = static_cast<int>(i % cin);
@@ -522,12 +530,11 @@ extern "C" int b2u_pack_conv3x3_weight_pair(const float* w, void* packed_fwd, vo
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(cin / 32, cout / 32);
   if (dtype == B2U_F32)
-    pack_conv3x3_pair_kernel<float><<<grid, 256, 0, st>>>(w, static_cast<float*>(packed_fwd), static_cast<float*>(packed_dgrad), cout, cin);
+    B2U_PDL_LAUNCH((pack_conv3x3_pair_kernel<float>), grid, 256, 0, st, w, static_cast<float*>(packed_fwd), static_cast<float*>(packed_dgrad), cout, cin);
   else if (dtype == B2U_F16)
-    pack_conv3x3_pair_kernel<__half><<<grid, 256, 0, st>>>(w, static_cast<__half*>(packed_fwd), static_cast<__half*>(packed_dgrad), cout, cin);
+    B2U_PDL_LAUNCH((pack_conv3x3_pair_kernel<__half>), grid, 256, 0, st, w, static_cast<__half*>(packed_fwd), static_cast<__half*>(packed_dgrad), cout, cin);
   else
-    pack_conv3x3_pair_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(packed_fwd),
-                                                                   static_cast<__nv_bfloat16*>(packed_dgrad), cout, cin);
+    B2U_PDL_LAUNCH((pack_conv3x3_pair_kernel<__nv_bfloat16>), grid, 256, 0, st, w, static_cast<__nv_bfloat16*>(packed_fwd), static_cast<__nv_bfloat16*>(packed_dgrad), cout, cin);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -536,9 +543,9 @@ extern "C" int b2u_pack_convT2x2_weight(const float* w, void* packed, int cin, i
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   long total = 4L * cout * cin;
   int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  if (dtype == B2U_F32) pack_convT_kernel<float><<<blocks, 256, 0, st>>>(w, static_cast<float*>(packed), cin, cout);
-  else if (dtype == B2U_F16) pack_convT_kernel<__half><<<blocks, 256, 0, st>>>(w, static_cast<__half*>(packed), cin, cout);
-  else pack_convT_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(packed), cin, cout);
+  if (dtype == B2U_F32) B2U_PDL_LAUNCH((pack_convT_kernel<float>), blocks, 256, 0, st, w, static_cast<float*>(packed), cin, cout);
+  else if (dtype == B2U_F16) B2U_PDL_LAUNCH((pack_convT_kernel<__half>), blocks, 256, 0, st, w, static_cast<__half*>(packed), cin, cout);
+  else B2U_PDL_LAUNCH((pack_convT_kernel<__nv_bfloat16>), blocks, 256, 0, st, w, static_cast<__nv_bfloat16*>(packed), cin, cout);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

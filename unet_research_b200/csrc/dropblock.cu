@@ -50,6 +50,8 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 __global__ void __launch_bounds__(256) dropblock_centers_kernel(const b2u_dropblock_call* __restrict__ table, uint64_t seed,
                                          const unsigned long long* __restrict__ offset_base,
                                          uint32_t* __restrict__ center_bits) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   const b2u_dropblock_call c = table[blockIdx.y];
   if (blockIdx.x >= c.grid) return;
   const uint32_t tn = c.grid * 256u;
@@ -161,6 +163,8 @@ template <int RING, int BS_CT>
 __global__ void __launch_bounds__(128) dropblock_dilate_kernel(const b2u_dropblock_call* __restrict__ table,
                                         const uint32_t* __restrict__ center_bits, uint32_t* __restrict__ mask_bits,
                                         unsigned long long* __restrict__ keep_counts, int band_rows) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   const b2u_dropblock_call c = table[blockIdx.z];
   const int cgs = c.c >> 5;
   const int wwords = (c.w + 31) >> 5;
@@ -258,7 +262,7 @@ extern "C" int b2u_dropblock_centers(const b2u_dropblock_call* table, int n_call
   if (rc) return rc;
   // torch's grid.x never exceeds SMs * (maxThreadsPerSM / 256); calls with a smaller grid exit early
   dim3 grid(sms * (mt / 256), n_calls);
-  dropblock_centers_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, seed, offset_base, center_bits);
+  B2U_PDL_LAUNCH((dropblock_centers_kernel), grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), table, seed, offset_base, center_bits);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -305,11 +309,11 @@ extern "C" int b2u_dropblock_dilate(const b2u_dropblock_call* table, int n_calls
   for (int i = 0; i < n_calls; ++i) all7 = all7 && host_table[i].block_size == 7;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (all7)
-    dropblock_dilate_kernel<7, 7><<<grid, 128, 0, st>>>(table, center_bits, mask_bits, keep_counts, band_rows);
+    B2U_PDL_LAUNCH((dropblock_dilate_kernel<7, 7>), grid, 128, 0, st, table, center_bits, mask_bits, keep_counts, band_rows);
   else if (max_bs <= 7)
-    dropblock_dilate_kernel<7, 0><<<grid, 128, 0, st>>>(table, center_bits, mask_bits, keep_counts, band_rows);
+    B2U_PDL_LAUNCH((dropblock_dilate_kernel<7, 0>), grid, 128, 0, st, table, center_bits, mask_bits, keep_counts, band_rows);
   else
-    dropblock_dilate_kernel<31, 0><<<grid, 128, 0, st>>>(table, center_bits, mask_bits, keep_counts, band_rows);
+    B2U_PDL_LAUNCH((dropblock_dilate_kernel<31, 0>), grid, 128, 0, st, table, center_bits, mask_bits, keep_counts, band_rows);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -54,6 +54,8 @@ constexpr int kFirstStrip = 4;
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ wgt, T* __restrict__ y,
                                   float* __restrict__ partials, int h0, int w0, int h, int w, int cout, int sgs) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   extern __shared__ float sm[];
   float* wsm = sm;                                  // [CIN*9][cout]: tap-major, so a thread's 8 channels are two LDS.128
   float* red = sm + cout * CIN * 9;
@@ -136,6 +138,8 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partials, int rows,
                                    double count, float eps, const unsigned long long* __restrict__ keep,
                                    int images_per_call, double numel_per_call, float2* __restrict__ mean_rstd,
                                    int shared_partials) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   const int g = blockIdx.x, n = blockIdx.y;
   const int gsize = c / num_groups;
   const int nsg_total = c / sgs;
@@ -213,6 +217,8 @@ template <typename T>
 __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const T* __restrict__ x, const float2* __restrict__ coef, const uint8_t* __restrict__ mask1,
                                 const uint8_t* __restrict__ mask2, const unsigned long long* __restrict__ keep2,
                                 T* __restrict__ out, ApplyParams p) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   const int n = blockIdx.y;
   const int cvs = p.c >> 3;
   const int cv = threadIdx.x % cvs;
@@ -269,6 +275,8 @@ __global__ void __launch_bounds__(256, 2) gn_apply_pool_kernel(const T* __restri
                                      const uint8_t* __restrict__ mask2, const unsigned long long* __restrict__ keep2,
                                      T* __restrict__ skip_out, T* __restrict__ pooled, float* __restrict__ pool_partials,
                                      uint8_t* __restrict__ argmax, int pool_sgs, ApplyParams p) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   extern __shared__ float sm[];
   const int n = blockIdx.y;
   const int cvs = p.c >> 3;
@@ -374,6 +382,8 @@ __global__ void __launch_bounds__(256, 3) head_kernel(const T* __restrict__ x, c
                             const float* __restrict__ w_head, float* __restrict__ out, float* __restrict__ logits,
                             const float* __restrict__ fov, double* __restrict__ acc, float* __restrict__ samples,
                             const long long* __restrict__ iter_base, b2u_head_desc d) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   const int lpp = d.c >> 3;
   const int lane_in = threadIdx.x % lpp;
   const long group = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) / lpp;
@@ -495,7 +505,11 @@ __global__ void mc_accumulate_kernel(const float* __restrict__ x, const float* _
   }
 }
 
-__global__ void advance_counter_kernel(long long* c, long long delta) { *c += delta; }
+__global__ void advance_counter_kernel(long long* c, long long delta) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
+  *c += delta;
+}
 
 // Confusion counts of a probability map against a binary ground truth inside the field-of-view mask
 // (utils_metrics.py:157-173: masked round() -> sklearn f1 / accuracy): counts[0..3] = TP, FP, FN, TN.
@@ -640,7 +654,7 @@ extern "C" int b2u_conv_first_fwd(const float* x_nchw, const float* w, void* y, 
 #define B2U_LAUNCH_FIRST(T, CIN)                                                                                  \
   do {                                                                                                            \
     B2U_CHECK_CUDA(cudaFuncSetAttribute(conv_first_kernel<T, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
-    conv_first_kernel<T, CIN><<<grid, threads, smem, st>>>(x_nchw, w, static_cast<T*>(y), parts, h0, w0, h, wd, cout, sgs); \
+    B2U_PDL_LAUNCH((conv_first_kernel<T, CIN>), grid, threads, smem, st, x_nchw, w, static_cast<T*>(y), parts, h0, w0, h, wd, cout, sgs); \
   } while (0)
   if (dtype == B2U_F32) {
     if (cin == 1) B2U_LAUNCH_FIRST(float, 1); else B2U_LAUNCH_FIRST(float, 3);
@@ -672,10 +686,7 @@ extern "C" int b2u_gn_finalize_ex(const float* partials, int rows_per_image, int
               subgroup_size, c / num_groups);
   B2U_REQUIRE(!keep_counts || images_per_call > 0, "images_per_call must be positive");
   dim3 grid(num_groups, n);
-  gn_finalize_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      partials, rows_per_image, subgroup_size, gamma, beta, reinterpret_cast<float2*>(coef), c, num_groups, count, eps,
-      keep_counts, images_per_call > 0 ? images_per_call : 1, numel_per_call, reinterpret_cast<float2*>(mean_rstd),
-      shared_partials);
+  B2U_PDL_LAUNCH((gn_finalize_kernel), grid, 128, 0, reinterpret_cast<cudaStream_t>(stream), partials, rows_per_image, subgroup_size, gamma, beta, reinterpret_cast<float2*>(coef), c, num_groups, count, eps, keep_counts, images_per_call > 0 ? images_per_call : 1, numel_per_call, reinterpret_cast<float2*>(mean_rstd), shared_partials);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -710,10 +721,10 @@ extern "C" int b2u_gn_apply(const void* x, const float* coef, const uint32_t* ma
   if (bpi < 1) bpi = 1;
   dim3 grid(static_cast<unsigned>(bpi), d->n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define B2U_APPLY_T(T)                                                                                                  \
-  gn_apply_kernel<T><<<grid, threads, 0, st>>>(static_cast<const T*>(x), reinterpret_cast<const float2*>(coef),            \
-                                               reinterpret_cast<const uint8_t*>(mask1), reinterpret_cast<const uint8_t*>(mask2), \
-                                               keep_counts2, static_cast<T*>(out), p)
+#define B2U_APPLY_T(T)                                                                                              \
+  B2U_PDL_LAUNCH((gn_apply_kernel<T>), grid, threads, 0, st, static_cast<const T*>(x), reinterpret_cast<const float2*>(coef), \
+                 reinterpret_cast<const uint8_t*>(mask1), reinterpret_cast<const uint8_t*>(mask2), keep_counts2,        \
+                 static_cast<T*>(out), p)
   if (d->dtype == B2U_F32) B2U_APPLY_T(float);
   else if (d->dtype == B2U_F16) B2U_APPLY_T(__half);
   else B2U_APPLY_T(__nv_bfloat16);
@@ -751,11 +762,11 @@ extern "C" int b2u_gn_apply_pool(const void* x, const float* coef, const uint32_
   dim3 grid(rows, d->n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* parts = pool_num_groups > 0 ? pool_partials : nullptr;
-#define B2U_POOL_T(T)                                                                                                   \
-  gn_apply_pool_kernel<T><<<grid, threads, smem, st>>>(                                                                   \
-      static_cast<const T*>(x), reinterpret_cast<const float2*>(coef), reinterpret_cast<const uint8_t*>(mask1),            \
-      reinterpret_cast<const uint8_t*>(mask2), keep_counts2, static_cast<T*>(skip_out), static_cast<T*>(pooled), parts,    \
-      argmax, sgs, p)
+#define B2U_POOL_T(T)                                                                                               \
+  B2U_PDL_LAUNCH((gn_apply_pool_kernel<T>), grid, threads, smem, st, static_cast<const T*>(x),                          \
+                 reinterpret_cast<const float2*>(coef), reinterpret_cast<const uint8_t*>(mask1),                        \
+                 reinterpret_cast<const uint8_t*>(mask2), keep_counts2, static_cast<T*>(skip_out), static_cast<T*>(pooled), \
+                 parts, argmax, sgs, p)
   if (d->dtype == B2U_F32) B2U_POOL_T(float);
   else if (d->dtype == B2U_F16) B2U_POOL_T(__half);
   else B2U_POOL_T(__nv_bfloat16);
@@ -775,10 +786,9 @@ extern "C" int b2u_head_fwd(const void* x, const float* coef, const uint32_t* ma
   const long groups = static_cast<long>(d->h0) * d->w0;
   const int grid = grid_for((groups + kHeadPix - 1) / kHeadPix * (d->c / 8), 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define B2U_HEAD_T(T)                                                                                                   \
-  head_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), reinterpret_cast<const float2*>(coef),                    \
-                                       reinterpret_cast<const uint8_t*>(mask1), w_head, out, logits, fov, acc, samples,    \
-                                       iter_base, *d)
+#define B2U_HEAD_T(T)                                                                                               \
+  B2U_PDL_LAUNCH((head_kernel<T>), grid, 256, 0, st, static_cast<const T*>(x), reinterpret_cast<const float2*>(coef),   \
+                 reinterpret_cast<const uint8_t*>(mask1), w_head, out, logits, fov, acc, samples, iter_base, *d)
   if (d->dtype == B2U_F32) B2U_HEAD_T(float);
   else if (d->dtype == B2U_F16) B2U_HEAD_T(__half);
   else B2U_HEAD_T(__nv_bfloat16);
@@ -815,7 +825,7 @@ extern "C" int b2u_confusion_counts(const float* seg, const float* gt, const flo
 
 extern "C" int b2u_advance_counter(long long* counter, long long delta, void* stream) {
   B2U_REQUIRE(counter, "null counter");
-  advance_counter_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(counter, delta);
+  B2U_PDL_LAUNCH((advance_counter_kernel), 1, 1, 0, reinterpret_cast<cudaStream_t>(stream), counter, delta);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

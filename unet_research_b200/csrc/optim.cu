@@ -22,6 +22,8 @@ struct SgdChunk {
 
 __global__ void __launch_bounds__(256) sgd_sumsq_kernel(const b2u_sgd_tensor* __restrict__ tensors, const SgdChunk* __restrict__ chunks,
                                                         double* __restrict__ partial) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   const SgdChunk ck = chunks[blockIdx.x];
   const float* g = tensors[ck.tensor].grad + ck.start;
   float acc = 0.f;
@@ -49,6 +51,8 @@ __global__ void __launch_bounds__(256) sgd_sumsq_kernel(const b2u_sgd_tensor* __
 __global__ void __launch_bounds__(256) sgd_step_kernel(const b2u_sgd_tensor* __restrict__ tensors, const SgdChunk* __restrict__ chunks,
                                                        const double* __restrict__ partial, int n_chunks, float lr, float momentum,
                                                        float max_norm, int first_step, float* __restrict__ norm_out) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   __shared__ double sh[256];
   __shared__ float clip_s;
   double a = 0.0;
@@ -118,11 +122,10 @@ extern "C" int b2u_sgd_step(const b2u_sgd_tensor* tensors_dev, const void* chunk
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const SgdChunk* chunks = reinterpret_cast<const SgdChunk*>(chunks_dev);
   if (max_grad_norm > 0.f) {
-    sgd_sumsq_kernel<<<n_chunks, 256, 0, st>>>(tensors_dev, chunks, partial_dev);
+    B2U_PDL_LAUNCH((sgd_sumsq_kernel), n_chunks, 256, 0, st, tensors_dev, chunks, partial_dev);
     B2U_LAUNCH_CHECK();
   }
-  sgd_step_kernel<<<n_chunks, 256, 0, st>>>(tensors_dev, chunks, partial_dev, n_chunks, lr, momentum, max_grad_norm, first_step,
-                                           grad_norm_out);
+  B2U_PDL_LAUNCH((sgd_step_kernel), n_chunks, 256, 0, st, tensors_dev, chunks, partial_dev, n_chunks, lr, momentum, max_grad_norm, first_step, grad_norm_out);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

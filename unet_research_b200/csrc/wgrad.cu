@@ -83,6 +83,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: barrier init, TMEM allocation and descriptor prefetch above overlapped the predecessor's tail; from here on the
+  // kernel touches tensors the predecessor wrote (or still reads)
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -167,6 +171,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
 // layout 0: Conv2d [cg][cx][3][3] (taps 9) ; layout 1: ConvTranspose2d [cx][cout][2][2] with cg = 4*cout, tap-major (taps 1)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int slices, int taps, int cg, int cx,
                                     int layout, int empty_slices_from) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   const long total = static_cast<long>(taps) * cg * cx;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int x = static_cast<int>(i % cx);
@@ -189,6 +195,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
 // layout 0 with 9 taps: one thread per (cg, cx) pair sums the slices of all nine taps (reads coalesced along cx)
 // and writes its nine taps as one 36-byte run, so a warp writes 1152 contiguous bytes of the PyTorch layout.
 __global__ void __launch_bounds__(256) wgrad_reduce9_kernel(const float* __restrict__ ws, float* __restrict__ dw, int slices, int cg, int cx) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   // blockDim = (32 pairs, SG slice groups): slice group y sums slices y, y + SG, ...; the groups are then added in a
   // fixed order through shared memory (deterministic), and thread (x, 0) writes the nine taps.
   __shared__ float part[8][32][9];
@@ -228,6 +236,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce9_kernel(const float* __restr
 template <typename T, int CIN>
 __global__ void __launch_bounds__(256) wgrad_first_kernel(const T* __restrict__ g, const float* __restrict__ x, float* __restrict__ ws, int h0,
                                    int w0, int h, int w, int cout) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   extern __shared__ float sm[];
   const int n = blockIdx.y;
   const int cvs = cout >> 3;
@@ -277,6 +287,8 @@ __global__ void __launch_bounds__(256) wgrad_first_kernel(const T* __restrict__ 
   }
 }
 __global__ void wgrad_first_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int rows, int elems) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += gridDim.x * blockDim.x) {
     double a = 0.0;
     for (int r = 0; r < rows; ++r) a += ws[static_cast<size_t>(r) * elems + i];
@@ -286,6 +298,8 @@ __global__ void wgrad_first_reduce_kernel(const float* __restrict__ ws, float* _
 
 template <typename T>
 __global__ void pack_convT_dgrad_kernel(const float* __restrict__ w, T* __restrict__ out, int cin, int cout) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
   const long total = 4L * cout * cin;          // out[ci][tap*cout + co] = w[ci][co][tap]
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int k = static_cast<int>(i % (4 * cout));
@@ -376,20 +390,20 @@ extern "C" int b2u_wgrad(const void* g, const void* x, float* workspace, float* 
   static bool attr9 = false, attr1 = false;
   if (d->taps == 9) {
     if (!attr9) { B2U_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr9 = true; }
-    wgrad_kernel<9><<<grid, kWgThreads, pl.smem, st>>>(tg, tx, p);
+    B2U_PDL_LAUNCH((wgrad_kernel<9>), grid, kWgThreads, pl.smem, st, tg, tx, p);
   } else {
     if (!attr1) { B2U_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr1 = true; }
-    wgrad_kernel<1><<<grid, kWgThreads, pl.smem, st>>>(tg, tx, p);
+    B2U_PDL_LAUNCH((wgrad_kernel<1>), grid, kWgThreads, pl.smem, st, tg, tx, p);
   }
   B2U_LAUNCH_CHECK();
   const long total = static_cast<long>(d->taps) * d->cg * d->cx;
   if (d->taps == 9 && d->layout == 0) {
     const long pairs = static_cast<long>(d->cg) * d->cx;
     const int nsg = pl.slices >= 8 ? 8 : (pl.slices >= 4 ? 4 : (pl.slices >= 2 ? 2 : 1));
-    wgrad_reduce9_kernel<<<static_cast<unsigned>((pairs + 31) / 32), dim3(32, nsg), 0, st>>>(workspace, dw, pl.slices, d->cg, d->cx);
+    B2U_PDL_LAUNCH((wgrad_reduce9_kernel), static_cast<unsigned>((pairs + 31) / 32), dim3(32, nsg), 0, st, workspace, dw, pl.slices, d->cg, d->cx);
   } else {
     int blocks = static_cast<int>((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
-    wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(workspace, dw, pl.slices, d->taps, d->cg, d->cx, d->layout, pl.slices);
+    B2U_PDL_LAUNCH((wgrad_reduce_kernel), blocks, 256, 0, st, workspace, dw, pl.slices, d->taps, d->cg, d->cx, d->layout, pl.slices);
   }
   B2U_LAUNCH_CHECK();
   return B2U_OK;
@@ -407,11 +421,11 @@ extern "C" int b2u_wgrad_first(const void* g, const float* x_nchw, float* worksp
   dim3 grid(rows, n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t smem = static_cast<size_t>(threads) * 8 * sizeof(float);
-  if (cin == 1) wgrad_first_kernel<__nv_bfloat16, 1><<<grid, threads, smem, st>>>(static_cast<const __nv_bfloat16*>(g), x_nchw, workspace, h0, w0, h, w, cout);
-  else wgrad_first_kernel<__nv_bfloat16, 3><<<grid, threads, smem, st>>>(static_cast<const __nv_bfloat16*>(g), x_nchw, workspace, h0, w0, h, w, cout);
+  if (cin == 1) B2U_PDL_LAUNCH((wgrad_first_kernel<__nv_bfloat16, 1>), grid, threads, smem, st, static_cast<const __nv_bfloat16*>(g), x_nchw, workspace, h0, w0, h, w, cout);
+  else B2U_PDL_LAUNCH((wgrad_first_kernel<__nv_bfloat16, 3>), grid, threads, smem, st, static_cast<const __nv_bfloat16*>(g), x_nchw, workspace, h0, w0, h, w, cout);
   B2U_LAUNCH_CHECK();
   const int elems = cout * cin * 9;
-  wgrad_first_reduce_kernel<<<(elems + 255) / 256, 256, 0, st>>>(workspace, dw, rows * n, elems);
+  B2U_PDL_LAUNCH((wgrad_first_reduce_kernel), (elems + 255) / 256, 256, 0, st, workspace, dw, rows * n, elems);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -421,8 +435,8 @@ extern "C" int b2u_pack_convT2x2_dgrad_weight(const float* w, void* packed, int 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long total = 4L * cout * cin;
   const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  if (dtype == B2U_F32) pack_convT_dgrad_kernel<float><<<blocks, 256, 0, st>>>(w, static_cast<float*>(packed), cin, cout);
-  else pack_convT_dgrad_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(packed), cin, cout);
+  if (dtype == B2U_F32) B2U_PDL_LAUNCH((pack_convT_dgrad_kernel<float>), blocks, 256, 0, st, w, static_cast<float*>(packed), cin, cout);
+  else B2U_PDL_LAUNCH((pack_convT_dgrad_kernel<__nv_bfloat16>), blocks, 256, 0, st, w, static_cast<__nv_bfloat16*>(packed), cin, cout);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
