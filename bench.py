@@ -255,10 +255,17 @@ def run_gpu(args):
             gbs = nbytes / (other[key] / 1000.0) / 1e9
             hbm[name] = {"algorithmic_mb_per_step": nbytes / 1e6, "ms_per_step": other[key], "achieved_gbs": gbs,
                          "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
-    traffic = load_traffic()
+    tj = load_traffic()
+    traffic = None
+    traffic_detail = None
+    if tj and tj.get("iter_batch") == NB:
+        # DRAM bytes (read + write) of the conv family per step = per group of 21 launches, like `achieved`
+        traffic = tj.get("conv_family_dram_bytes_per_step")
+        traffic_detail = {"unit": "bytes per step (17 conv3x3 + 4 convT launches)", "source": tj.get("source"),
+                          "algorithmic_bytes_per_step": conv_bytes_per_step(NB)}
     roofline = {"bound": "tensor", "kernel": "conv3x3_v2_kernel + convT_v2_kernel (17 conv3x3 + 4 convT launches per step)",
                 "achieved": conv_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": conv_tflops / peaks["bf16_tflops_sustained"], "traffic": traffic,
+                "frac": conv_tflops / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_detail": traffic_detail,
                 "hbm_bound_kernels": hbm, "hbm_peak_gbs": peaks["hbm_gbs"],
                 "peak_source": peaks["src"] + " bf16_tflops_sustained (kernels timed inside a long step)",
                 "conv_ms_per_step": conv_ms, "step_ms": ms_max / K, "conv_share_of_step": conv_ms / (ms_max / K),
@@ -330,6 +337,25 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def conv_bytes_per_step(nb, filters=64, depth=4, h=592, w=576):
+    """ALGORITHMIC HBM bytes of the tensor-core conv family for one step of nb batched iterations: every conv reads
+    its bf16 input once and writes its bf16 output once, weights once per launch (the first conv is not in the family)."""
+    tot = 0.0
+    c = filters
+    for lvl in range(depth + 1):
+        m = float(h >> lvl) * (w >> lvl) * nb
+        cin1 = c // 2 if lvl > 0 else None                     # encoder unit 1 input channels (level 0 = first conv)
+        if lvl > 0:
+            tot += 2.0 * m * (cin1 + c) + 2.0 * 9 * cin1 * c    # encoder / bottleneck unit 1
+        tot += 2.0 * m * (c + c) + 2.0 * 9 * c * c              # unit 2
+        if lvl < depth:
+            tot += 2.0 * m * (2 * c + c) + 2.0 * 9 * 2 * c * c  # decoder unit 1 (reads the concat buffer)
+            tot += 2.0 * m * (c + c) + 2.0 * 9 * c * c          # decoder unit 2
+            tot += 2.0 * (m / 4) * (2 * c) + 2.0 * m * c + 2.0 * 4 * 2 * c * c   # up-conv into this level
+        c *= 2
+    return tot
 
 
 def elementwise_bytes_per_step(nb, filters=64, depth=4, h=592, w=576, h0=H0, w0=W0):

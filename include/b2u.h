@@ -181,8 +181,14 @@ typedef struct {
   int32_t n_img, c, h, w;     /* tensor this call masks                                               */
   int32_t block_size;         /* odd, <= 31                                                           */
   int32_t count_index;        /* slot of keep_counts this call adds to                                */
-  int32_t reserved[2];
+  int32_t dilate_first_block; /* first block of this call in the flat dilate grid: filled by b2u_dropblock_plan */
+  int32_t reserved;
 } b2u_dropblock_call;
+/* Fills dilate_first_block of every descriptor of a HOST table (prefix sum of the blocks each call needs in
+ * b2u_dropblock_dilate's flat 1-D grid) and returns the total in *total_blocks.  Call it once, after the shapes are
+ * set and before the table is copied to the device; b2u_dropblock_dilate rejects a table that was not planned.
+ * (A one-entry table is planned by construction: the field is 0.) */
+int b2u_dropblock_plan(b2u_dropblock_call* host_table, int n_calls, long long* total_blocks);
 /* table: device array of n_calls descriptors; seed: host value; offset_base: device scalar added to every
  * philox_offset (lets a captured CUDA graph advance the stream between replays); may be NULL. */
 int b2u_dropblock_centers(const b2u_dropblock_call* table, int n_calls, uint64_t seed,

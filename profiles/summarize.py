@@ -19,7 +19,7 @@ for r in rows:
     a[1] += v
 tot = sum(v[1] for v in agg.values())
 with open(f"profiles/{tag}_launches.md", "w") as f:
-    f.write(f"# {tag}: ncu launch list of `python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu` (first {len(rows)} launches)\n\n")
+    f.write(f"# {tag}: ncu launch list of `python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-train` (first {len(rows)} launches)\n\n")
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` -- per-launch times are cold-cache and serialised: compare SHARES.\n\n")
     f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -34,7 +34,7 @@ want = ["Grid Size", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.av
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor"]
 with open(f"profiles/{tag}_conv_ncu.md", "w") as f:
-    f.write(f"# {tag}: `ncu --set full --clock-control none -k regex:conv_gemm` on the first conv launches of one MC step (5 batched iterations)\n\n")
+    f.write(f"# {tag}: `ncu --set full --clock-control none -k regex:conv3x3_v2` on the first conv launches of one MC step (`python tests/prof_step.py 10 2`, 10 batched iterations)\n\n")
     f.write("| # | kernel | " + " | ".join(w.split(".")[0] for w in want) + " |\n|---|---|" + "---|" * len(want) + "\n")
     for i, r in enumerate(rr[2:]):
         name = r[idx["Kernel Name"]].split("(")[0].replace("void b2u::", "")

@@ -62,6 +62,24 @@ def test_argument_validation_without_gpu():
         _lib.call("b2u_gn_apply", None, None, None, None, None, None, None, None)
 
 
+def test_dropblock_plan_flat_dilate_grid():
+    """b2u_dropblock_plan (host only): prefix sum of the dilate blocks of every call = planes x ceil(items / 4) with
+    items = ceil(h / 37) bands x ceil(w / 32) words; the canonical U-Net needs 1792 blocks per iteration."""
+    sites = engine.site_shapes(592, 576, 64, 4)
+    calls = (_lib.DropblockCall * len(sites))()
+    expect = []
+    for d, (c, h, w) in zip(calls, sites):
+        d.n_img, d.c, d.h, d.w, d.block_size = 1, c, h, w, 7
+        expect.append((c // 32) * ((-(-h // 37) * -(-w // 32) + 3) // 4))
+    total = C.c_longlong(0)
+    _lib.call("b2u_dropblock_plan", calls, len(sites), C.byref(total))
+    assert [d.dilate_first_block for d in calls] == [sum(expect[:i]) for i in range(len(sites))]
+    assert total.value == sum(expect) == 1792
+    calls[3].block_size = 8
+    with pytest.raises(_lib.B2uError, match="odd"):
+        _lib.call("b2u_dropblock_plan", calls, len(sites), C.byref(total))
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))

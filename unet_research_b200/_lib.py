@@ -54,7 +54,8 @@ class DropblockCall(C.Structure):
     _fields_ = [("philox_offset", C.c_uint64), ("center_word_off", C.c_uint64), ("mask_word_off", C.c_uint64),
                 ("numel", C.c_uint32), ("grid", C.c_uint32), ("thresh_lo", C.c_uint32), ("thresh_hi", C.c_uint32),
                 ("n_img", C.c_int32), ("c", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
-                ("block_size", C.c_int32), ("count_index", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("block_size", C.c_int32), ("count_index", C.c_int32), ("dilate_first_block", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -97,6 +98,7 @@ SIGNATURES = {
     "b2u_advance_counter": (_I, [_P, _LL, _P]),
     "b2u_dropblock_centers": (_I, [_P, _I, C.c_uint64, _P, _P, _P]),
     "b2u_dropblock_centers_ichan": (_I, [_P, _I, C.POINTER(DropblockCall), C.c_uint64, _P, _P, _LL, _P]),
+    "b2u_dropblock_plan": (_I, [C.POINTER(DropblockCall), _I, C.POINTER(_LL)]),
     "b2u_dropblock_dilate": (_I, [_P, _I, C.POINTER(DropblockCall), _P, _P, _P, _P]),
     "b2u_dropblock_centers_from_uniform": (_I, [_P, _P, _LL, _F, _P]),
     "b2u_rotate_bilinear": (_I, [_P, _P, _I, _I, _I, _I, C.POINTER(_D), _I, _P]),

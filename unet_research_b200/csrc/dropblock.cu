@@ -45,8 +45,11 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// grid = (ceil(torch_grid / 1), n_calls) blocks of 256 threads: block b, thread t IS torch's thread
-// idx = 256*b + t for every trip, so no index arithmetic beyond one add per trip.
+// grid = (SMs * 8, n_calls) blocks of 256 threads: block b of call k, thread t IS torch's thread idx = 256*b + t for
+// every trip, so there is no index arithmetic beyond one add per trip; blocks beyond the call's torch grid exit.
+// Blocks are SHORT on purpose: next to the high-priority forward pass the block scheduler hands freed SM slots to the
+// forward's CTAs first, so the mask build only fills what the forward leaves idle (a persistent grid keeps its warps
+// resident and was measured to destroy that overlap: 11.4 instead of 8.8 ms per Monte-Carlo step).
 __global__ void __launch_bounds__(256) dropblock_centers_kernel(const b2u_dropblock_call* __restrict__ table, uint64_t seed,
                                          const unsigned long long* __restrict__ offset_base,
                                          uint32_t* __restrict__ center_bits) {
@@ -59,11 +62,20 @@ __global__ void __launch_bounds__(256) dropblock_centers_kernel(const b2u_dropbl
   const uint64_t off = c.philox_offset + (offset_base ? *offset_base : 0ull);
   const uint64_t ctr_base = off >> 2;                         // curand skipahead: offset counts 32-bit words
   const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
-  const int lane = threadIdx.x & 31;
+  const uint32_t lane = threadIdx.x & 31u;
   const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
   const uint32_t idx0 = idx & ~31u;
-  uint32_t* out = center_bits + c.center_word_off;
   const uint32_t lo_t = c.thresh_lo, hi_t = c.thresh_hi;
+  // Store role, fixed before the loop so that the loop body stays branch-free: lane ii < 4 owns ballot word ii of
+  // every trip, i.e. elements (4 trip + ii) * tn + idx0 .. + 31; it stores for trip < my_trips (0 for lanes >= 4).
+  // (Selecting the word and bounds-checking per trip cost 40 % of the instructions of the first version.)
+  uint32_t my_trips = 0u;
+  const uint64_t first = static_cast<uint64_t>(lane) * tn + idx0;
+  if (lane < 4u && first < c.numel) my_trips = static_cast<uint32_t>((c.numel - first - 1ull) / (4ull * tn)) + 1u;
+  uint32_t* wp = center_bits + c.center_word_off + (first >> 5);
+  const uint32_t wstep = tn >> 3;                              // words per trip (4 tn bits)
+  const bool is1 = lane == 1u, is2 = lane == 2u, is3 = lane == 3u;
+#pragma unroll 1
   for (uint32_t trip = 0; trip < trips; ++trip) {
     const uint64_t ctr = ctr_base + trip;
     uint32_t r[4];
@@ -71,13 +83,12 @@ __global__ void __launch_bounds__(256) dropblock_centers_kernel(const b2u_dropbl
     uint32_t words[4];
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii) words[ii] = __ballot_sync(0xffffffffu, r[ii] < lo_t || r[ii] >= hi_t);
-    if (lane < 4) {
-      const uint64_t p0 = (static_cast<uint64_t>(trip) * 4ull + lane) * tn + idx0;   // first element of this word
-      if (p0 < c.numel) {
-        const uint32_t wsel = lane == 0 ? words[0] : lane == 1 ? words[1] : lane == 2 ? words[2] : words[3];
-        out[p0 >> 5] = wsel;
-      }
-    }
+    uint32_t wsel = words[0];
+    wsel = is1 ? words[1] : wsel;
+    wsel = is2 ? words[2] : wsel;
+    wsel = is3 ? words[3] : wsel;
+    if (trip < my_trips) *wp = wsel;
+    wp += wstep;
   }
 }
 
@@ -156,24 +167,35 @@ __device__ __forceinline__ uint32_t row_bits(const uint32_t* __restrict__ bits, 
 }
 
 // One warp: 32 channels (lane = channel) x 32 pixels of one image row band.
-// grid = (bands * wwords, c/32 * n_img, n_calls).
+// Flat 1-D grid over all calls of the table: call k owns blocks [dilate_first_block_k, dilate_first_block_{k+1}),
+// = planes(k) x ceil(items(k) / 4) blocks (b2u_dropblock_plan); a block finds its call by binary search.  (A 3-D grid
+// sized for the largest call in every dimension launched 28x more blocks than there is work for the U-Net's sites.)
 // BS_CT > 0: block size known at compile time (the reference default 7): the smear, the ring and the slot
 // arithmetic unroll into straight-line code.
+constexpr int kDilateBandRows = 37;
+constexpr int kDilateWarps = 4;
+
+static inline int dilate_items(const b2u_dropblock_call& c) {
+  return ((c.h + kDilateBandRows - 1) / kDilateBandRows) * ((c.w + 31) / 32);
+}
+static inline int dilate_blocks(const b2u_dropblock_call& c) {
+  return ((dilate_items(c) + kDilateWarps - 1) / kDilateWarps) * ((c.c / 32) * c.n_img);
+}
+
 template <int RING, int BS_CT>
-__global__ void __launch_bounds__(128) dropblock_dilate_kernel(const b2u_dropblock_call* __restrict__ table,
-                                        const uint32_t* __restrict__ center_bits, uint32_t* __restrict__ mask_bits,
-                                        unsigned long long* __restrict__ keep_counts, int band_rows) {
-  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
-  pdl_trigger();    // the successor may be scheduled once every CTA got here
-  const b2u_dropblock_call c = table[blockIdx.z];
+__device__ __forceinline__ void dilate_block(const b2u_dropblock_call& c, int local, const uint32_t* __restrict__ center_bits,
+                                             uint32_t* __restrict__ mask_bits, unsigned long long* __restrict__ keep_counts) {
+  constexpr int band_rows = kDilateBandRows;
   const int cgs = c.c >> 5;
   const int wwords = (c.w + 31) >> 5;
   const int bands = (c.h + band_rows - 1) / band_rows;
+  const int nitems = bands * wwords;
+  const int blocks_x = (nitems + kDilateWarps - 1) / kDilateWarps;
+  const int plane_grp = local / blocks_x;                               // (img, channel group)
   const int warp_in_block = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int item = blockIdx.x * (blockDim.x >> 5) + warp_in_block;       // (band, wword)
-  const int plane_grp = blockIdx.y;                                     // (img, channel group)
-  if (item >= bands * wwords || plane_grp >= cgs * c.n_img) return;     // uniform per warp
+  const int item = (local - plane_grp * blocks_x) * kDilateWarps + warp_in_block;       // (band, wword)
+  if (item >= nitems || plane_grp >= cgs * c.n_img) return;             // uniform per warp
   const int band = item / wwords, wj = item - band * wwords;
   const int img = plane_grp / cgs, cg = plane_grp - img * cgs;
   const int bs = BS_CT > 0 ? BS_CT : c.block_size;
@@ -250,6 +272,30 @@ __global__ void __launch_bounds__(128) dropblock_dilate_kernel(const b2u_dropblo
   if (lane == 0 && keep) atomicAdd(keep_counts + c.count_index, keep);
 }
 
+// One short block per entry of the flat block list (see the centre kernel for why not a persistent grid).
+template <int RING, int BS_CT>
+__global__ void __launch_bounds__(128) dropblock_dilate_kernel(const b2u_dropblock_call* __restrict__ table, int n_calls,
+                                        int total_blocks, const uint32_t* __restrict__ center_bits,
+                                        uint32_t* __restrict__ mask_bits, unsigned long long* __restrict__ keep_counts) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
+  int k = 0, hi_k = n_calls - 1;
+  while (k < hi_k) {                                          // last call whose first block is <= blockIdx.x
+    const int mid = (k + hi_k + 1) >> 1;
+    if (__ldg(&table[mid].dilate_first_block) <= static_cast<int>(blockIdx.x)) k = mid;
+    else hi_k = mid - 1;
+  }
+  int next_first = k + 1 < n_calls ? __ldg(&table[k + 1].dilate_first_block) : total_blocks;
+  for (int b = blockIdx.x; b < total_blocks; b += gridDim.x) {
+    while (b >= next_first) {
+      ++k;
+      next_first = k + 1 < n_calls ? __ldg(&table[k + 1].dilate_first_block) : total_blocks;
+    }
+    const b2u_dropblock_call c = table[k];
+    dilate_block<RING, BS_CT>(c, b - c.dilate_first_block, center_bits, mask_bits, keep_counts);
+  }
+}
+
 }  // namespace b2u
 
 using namespace b2u;
@@ -285,35 +331,48 @@ extern "C" int b2u_dropblock_centers_ichan(const b2u_dropblock_call* table, int 
   return B2U_OK;
 }
 
+extern "C" int b2u_dropblock_plan(b2u_dropblock_call* host_table, int n_calls, long long* total_blocks) {
+  B2U_REQUIRE(host_table && n_calls > 0, "bad arguments");
+  long long total = 0;
+  for (int i = 0; i < n_calls; ++i) {
+    b2u_dropblock_call& c = host_table[i];
+    B2U_REQUIRE(c.block_size >= 1 && c.block_size <= 31 && (c.block_size & 1), "block_size must be odd and <= 31 (got %d)", c.block_size);
+    B2U_REQUIRE(c.c % 32 == 0 && c.c > 0, "channels must be a multiple of 32 (got %d)", c.c);
+    B2U_REQUIRE(c.h >= c.block_size && c.w >= c.block_size, "feature map %dx%d smaller than block_size %d", c.h, c.w, c.block_size);
+    B2U_REQUIRE(total < 0x7fffffffll, "too many dilate blocks");
+    c.dilate_first_block = static_cast<int32_t>(total);
+    total += dilate_blocks(c);
+  }
+  B2U_REQUIRE(total < 0x7fffffffll, "too many dilate blocks");
+  if (total_blocks) *total_blocks = total;
+  return B2U_OK;
+}
+
 extern "C" int b2u_dropblock_dilate(const b2u_dropblock_call* table, int n_calls, const b2u_dropblock_call* host_table,
                                     const uint32_t* center_bits, uint32_t* mask_bits, unsigned long long* keep_counts,
                                     void* stream) {
   B2U_REQUIRE(table && host_table && center_bits && mask_bits && keep_counts && n_calls > 0, "bad arguments");
-  // the grid must cover the largest call of the table; smaller calls exit early
-  const int band_rows = 37;
-  int max_items = 0, max_planes = 0, max_bs = 0;
+  long long total = 0;
+  int max_bs = 0;
+  bool all7 = true;
   for (int i = 0; i < n_calls; ++i) {
     const b2u_dropblock_call& c = host_table[i];
     B2U_REQUIRE(c.block_size >= 1 && c.block_size <= 31 && (c.block_size & 1), "block_size must be odd and <= 31 (got %d)", c.block_size);
     B2U_REQUIRE(c.c % 32 == 0 && c.c > 0, "channels must be a multiple of 32 (got %d)", c.c);
-    B2U_REQUIRE(c.h >= c.block_size && c.w >= c.block_size, "feature map %dx%d smaller than block_size %d", c.h, c.w, c.block_size);
-    const int items = ((c.h + band_rows - 1) / band_rows) * ((c.w + 31) / 32);
-    const int planes = (c.c / 32) * c.n_img;
-    if (items > max_items) max_items = items;
-    if (planes > max_planes) max_planes = planes;
+    B2U_REQUIRE(c.dilate_first_block == total, "call table was not planned (b2u_dropblock_plan) or changed shape afterwards");
+    total += dilate_blocks(c);
     if (c.block_size > max_bs) max_bs = c.block_size;
+    all7 = all7 && c.block_size == 7;
   }
-  B2U_REQUIRE(max_planes <= 65535, "too many channel groups x images (%d)", max_planes);
-  dim3 grid((max_items + 3) / 4, max_planes, n_calls);
-  bool all7 = true;
-  for (int i = 0; i < n_calls; ++i) all7 = all7 && host_table[i].block_size == 7;
+  dim3 grid(static_cast<unsigned>(total));
+  const int tb = static_cast<int>(total);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (all7)
-    B2U_PDL_LAUNCH((dropblock_dilate_kernel<7, 7>), grid, 128, 0, st, table, center_bits, mask_bits, keep_counts, band_rows);
+    B2U_PDL_LAUNCH((dropblock_dilate_kernel<7, 7>), grid, 128, 0, st, table, n_calls, tb, center_bits, mask_bits, keep_counts);
   else if (max_bs <= 7)
-    B2U_PDL_LAUNCH((dropblock_dilate_kernel<7, 0>), grid, 128, 0, st, table, center_bits, mask_bits, keep_counts, band_rows);
+    B2U_PDL_LAUNCH((dropblock_dilate_kernel<7, 0>), grid, 128, 0, st, table, n_calls, tb, center_bits, mask_bits, keep_counts);
   else
-    B2U_PDL_LAUNCH((dropblock_dilate_kernel<31, 0>), grid, 128, 0, st, table, center_bits, mask_bits, keep_counts, band_rows);
+    B2U_PDL_LAUNCH((dropblock_dilate_kernel<31, 0>), grid, 128, 0, st, table, n_calls, tb, center_bits, mask_bits, keep_counts);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -193,6 +193,7 @@ class MaskPlan:
                 center_words += (numel + 31) // 32 + 2
             mask_words += n_img * hh * ww * (c // 32)
         self.host_table = calls
+        call("b2u_dropblock_plan", calls, n_calls * self.n_sites, None)     # flat dilate grid: first block of every call
         raw = np.frombuffer(bytes(calls), dtype=np.uint8).copy()
         self.table = torch.from_numpy(raw).to(device)
         self.center_words = center_words + 4
@@ -466,8 +467,11 @@ class UNetEngine:
     # ---- the forward schedule
     def forward(self, x: torch.Tensor, ws: Workspace, masks: Optional[MaskPlan] = None, *, head_out: bool = True,
                 want_logits: bool = False, mc: Optional[dict] = None, argmax: Optional[Dict[int, torch.Tensor]] = None,
-                shared_input: bool = False):
+                shared_input: bool = False, hook=None):
         """x: fp32 NCHW [n, Cin, h0, w0] on the engine's device (contiguous).  Launches only.
+        hook(point): optional callback invoked between launches at the schedule points "enc{lvl}" (before encoder
+        level lvl), "bottleneck" and "dec{u}" (before decoder stage u) -- the Monte-Carlo runner forks its mask-build
+        stream there.
         shared_input: the n images are the SAME image (Monte-Carlo iterations batched along n): the first conv and
         its GroupNorm statistics are computed once and shared; only the DropBlock mask / rescale differ per image.
         mc = {"acc": double[2,h0,w0], "fov": float[h0,w0] | None, "samples": float[R,h0,w0] | None,
@@ -486,6 +490,8 @@ class UNetEngine:
 
         c = f
         for lvl in range(d):
+            if hook is not None:
+                hook(f"enc{lvl}")
             hh, ww = ws.h >> lvl, ws.w >> lvl
             p = f"down_blocks.{lvl}.0"
             s1, s2, scat = 2 * lvl, 2 * lvl + 1, 2 * d + 2 + 3 * (d - 1 - lvl)
@@ -515,6 +521,8 @@ class UNetEngine:
                  ptr(B[f"d{lvl}.pact"]), C.byref(a), st)
             c *= 2
         # bottleneck
+        if hook is not None:
+            hook("bottleneck")
         hh, ww = ws.h >> d, ws.w >> d
         prev = f"d{d - 1}.pact"
         for j, (idx, site) in enumerate(((0, 2 * d), (4, 2 * d + 1)), start=1):
@@ -527,6 +535,8 @@ class UNetEngine:
             prev = f"b.act{j}"
         # decoder
         for u in range(d):
+            if hook is not None:
+                hook(f"dec{u}")
             lvl = d - 1 - u
             cin = c
             c //= 2

@@ -13,6 +13,8 @@
 """
 from __future__ import annotations
 
+import os
+
 from typing import Optional, Tuple
 
 import torch
@@ -107,11 +109,15 @@ class MCRunner:
         self.graph = None
         self.launches_per_step = 0
         self.seed = 0
+        # Where in the forward the mask build of the next step is forked (engine.forward hook points).  The mask
+        # kernels take issue slots from whatever runs next to them; the deep levels' conv kernels (long K loops, short
+        # epilogues) have the most to spare, the 592x576 levels the least (tests/exp_overlap.py).
+        self.fork_point = os.environ.get("B2U_MC_FORK", "enc0")
 
     # ---- building blocks (all launch-only)
-    def _forward(self, k: int):
+    def _forward(self, k: int, hook=None):
         m = self.masks[k] if self.active else None
-        self.eng.forward(self.x, self.ws, m, head_out=False, mc=self.mc, shared_input=True)
+        self.eng.forward(self.x, self.ws, m, head_out=False, mc=self.mc, shared_input=True, hook=hook)
         call("b2u_advance_counter", ptr(self.iter_base), self.nb, stream_ptr())
 
     def _generate(self, k: int, stride_blocks: int):
@@ -133,10 +139,13 @@ class MCRunner:
             return
         main = torch.cuda.current_stream(self.dev)
         for cur, nxt in ((0, 1), (1, 0)):
-            self.side.wait_stream(main)                 # fork: side sees everything enqueued so far
-            with torch.cuda.stream(self.side):
-                self._generate(nxt, 2)                  # masks for the following step, concurrently ...
-            self._forward(cur)                          # ... with this step's forward
+            def fork(point, nxt=nxt):
+                if point != self.fork_point:
+                    return
+                self.side.wait_stream(main)             # fork: side sees everything enqueued so far
+                with torch.cuda.stream(self.side):
+                    self._generate(nxt, 2)              # masks for the following step, concurrently ...
+            self._forward(cur, fork)                    # ... with the rest of this step's forward
             main.wait_stream(self.side)                 # join
 
     def begin(self, im: torch.Tensor, fov: torch.Tensor, t0: int, seed: int, stream_start: int):
