@@ -163,7 +163,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -183,7 +183,7 @@ def run_gpu(args):
     import unet_research_b200 as U
     from unet_research_b200 import _lib, synthetic
     from unet_research_b200._lib import call, ptr, stream_ptr
-    from unet_research_b200.smoke_test import build_canonical
+    from unet_research_b200.canonical import build_canonical
 
     peaks = load_peaks()
     sampler = ClockSampler(local)
@@ -333,7 +333,7 @@ def run_gpu(args):
             "tflops_whole_step": FLOP_PER_FORWARD * NB * world * K / (ms_max / 1000.0) / 1e12,
             "mc_1000_iter_projected_s": 1000.0 / value, "allreduce_ms": allreduce_ms,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -399,7 +399,7 @@ def bench_train(dev, rank, world, steps, warmup):
     from torch import nn
     import unet_research_b200 as U
     from unet_research_b200 import synthetic
-    from unet_research_b200.smoke_test import build_canonical
+    from unet_research_b200.canonical import build_canonical
     model, _ = build_canonical(dev, dropblock=True, compute="bf16")
     model.train()
     model.data_parallel = world > 1
@@ -486,7 +486,23 @@ def time_conv_kernels(runner, dev, reps):
     return conv, per_step
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # Libraries chat on stdout (NCCL prints its version banner there under torchrun): keep the original stdout for
+    # the JSON line only and send everything else to stderr.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

@@ -14,7 +14,7 @@ import torch
 
 import unet_research_b200 as U
 from unet_research_b200 import _lib, engine, synthetic, uncertainty
-from unet_research_b200.smoke_test import build_canonical
+from unet_research_b200.canonical import build_canonical
 
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 dev = torch.device("cuda")

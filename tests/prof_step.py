@@ -11,7 +11,7 @@ import torch
 
 import unet_research_b200 as U
 from unet_research_b200 import _lib, synthetic
-from unet_research_b200.smoke_test import build_canonical
+from unet_research_b200.canonical import build_canonical
 
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
