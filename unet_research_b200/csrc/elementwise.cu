@@ -270,7 +270,17 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const T* __restrict__ 
 
 // Encoder tail: apply + skip store (with concat mask) + 2x2 max-pool + pooled GroupNorm partials.
 constexpr int kPoolUnroll = 2;
-template <typename T>
+// ATen's max-pool update rule `val > maxval || isnan(val)` without the window index = a NaN-propagating maximum
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+// ARGMAX: also record the window index of the maximum (training: the backward scatters through it); the inference
+// instantiation drops the index bookkeeping (a third of the kernel's instructions).
+// MODE 1: both DropBlock masks and the skip store present (Monte-Carlo / training), 0: neither mask (eval forward),
+// 2: decided at run time (any other combination) -- the specialised modes are free of per-tap null checks.
+template <typename T, bool ARGMAX, int MODE>
 __global__ void __launch_bounds__(256, 2) gn_apply_pool_kernel(const T* __restrict__ x, const float2* __restrict__ coef, const uint8_t* __restrict__ mask1,
                                      const uint8_t* __restrict__ mask2, const unsigned long long* __restrict__ keep2,
                                      T* __restrict__ skip_out, T* __restrict__ pooled, float* __restrict__ pool_partials,
@@ -295,23 +305,49 @@ __global__ void __launch_bounds__(256, 2) gn_apply_pool_kernel(const T* __restri
   const bool relu = p.relu != 0;
   const int m2s = p.mask2_cstride >> 3, m2o = (p.mask2_coffset >> 3) + cv;
   constexpr int U = kPoolUnroll;                        // pooled pixels per trip: 8 x 16 B loads in flight per thread
+  // Addressing: 64-bit base pointers per image (channel slice folded in), 32-bit element offsets inside the image
+  // (the launcher checks h*w*max(c, out_cstride) < 2^31), window taps at constant offsets, and the pooled (row, col)
+  // advanced incrementally instead of divided out per trip -- the first version of this loop spent two thirds of its
+  // ~225 instructions per 16-byte vector on 64-bit index arithmetic.
+  const size_t img_pix = static_cast<size_t>(n) * p.h * p.w;
+  const T* const xb = x + img_pix * p.c + cv * 8;
+  const bool has1 = MODE == 2 ? mask1 != nullptr : MODE == 1;
+  const bool has2 = MODE == 2 ? mask2 != nullptr : MODE == 1;
+  const bool has_skip = MODE == 2 ? skip_out != nullptr : true;
+  const uint8_t* const m1b = mask1 + img_pix * cvs + cv;
+  const uint8_t* const m2b = mask2 + img_pix * m2s + m2o;
+  T* const sb = skip_out + img_pix * p.out_cstride + p.out_coffset + cv * 8;
+  T* const pb = pooled + static_cast<size_t>(n) * npool * p.c + cv * 8;
+  uint8_t* const ab = ARGMAX ? argmax + static_cast<size_t>(n) * npool * p.c + cv * 8 : nullptr;
+  const uint32_t tap_x[4] = {0u, static_cast<uint32_t>(p.c), static_cast<uint32_t>(p.w) * p.c, static_cast<uint32_t>(p.w) * p.c + p.c};
+  const uint32_t tap_m1[4] = {0u, static_cast<uint32_t>(cvs), static_cast<uint32_t>(p.w) * cvs, static_cast<uint32_t>(p.w) * cvs + cvs};
+  const uint32_t tap_m2[4] = {0u, static_cast<uint32_t>(m2s), static_cast<uint32_t>(p.w) * m2s, static_cast<uint32_t>(p.w) * m2s + m2s};
+  const uint32_t tap_s[4] = {0u, static_cast<uint32_t>(p.out_cstride), static_cast<uint32_t>(p.w) * p.out_cstride,
+                             static_cast<uint32_t>(p.w) * p.out_cstride + p.out_cstride};
   const int stride = gridDim.x * slots * U;
+  const int dq = stride / pw, dr = stride - dq * pw;    // (row, col) step of one trip
+  int py[U], px[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int pp0 = blockIdx.x * slots * U + slot + u * slots;
+    py[u] = pp0 / pw;
+    px[u] = pp0 - py[u] * pw;
+  }
   for (int base = blockIdx.x * slots * U + slot; base < npool; base += stride) {
     Vec8<T> vec[U][4];
     uint32_t m1[U][4], m2[U][4];
-    long pix00[U];
+    uint32_t q00[U];                                    // in-image pixel index of the window's top-left tap
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int pp = base + u * slots;
+      q00[u] = static_cast<uint32_t>(2 * py[u]) * p.w + 2 * px[u];
       if (pp < npool) {
-        const int py = pp / pw, px = pp - py * pw;
-        pix00[u] = (static_cast<long>(n) * p.h + 2 * py) * p.w + 2 * px;
+        const uint32_t ox = q00[u] * p.c, om1 = q00[u] * cvs, om2 = q00[u] * m2s;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const long pix = pix00[u] + (k >> 1) * p.w + (k & 1);
-          vec[u][k].load(x + pix * p.c + cv * 8);
-          m1[u][k] = mask1 ? mask1[pix * cvs + cv] : 0xFFu;
-          m2[u][k] = mask2 ? mask2[pix * m2s + m2o] : 0xFFu;
+          vec[u][k].load(xb + (ox + tap_x[k]));
+          m1[u][k] = has1 ? m1b[om1 + tap_m1[k]] : 0xFFu;
+          m2[u][k] = has2 ? m2b[om2 + tap_m2[k]] : 0xFFu;
         }
       }
     }
@@ -321,26 +357,32 @@ __global__ void __launch_bounds__(256, 2) gn_apply_pool_kernel(const T* __restri
       if (pp < npool) {
         float best[8];
         uint32_t arg_lo = 0u, arg_hi = 0u;                 // window index (0..3) of the maximum, one byte per channel
+        const uint32_t os = q00[u] * p.out_cstride;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           float f[8];
           vec[u][k].to_float(f);
           apply8(f, cf, m1[u][k], relu);
+          if (ARGMAX) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            // ATen max_pool2d: first maximum in row-major window order wins (val > maxval || isnan(val))
-            if (k == 0 || f[i] > best[i] || f[i] != f[i]) {
-              best[i] = f[i];
-              if (k > 0) {
-                uint32_t& a = i < 4 ? arg_lo : arg_hi;
-                const int sh = 8 * (i & 3);
-                a = (a & ~(0xFFu << sh)) | (static_cast<uint32_t>(k) << sh);
+            for (int i = 0; i < 8; ++i) {
+              // ATen max_pool2d: first maximum in row-major window order wins (val > maxval || isnan(val))
+              if (k == 0 || f[i] > best[i] || f[i] != f[i]) {
+                best[i] = f[i];
+                if (k > 0) {
+                  uint32_t& a = i < 4 ? arg_lo : arg_hi;
+                  const int sh = 8 * (i & 3);
+                  a = (a & ~(0xFFu << sh)) | (static_cast<uint32_t>(k) << sh);
+                }
               }
             }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) best[i] = k == 0 ? f[i] : max_nan(best[i], f[i]);
           }
-          if (skip_out) {
+          if (has_skip) {
             float g[8];
-            if (mask2) {
+            if (has2) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) g[i] = ((m2[u][k] >> i) & 1u) ? f[i] * s2 : 0.f;
             } else {
@@ -350,7 +392,7 @@ __global__ void __launch_bounds__(256, 2) gn_apply_pool_kernel(const T* __restri
             round_for_storage<T>(g);
             Vec8<T> o;
             o.from_float(g);
-            o.store(skip_out + (pix00[u] + (k >> 1) * p.w + (k & 1)) * p.out_cstride + p.out_coffset + cv * 8);
+            o.store(sb + (os + tap_s[k]));
           }
         }
 #pragma unroll
@@ -358,13 +400,17 @@ __global__ void __launch_bounds__(256, 2) gn_apply_pool_kernel(const T* __restri
           s[i] += best[i];
           q[i] += best[i] * best[i];
         }
-        const long po = (static_cast<long>(n) * npool + pp) * p.c + cv * 8;
+        const uint32_t po = static_cast<uint32_t>(pp) * p.c;
         Vec8<T> o;
         o.from_float(best);
-        o.store(pooled + po);
-        if (argmax) {
-          *reinterpret_cast<uint2*>(argmax + po) = make_uint2(arg_lo, arg_hi);
-        }
+        o.store(pb + po);
+        if (ARGMAX) *reinterpret_cast<uint2*>(ab + po) = make_uint2(arg_lo, arg_hi);
+      }
+      py[u] += dq;
+      px[u] += dr;
+      if (px[u] >= pw) {
+        px[u] -= pw;
+        ++py[u];
       }
     }
   }
@@ -847,6 +893,11 @@ extern "C" int b2u_gn_apply_pool(const void* x, const float* coef, const uint32_
   B2U_REQUIRE(x && coef && pooled, "null pointer");
   B2U_REQUIRE(!mask2 || keep_counts2, "mask2 needs keep counts");
   B2U_REQUIRE(p.x_shared == 0, "b2u_gn_apply_pool does not support a shared input");
+  {
+    const long cmax = d->out_cstride > d->c ? d->out_cstride : d->c;
+    B2U_REQUIRE(static_cast<long>(d->h) * d->w * (cmax > d->mask2_cstride ? cmax : d->mask2_cstride) < (1l << 31),
+                "one image must stay below 2^31 elements (32-bit in-image offsets)");
+  }
   int rows = 0, sgs = 1;
   rc = b2u_pool_stat_layout(d->h, d->w, d->c, pool_num_groups > 0 ? pool_num_groups : 1, &rows, &sgs);
   if (rc) return rc;
@@ -856,15 +907,29 @@ extern "C" int b2u_gn_apply_pool(const void* x, const float* coef, const uint32_
   dim3 grid(rows, d->n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* parts = pool_num_groups > 0 ? pool_partials : nullptr;
-#define B2U_POOL_T(T)                                                                                               \
-  B2U_PDL_LAUNCH((gn_apply_pool_kernel<T>), grid, threads, smem, st, static_cast<const T*>(x),                          \
+  const int mode = (mask1 && mask2 && skip_out) ? 1 : (!mask1 && !mask2 && skip_out) ? 0 : 2;
+#define B2U_POOL_TAM(T, A, M)                                                                                       \
+  B2U_PDL_LAUNCH((gn_apply_pool_kernel<T, A, M>), grid, threads, smem, st, static_cast<const T*>(x),                    \
                  reinterpret_cast<const float2*>(coef), reinterpret_cast<const uint8_t*>(mask1),                        \
                  reinterpret_cast<const uint8_t*>(mask2), keep_counts2, static_cast<T*>(skip_out), static_cast<T*>(pooled), \
                  parts, argmax, sgs, p)
+#define B2U_POOL_TA(T, A)                                                                                           \
+  do {                                                                                                              \
+    if (mode == 1) B2U_POOL_TAM(T, A, 1);                                                                           \
+    else if (mode == 0) B2U_POOL_TAM(T, A, 0);                                                                      \
+    else B2U_POOL_TAM(T, A, 2);                                                                                     \
+  } while (0)
+#define B2U_POOL_T(T)                                                                                               \
+  do {                                                                                                              \
+    if (argmax) B2U_POOL_TA(T, true);                                                                               \
+    else B2U_POOL_TA(T, false);                                                                                     \
+  } while (0)
   if (d->dtype == B2U_F32) B2U_POOL_T(float);
   else if (d->dtype == B2U_F16) B2U_POOL_T(__half);
   else B2U_POOL_T(__nv_bfloat16);
 #undef B2U_POOL_T
+#undef B2U_POOL_TA
+#undef B2U_POOL_TAM
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
