@@ -79,7 +79,7 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* t_full = empty + S;                                // [2]
   uint64_t* t_empty = t_full + 2;                              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-  float* stat_scratch = reinterpret_cast<float*>(tmem_slot + 2);   // [4 lane quarters][256]
+  float* stat_scratch = reinterpret_cast<float*>(tmem_slot + 2);   // [2 epilogue groups][4 lane quarters][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,7 +89,7 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -154,16 +154,24 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncwarp();
   } else {
     // ===================== epilogue (warps 2..9) =====================
+    // Two independent groups of four warps (one warp per TMEM lane quarter): group g owns accumulator buffer g, i.e.
+    // every other item of this CTA, and all 256 of its columns.  The groups never synchronise with each other, so
+    // while one sits in its statistics barrier or waits for TMEM the other keeps the store pipe busy -- with all
+    // eight warps on the same item the epilogue was one latency chain of ~10k cycles per item next to 512 cycles
+    // of MMA (shallow levels: 2.4 TB/s of the HBM-write-bound 6.4).
     const int q = warp & 3;                                      // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;                            // which four chunks of the accumulator
+    const int grp = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int dh = row >> 3, dw = row & 7;
-    float* my_scratch = stat_scratch + q * 256;
-    const int et = threadIdx.x - 64;                             // 0..255
+    float* grp_scratch = stat_scratch + grp * 1024;              // [4 lane quarters][256]
+    float* my_scratch = grp_scratch + q * 256;
+    const int et = threadIdx.x - 64 - grp * 128;                 // 0..127 within the group
     const int out_w = 2 * p.w;
-    int buf = 0;
+    const int buf = grp;
     uint32_t pf = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    int li = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++li) {
+      if ((li & 1) != grp) continue;
       const int nt = item / p.total_tiles;
       const int tile = item - nt * p.total_tiles;
       const int img = tile / tiles_per_image;
@@ -173,11 +181,8 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const bool valid = hh < p.h && ww < p.w;
       mbar_wait(&t_full[buf], pf);
       tc_fence_after();
-#pragma unroll 1
-      for (int chunk = half * 4; chunk < half * 4 + 4; ++chunk) {
-        uint32_t rr[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kTBlockN + chunk * 32, rr);
-        tmem_ld_wait();
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kTBlockN;
+      auto process = [&](uint32_t (&rr)[32], int chunk) {
         float x[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(rr[i]);
@@ -198,24 +203,38 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           OutT* yrow = reinterpret_cast<OutT*>(p.y) + opix * p.cout + co0;
           store_chunk32<OutT>(yrow, x);
         }
+      };
+      // the TMEM load of chunk c+1 is in flight while chunk c is reduced and stored
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(tbase, ra);
+#pragma unroll 1
+      for (int chunk = 0; chunk < kTBlockN / 32; chunk += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32(tbase + (chunk + 1) * 32, rb);
+        process(ra, chunk);
+        tmem_ld_wait();
+        if (chunk + 2 < kTBlockN / 32) tmem_ld_32x32(tbase + (chunk + 2) * 32, ra);
+        process(rb, chunk + 1);
       }
       // the accumulator has been read: release it before the (shared-memory only) statistics reduction
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[buf]);
-      if (++buf == 2) { buf = 0; pf ^= 1; }
+      pf ^= 1;
       if (p.sgs_log2 >= 0) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");           // all quarter-tile partials are in smem
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // all quarter-tile partials of this group are in smem
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
         const int nslots = (kTBlockN * 2) >> p.sgs_log2;
         const int slots_per_row = (p.cout * 2) >> p.sgs_log2;
-        for (int e = et; e < nslots; e += 256) {
-          const float s = stat_scratch[e] + stat_scratch[256 + e] + stat_scratch[512 + e] + stat_scratch[768 + e];
+        for (int e = et; e < nslots; e += 128) {
+          const float s = grp_scratch[e] + grp_scratch[256 + e] + grp_scratch[512 + e] + grp_scratch[768 + e];
           const int gcol = nt * kTBlockN + ((e >> 1) << p.sgs_log2);
           const int tap = gcol / p.cout;
           const int cot = gcol - tap * p.cout;
           p.partials[((static_cast<size_t>(img) * tiles_per_image + r) * 4 + tap) * slots_per_row + ((cot >> p.sgs_log2) << 1) + (e & 1)] = s;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");           // scratch may be overwritten by the next item
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // scratch may be overwritten by this group's next item
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
       }
     }
   }
@@ -291,7 +310,7 @@ int convT_v2_run(const void* x, const void* wpacked, void* y, float* partials, c
   gp.sgs_log2 = sgs > 0 ? conv_ilog2(sgs) : -1;
   gp.y = y;
   gp.partials = partials;
-  const size_t smem = static_cast<size_t>(gp.stages) * (kTABytes + kTBBytes) + 1024 + (2 * gp.stages + 4) * 8 + 16 + 4 * 256 * 4;
+  const size_t smem = static_cast<size_t>(gp.stages) * (kTABytes + kTBBytes) + 1024 + (2 * gp.stages + 4) * 8 + 16 + 2 * 4 * 256 * 4;
   int grid = b2u_num_sms();
   if (grid > gp.num_items) grid = gp.num_items;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
