@@ -83,7 +83,10 @@ def test_rotate_matches_torchvision_restatement():
     assert max(D.sec_rotate()) < 5e-4
 
 
-@pytest.mark.parametrize("h,w,n", [(120, 116, 1), (120, 116, 3), (584, 565, 1)])
+# (146, 141) / (292, 283) / 128^2 / 256^2: the multi-fidelity sweep sizes of BASELINE configs[4] (MF-training-UNI.py:33-44),
+# batched 8 / 4 / 8 / 2 images per call
+@pytest.mark.parametrize("h,w,n", [(120, 116, 1), (120, 116, 3), (584, 565, 1), (146, 141, 8), (292, 283, 4), (128, 128, 8),
+                                   (256, 256, 2)])
 def test_forward_bf16_vs_oracle(h, w, n):
     r = D._forward_case(h, w, n, "bf16")
     assert r["out_rel"] < 1e-2 and r["logits_rel"] < 2.5e-2
@@ -121,6 +124,31 @@ def test_mc_dropblock_vs_oracle():
 def test_rotation_ensemble_vs_oracle():
     r = D.sec_rot_ens()
     assert r["samples"] < 1e-2 and r["mean"] < 5e-3 and r["std_maxabs"] < 1.5e-2
+
+
+def test_rotation_full_size_properties():
+    """BASELINE configs[3] at full size (584x565), 6 angles: statistics finite and in range, exactly zero outside the FOV,
+    reproducible, independent of the angle batch, and equal to the mean / unbiased std of the returned samples."""
+    import unet_research_b200 as U
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    m, _ = D._build_model(dev)
+    x = synthetic.make_image(584, 565, seed=1234).to(dev)
+    fov = synthetic.make_fov_mask(584, 565).to(dev)
+    outs = []
+    for ab in (3, 2, 3):
+        ev = U.RotationEval(m, num_iterations=6, return_num=6, angle_batch=ab)
+        _, (mean, std, tens) = ev.predict_step((x, None, fov), 0)
+        outs.append((mean, std, tens))
+    mean, std, tens = outs[0]
+    assert tuple(mean.shape) == (1, 1, 584, 565) and tuple(tens.shape) == (6, 1, 1, 584, 565)
+    assert torch.isfinite(mean).all() and torch.isfinite(std).all()
+    assert float(mean[fov == 0].abs().max()) == 0.0 and float(std[fov == 0].abs().max()) == 0.0
+    assert 0.0 <= float(mean.min()) and float(mean.max()) <= 1.0
+    assert torch.equal(outs[0][2], outs[2][2]) and torch.equal(outs[0][0], outs[2][0])     # reproducible
+    assert torch.equal(outs[0][2], outs[1][2])                                             # angle batch does not matter
+    torch.testing.assert_close(mean, tens.double().mean(0).float(), rtol=0, atol=1e-6)      # Rotational_Uncertainty.py:62-63
+    torch.testing.assert_close(std, tens.double().std(0).float(), rtol=0, atol=1e-5)
 
 
 def test_mc_full_size_properties():
