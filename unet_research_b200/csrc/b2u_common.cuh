@@ -186,6 +186,55 @@ __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_
 }
 // Arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
+// Warp-converged issue: the WHOLE warp executes these and the instruction itself is predicated on `leader` (one lane,
+// chosen once with elect_one()).  Issuing from inside `if (lane == 0)` makes the region divergent, and ptxas then wraps
+// every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall to move its operands into uniform registers:
+// ~9 dependent instructions = ~100 cycles per MMA, more than an M128 x N64 x K16 MMA takes on the tensor pipe.
+template <bool kTf32>
+__device__ __forceinline__ void umma_ss_conv(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate, uint32_t leader) {
+  if constexpr (kTf32) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 e, %5, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 e, %5, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+  }
+}
+// Four K steps (4 x 32 bytes along K: one 128-byte swizzle row) in ONE asm statement: the operands are moved to
+// uniform registers once and the descriptor advance stays in the uniform datapath.
+template <bool kTf32>
+__device__ __forceinline__ void umma_ss_conv4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate_first, uint32_t leader) {
+#define B2U_MMA4(KIND)                                                                                              \
+  asm volatile(                                                                                                     \
+      "{\n\t.reg .pred p, e, t;\n\t.reg .b64 a1, b1, a2, b2, a3, b3;\n\t"                                          \
+      "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 e, %5, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"                                \
+      "add.u64 a1, %1, 2;\n\tadd.u64 b1, %2, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 b2, %2, 4;\n\t"                 \
+      "add.u64 a3, %1, 6;\n\tadd.u64 b3, %2, 6;\n\t"                                                               \
+      "@e tcgen05.mma.cta_group::1.kind::" KIND " [%0], %1, %2, %3, p;\n\t"                                         \
+      "@e tcgen05.mma.cta_group::1.kind::" KIND " [%0], a1, b1, %3, t;\n\t"                                         \
+      "@e tcgen05.mma.cta_group::1.kind::" KIND " [%0], a2, b2, %3, t;\n\t"                                         \
+      "@e tcgen05.mma.cta_group::1.kind::" KIND " [%0], a3, b3, %3, t;\n\t}\n"                                     \
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(leader)                          \
+      : "memory")
+  if constexpr (kTf32) B2U_MMA4("tf32");
+  else B2U_MMA4("f16");
+#undef B2U_MMA4
+}
+__device__ __forceinline__ void umma_commit_conv(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %1, 0;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+      ::"r"(smem_u32(bar)), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");

@@ -166,7 +166,9 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // the whole warp runs the loop (converged control flow); one elected lane issues (see umma_ss_conv)
+    {
+      const uint32_t leader = elect_one() ? 1u : 0u;
       int sa = 0, sb = 0, buf = 0;
       uint32_t pa = 0, pb = 0, pt = 1;                           // pt: parity to wait on t_empty[buf]
       const uint64_t adesc0 = umma_desc_k_sw128_sbo(smem_u32(smA), 1280);
@@ -188,19 +190,17 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int t = 0; t < MT; ++t) {
               const uint64_t adesc = adesc_stage + static_cast<uint64_t>((t * kPatchStride + row_off * 128) >> 4);
-#pragma unroll
-              for (int k = 0; k < kKElems / kUmmaK; ++k) {
-                const uint32_t accumulate = (tap == 0 && k == 0) ? (kc != 0 ? 1u : 0u) : 1u;
-                umma_ss<kTf32>(acc0 + t * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, kIdesc, accumulate);
-              }
+              static_assert(kKElems / kUmmaK == 4, "one swizzle row = four K steps");
+              const uint32_t accumulate = tap == 0 ? (kc != 0 ? 1u : 0u) : 1u;
+              umma_ss_conv4<kTf32>(acc0 + t * BLOCK_N, adesc, bdesc, kIdesc, accumulate, leader);
             }
-            umma_commit(&b_empty[sb]);
+            umma_commit_conv(&b_empty[sb], leader);
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
-          umma_commit(&a_empty[sa]);
+          umma_commit_conv(&a_empty[sa], leader);
           if (++sa == SA) { sa = 0; pa ^= 1; }
         }
-        umma_commit(&t_full[buf]);
+        umma_commit_conv(&t_full[buf], leader);
         if (++buf == kNumBuf) { buf = 0; pt ^= 1; }
       }
     }

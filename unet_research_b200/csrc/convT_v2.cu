@@ -127,7 +127,9 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // the whole warp runs the loop (converged control flow); one elected lane issues (see umma_ss_conv)
+    {
+      const uint32_t leader = elect_one() ? 1u : 0u;
       int s = 0, buf = 0;
       uint32_t ph = 0, pt = 1;
       const uint64_t adesc0 = umma_desc_k_sw128(smem_u32(smA));
@@ -141,13 +143,12 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tc_fence_after();
           const uint64_t adesc = adesc0 + static_cast<uint64_t>((s * kTABytes) >> 4);
           const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((s * kTBBytes) >> 4);
-#pragma unroll
-          for (int k = 0; k < kKElems / kUmmaK; ++k)
-            umma_ss<kTf32>(acc, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kc | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[s]);
+          static_assert(kKElems / kUmmaK == 4, "one swizzle row = four K steps");
+          umma_ss_conv4<kTf32>(acc, adesc, bdesc, kIdesc, kc != 0 ? 1u : 0u, leader);
+          umma_commit_conv(&empty[s], leader);
           if (++s == S) { s = 0; ph ^= 1; }
         }
-        umma_commit(&t_full[buf]);
+        umma_commit_conv(&t_full[buf], leader);
         if (++buf == 2) { buf = 0; pt ^= 1; }
       }
     }

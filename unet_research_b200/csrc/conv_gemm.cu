@@ -150,7 +150,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // the whole warp runs the loop (converged control flow); one elected lane issues (see umma_ss_conv)
+    {
+      const uint32_t leader = elect_one() ? 1u : 0u;
       int s = 0;
       uint32_t ph = 0;
       const uint64_t adesc0 = umma_desc_k_sw128(smem_u32(smA));
@@ -160,15 +162,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint64_t adesc = adesc0 + static_cast<uint64_t>((s * kABytes) >> 4);
         const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((s * kBBytes) >> 4);
-#pragma unroll
-        for (int k = 0; k < kKElems / kUmmaK; ++k) {
-          // +32 bytes of K inside the 128-byte swizzle atom = +2 in the 16-byte address field
-          umma_ss<kTf32>(tmem_base, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&empty_bar[s]);           // frees the smem stage once these MMAs retire
+        // +32 bytes of K inside the 128-byte swizzle atom = +2 in the 16-byte address field (four steps per stage)
+        static_assert(kKElems / kUmmaK == 4, "one swizzle row = four K steps");
+        umma_ss_conv4<kTf32>(tmem_base, adesc, bdesc, kIdesc, kb != 0 ? 1u : 0u, leader);
+        umma_commit_conv(&empty_bar[s], leader);           // frees the smem stage once these MMAs retire
         if (++s == stages) { s = 0; ph ^= 1; }
       }
-      umma_commit(tmem_full_bar);             // accumulator complete
+      umma_commit_conv(tmem_full_bar, leader);             // accumulator complete
     }
     __syncwarp();
   } else {
