@@ -207,27 +207,40 @@ __device__ __forceinline__ void umma_ss_conv(uint32_t tmem_d, uint64_t adesc, ui
         : "memory");
   }
 }
-// Four K steps (4 x 32 bytes along K: one 128-byte swizzle row) in ONE asm statement: the operands are moved to
-// uniform registers once and the descriptor advance stays in the uniform datapath.
+// Four K steps (4 x 32 bytes along K: one 128-byte swizzle row) in ONE asm statement.  Only the low word of a shared
+// memory descriptor moves (start address, 16-byte units); the high words are per-kernel constants, so the advance is a
+// 32-bit add and ptxas needs one register -> uniform-register move per descriptor instead of two per MMA.
 template <bool kTf32>
-__device__ __forceinline__ void umma_ss_conv4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                              uint32_t accumulate_first, uint32_t leader) {
+__device__ __forceinline__ void umma_ss_conv4(uint32_t tmem_d, uint32_t adesc_lo, uint32_t adesc_hi, uint32_t bdesc_lo,
+                                              uint32_t bdesc_hi, uint32_t idesc, uint32_t accumulate_first, uint32_t leader) {
 #define B2U_MMA4(KIND)                                                                                              \
   asm volatile(                                                                                                     \
-      "{\n\t.reg .pred p, e, t;\n\t.reg .b64 a1, b1, a2, b2, a3, b3;\n\t"                                          \
+      "{\n\t.reg .pred p, e, t;\n\t.reg .b32 x, y;\n\t.reg .b64 a, b;\n\t"                                        \
       "setp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 e, %5, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"                                \
-      "add.u64 a1, %1, 2;\n\tadd.u64 b1, %2, 2;\n\tadd.u64 a2, %1, 4;\n\tadd.u64 b2, %2, 4;\n\t"                 \
-      "add.u64 a3, %1, 6;\n\tadd.u64 b3, %2, 6;\n\t"                                                               \
-      "@e tcgen05.mma.cta_group::1.kind::" KIND " [%0], %1, %2, %3, p;\n\t"                                         \
-      "@e tcgen05.mma.cta_group::1.kind::" KIND " [%0], a1, b1, %3, t;\n\t"                                         \
-      "@e tcgen05.mma.cta_group::1.kind::" KIND " [%0], a2, b2, %3, t;\n\t"                                         \
-      "@e tcgen05.mma.cta_group::1.kind::" KIND " [%0], a3, b3, %3, t;\n\t}\n"                                     \
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(leader)                          \
+      "mov.b64 a, {%1, %6};\n\tmov.b64 b, {%2, %7};\n\t"                                                          \
+      "@e tcgen05.mma.cta_group::1.kind::" KIND " [%0], a, b, %3, p;\n\t"                                           \
+      "add.u32 x, %1, 2;\n\tadd.u32 y, %2, 2;\n\tmov.b64 a, {x, %6};\n\tmov.b64 b, {y, %7};\n\t"                 \
+      "@e tcgen05.mma.cta_group::1.kind::" KIND " [%0], a, b, %3, t;\n\t"                                           \
+      "add.u32 x, %1, 4;\n\tadd.u32 y, %2, 4;\n\tmov.b64 a, {x, %6};\n\tmov.b64 b, {y, %7};\n\t"                 \
+      "@e tcgen05.mma.cta_group::1.kind::" KIND " [%0], a, b, %3, t;\n\t"                                           \
+      "add.u32 x, %1, 6;\n\tadd.u32 y, %2, 6;\n\tmov.b64 a, {x, %6};\n\tmov.b64 b, {y, %7};\n\t"                 \
+      "@e tcgen05.mma.cta_group::1.kind::" KIND " [%0], a, b, %3, t;\n\t}\n"                                       \
+      ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accumulate_first), "r"(leader), "r"(adesc_hi),    \
+        "r"(bdesc_hi)                                                                                               \
       : "memory")
   if constexpr (kTf32) B2U_MMA4("tf32");
   else B2U_MMA4("f16");
 #undef B2U_MMA4
 }
+template <bool kTf32>
+__device__ __forceinline__ void umma_ss_conv4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate_first, uint32_t leader) {
+  umma_ss_conv4<kTf32>(tmem_d, static_cast<uint32_t>(adesc), static_cast<uint32_t>(adesc >> 32), static_cast<uint32_t>(bdesc),
+                       static_cast<uint32_t>(bdesc >> 32), idesc, accumulate_first, leader);
+}
+// TMEM base address as a value ptxas can prove warp-uniform (it is read from shared memory, i.e. per thread): without
+// this every tcgen05.mma gets its own predicated R2UR.BROADCAST of the accumulator address.
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ void umma_commit_conv(uint64_t* bar, uint32_t leader) {
   asm volatile(
       "{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %1, 0;\n\t"

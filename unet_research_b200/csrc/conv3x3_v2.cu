@@ -173,26 +173,30 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t pa = 0, pb = 0, pt = 1;                           // pt: parity to wait on t_empty[buf]
       const uint64_t adesc0 = umma_desc_k_sw128_sbo(smem_u32(smA), 1280);
       const uint64_t bdesc0 = umma_desc_k_sw128(smem_u32(smB));
+      // only the low descriptor word (start address in 16-byte units) changes between MMAs
+      const uint32_t a_lo0 = static_cast<uint32_t>(adesc0), a_hi = static_cast<uint32_t>(adesc0 >> 32);
+      const uint32_t b_lo0 = static_cast<uint32_t>(bdesc0), b_hi = static_cast<uint32_t>(bdesc0 >> 32);
+      const uint32_t tmem_u = warp_uniform(tmem_base);
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         mbar_wait(&t_empty[buf], pt);                            // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t acc0 = tmem_base + buf * kAccCols;
+        const uint32_t acc0 = tmem_u + buf * kAccCols;
         for (int kc = 0; kc < p.kc_chunks; ++kc) {
           mbar_wait(&a_full[sa], pa);
-          const uint64_t adesc_stage = adesc0 + static_cast<uint64_t>((sa * MT * kPatchStride) >> 4);
+          const uint32_t a_stage = a_lo0 + static_cast<uint32_t>((sa * MT * kPatchStride) >> 4);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(&b_full[sb], pb);
             tc_fence_after();
-            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((sb * kBBytes) >> 4);
+            const uint32_t b_lo = b_lo0 + static_cast<uint32_t>((sb * kBBytes) >> 4);
             constexpr int kRowsPerGroup = 10;
             const int row_off = (tap / 3) * kRowsPerGroup + (tap % 3);     // compile-time: shifted view of the patch
 #pragma unroll
             for (int t = 0; t < MT; ++t) {
-              const uint64_t adesc = adesc_stage + static_cast<uint64_t>((t * kPatchStride + row_off * 128) >> 4);
+              const uint32_t a_lo = a_stage + static_cast<uint32_t>((t * kPatchStride + row_off * 128) >> 4);
               static_assert(kKElems / kUmmaK == 4, "one swizzle row = four K steps");
               const uint32_t accumulate = tap == 0 ? (kc != 0 ? 1u : 0u) : 1u;
-              umma_ss_conv4<kTf32>(acc0 + t * BLOCK_N, adesc, bdesc, kIdesc, accumulate, leader);
+              umma_ss_conv4<kTf32>(acc0 + t * BLOCK_N, a_lo, a_hi, b_lo, b_hi, kIdesc, accumulate, leader);
             }
             umma_commit_conv(&b_empty[sb], leader);
             if (++sb == SB) { sb = 0; pb ^= 1; }

@@ -130,6 +130,7 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // the whole warp runs the loop (converged control flow); one elected lane issues (see umma_ss_conv)
     {
       const uint32_t leader = elect_one() ? 1u : 0u;
+      const uint32_t tmem_u = warp_uniform(tmem_base);
       int s = 0, buf = 0;
       uint32_t ph = 0, pt = 1;
       const uint64_t adesc0 = umma_desc_k_sw128(smem_u32(smA));
@@ -137,7 +138,7 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         mbar_wait(&t_empty[buf], pt);
         tc_fence_after();
-        const uint32_t acc = tmem_base + buf * kTBlockN;
+        const uint32_t acc = tmem_u + buf * kTBlockN;
         for (int kc = 0; kc < p.kc_chunks; ++kc) {
           mbar_wait(&full[s], ph);
           tc_fence_after();

@@ -153,6 +153,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // the whole warp runs the loop (converged control flow); one elected lane issues (see umma_ss_conv)
     {
       const uint32_t leader = elect_one() ? 1u : 0u;
+      const uint32_t tmem_u = warp_uniform(tmem_base);
       int s = 0;
       uint32_t ph = 0;
       const uint64_t adesc0 = umma_desc_k_sw128(smem_u32(smA));
@@ -164,7 +165,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((s * kBBytes) >> 4);
         // +32 bytes of K inside the 128-byte swizzle atom = +2 in the 16-byte address field (four steps per stage)
         static_assert(kKElems / kUmmaK == 4, "one swizzle row = four K steps");
-        umma_ss_conv4<kTf32>(tmem_base, adesc, bdesc, kIdesc, kb != 0 ? 1u : 0u, leader);
+        umma_ss_conv4<kTf32>(tmem_u, adesc, bdesc, kIdesc, kb != 0 ? 1u : 0u, leader);
         umma_commit_conv(&empty_bar[s], leader);           // frees the smem stage once these MMAs retire
         if (++s == stages) { s = 0; ph ^= 1; }
       }

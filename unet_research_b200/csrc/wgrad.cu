@@ -110,6 +110,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
     // the whole warp runs the loop (converged control flow); one elected lane issues (see umma_ss_conv)
     {
       const uint32_t leader = elect_one() ? 1u : 0u;
+      const uint32_t tmem_u = warp_uniform(tmem_base);
       int s = 0;
       uint32_t ph = 0;
       bool first = true;
@@ -126,7 +127,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
             const uint64_t adesc = umma_desc_mn_sw128(g_addr + ks * 2048, 128 * 128, 1024);
             const uint64_t bdesc = TAPS == 9 ? umma_desc_mn_sw128(x_addr + (row_off + ks * 20) * 128, 128 * 128, 1280)
                                              : umma_desc_mn_sw128(x_addr + ks * 2048, 128 * 128, 1024);
-            umma_ss_conv<false>(tmem_base + t * 64, adesc, bdesc, kIdesc, (first && ks == 0) ? 0u : 1u, leader);
+            umma_ss_conv<false>(tmem_u + t * 64, adesc, bdesc, kIdesc, (first && ks == 0) ? 0u : 1u, leader);
           }
         }
         first = false;
