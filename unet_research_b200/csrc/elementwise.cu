@@ -226,9 +226,13 @@ __device__ __forceinline__ void apply8(float (&f)[8], const Coef8& cf, uint32_t 
 }
 
 // grid = (blocks per image, n); thread t owns channel vector t % cvs (coefficients live in registers) and
-// streams kApplyUnroll pixels per trip with all loads issued before the first use.
+// streams kApplyUnroll pixels per trip with all loads issued before the first use.  Specialised by mask presence
+// (M1 = this unit's DropBlock mask, M2 = the concat-site mask); per-image base pointers with the channel slice folded in
+// and 32-bit in-image offsets (the launcher checks h*w*max(c, out_cstride, mask2_cstride) < 2^31) keep the index
+// arithmetic to a handful of instructions per vector -- the kernel shares the SM with the mask build, so every issue
+// slot it does not need is one the Philox warps get.
 constexpr int kApplyUnroll = 4;
-template <typename T>
+template <typename T, bool M1, bool M2>
 __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const T* __restrict__ x, const float2* __restrict__ coef, const uint8_t* __restrict__ mask1,
                                 const uint8_t* __restrict__ mask2, const unsigned long long* __restrict__ keep2,
                                 T* __restrict__ out, ApplyParams p) {
@@ -239,45 +243,46 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const T* __restrict__ 
   const int cv = threadIdx.x % cvs;
   const int slot = threadIdx.x / cvs;
   const int slots = blockDim.x / cvs;
-  const long hw = static_cast<long>(p.h) * p.w;
+  const int hw = p.h * p.w;
   Coef8 cf;
   cf.load(coef + static_cast<size_t>(n) * p.c + cv * 8);
   float s2 = 1.f;
-  if (mask2) s2 = static_cast<float>(p.numel_per_call2 / static_cast<double>(keep2[n / p.images_per_call2]));
+  if (M2) s2 = static_cast<float>(p.numel_per_call2 / static_cast<double>(keep2[n / p.images_per_call2]));
   const bool relu = p.relu != 0;
-  const long img0 = static_cast<long>(n) * hw;
-  const long xoff = p.x_shared ? -img0 : 0;               // input pixel index = pix + xoff
+  const size_t img0 = static_cast<size_t>(n) * hw;
   const int m2s = p.mask2_cstride >> 3, m2o = (p.mask2_coffset >> 3) + cv;
-  const long stride = static_cast<long>(gridDim.x) * slots * kApplyUnroll;
-  for (long base = static_cast<long>(blockIdx.x) * slots * kApplyUnroll + slot; base < hw; base += stride) {
+  const T* const xb = x + (p.x_shared ? 0 : img0 * p.c) + cv * 8;
+  const uint8_t* const m1b = M1 ? mask1 + img0 * cvs + cv : nullptr;
+  const uint8_t* const m2b = M2 ? mask2 + img0 * m2s + m2o : nullptr;
+  T* const ob = out + img0 * p.out_cstride + p.out_coffset + cv * 8;
+  const int stride = gridDim.x * slots * kApplyUnroll;
+  for (int base = blockIdx.x * slots * kApplyUnroll + slot; base < hw; base += stride) {
     Vec8<T> vec[kApplyUnroll];
     uint32_t m1[kApplyUnroll], m2[kApplyUnroll];
 #pragma unroll
     for (int u = 0; u < kApplyUnroll; ++u) {
-      const long pl = base + static_cast<long>(u) * slots;
+      const int pl = base + u * slots;
       if (pl < hw) {
-        const long pix = img0 + pl;
-        vec[u].load(x + (pix + xoff) * p.c + cv * 8);
-        m1[u] = mask1 ? mask1[pix * cvs + cv] : 0xFFu;
-        m2[u] = mask2 ? mask2[pix * m2s + m2o] : 0xFFu;
+        vec[u].load(xb + static_cast<uint32_t>(pl) * static_cast<uint32_t>(p.c));
+        m1[u] = M1 ? m1b[static_cast<uint32_t>(pl) * static_cast<uint32_t>(cvs)] : 0xFFu;
+        m2[u] = M2 ? m2b[static_cast<uint32_t>(pl) * static_cast<uint32_t>(m2s)] : 0xFFu;
       }
     }
 #pragma unroll
     for (int u = 0; u < kApplyUnroll; ++u) {
-      const long pl = base + static_cast<long>(u) * slots;
+      const int pl = base + u * slots;
       if (pl < hw) {
-        const long pix = img0 + pl;
         float f[8];
         vec[u].to_float(f);
         apply8(f, cf, m1[u], relu);
-        if (mask2) {
+        if (M2) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = ((m2[u] >> i) & 1u) ? f[i] * s2 : 0.f;
         }
         round_for_storage<T>(f);
         Vec8<T> o;
         o.from_float(f);
-        o.store(out + pix * p.out_cstride + p.out_coffset + cv * 8);
+        o.store(ob + static_cast<uint32_t>(pl) * static_cast<uint32_t>(p.out_cstride));
       }
     }
   }
@@ -867,6 +872,11 @@ extern "C" int b2u_gn_apply(const void* x, const float* coef, const uint32_t* ma
   B2U_REQUIRE(x && coef && out, "null pointer");
   B2U_REQUIRE(!mask2 || (keep_counts2 && d->mask2_cstride % 8 == 0 && d->mask2_coffset % 8 == 0), "mask2 needs keep counts and 8-aligned channel layout");
   B2U_REQUIRE(d->c / 8 <= 256, "at most 2048 channels");
+  {
+    long cmax = d->out_cstride > d->c ? d->out_cstride : d->c;
+    if (mask2 && d->mask2_cstride > cmax) cmax = d->mask2_cstride;
+    B2U_REQUIRE(static_cast<long>(d->h) * d->w * cmax < (1l << 31), "one image must stay below 2^31 elements (32-bit in-image offsets)");
+  }
   const int threads = pick_threads(d->c / 8);
   const int slots = threads / (d->c / 8);
   const long hw = static_cast<long>(d->h) * d->w;
@@ -876,13 +886,21 @@ extern "C" int b2u_gn_apply(const void* x, const float* coef, const uint32_t* ma
   if (bpi < 1) bpi = 1;
   dim3 grid(static_cast<unsigned>(bpi), d->n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define B2U_APPLY_T(T)                                                                                              \
-  B2U_PDL_LAUNCH((gn_apply_kernel<T>), grid, threads, 0, st, static_cast<const T*>(x), reinterpret_cast<const float2*>(coef), \
+#define B2U_APPLY_TM(T, A, B)                                                                                       \
+  B2U_PDL_LAUNCH((gn_apply_kernel<T, A, B>), grid, threads, 0, st, static_cast<const T*>(x), reinterpret_cast<const float2*>(coef), \
                  reinterpret_cast<const uint8_t*>(mask1), reinterpret_cast<const uint8_t*>(mask2), keep_counts2,        \
                  static_cast<T*>(out), p)
+#define B2U_APPLY_T(T)                                                                                              \
+  do {                                                                                                              \
+    if (mask1 && mask2) B2U_APPLY_TM(T, true, true);                                                                \
+    else if (mask1) B2U_APPLY_TM(T, true, false);                                                                   \
+    else if (mask2) B2U_APPLY_TM(T, false, true);                                                                   \
+    else B2U_APPLY_TM(T, false, false);                                                                             \
+  } while (0)
   if (d->dtype == B2U_F32) B2U_APPLY_T(float);
   else if (d->dtype == B2U_F16) B2U_APPLY_T(__half);
   else B2U_APPLY_T(__nv_bfloat16);
+#undef B2U_APPLY_TM
 #undef B2U_APPLY_T
   B2U_LAUNCH_CHECK();
   return B2U_OK;
