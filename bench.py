@@ -305,8 +305,9 @@ def run_gpu(args):
         e2e = {"value": reps * T_e2e / float(tt.item()), "unit": UNIT,
                "h2d_bytes_per_step": im_h.numel() * 4 + fov_h.numel() * 4,
                "d2h_bytes_per_step": sum(o.numel() * 4 for o in outs_h),
-               "step": f"DropBlockEval.predict_step, {T_e2e} iterations per call (sharded over ranks), pinned host in/out",
-               "mc_1000_iter_projected_s": 1000.0 / (reps * T_e2e / float(tt.item()))}
+               "step": f"one DropBlockEval.predict_step call = {T_e2e} iterations (BASELINE configs[2] iter_num; sharded over ranks), pinned host in/out, bytes per call",
+               "mc_1000_iter_projected_s": 1000.0 / (reps * T_e2e / float(tt.item())),
+               "seconds_per_call": float(tt.item()) / reps}
 
     train = None
     if not args.no_train:
@@ -509,7 +510,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--iter-batch", type=int, default=10)
-    ap.add_argument("--e2e-iters", type=int, default=100)
+    ap.add_argument("--e2e-iters", type=int, default=1000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-train", action="store_true")
