@@ -552,22 +552,31 @@ def sec_dropblock():
     dev = torch.device("cuda")
     res = []
     # (a) does torch compare `rand < gamma` in fp32?  (b) bit-exact masks vs the oracle using torch.rand on this GPU
-    for shape in ((1, 64, 128, 128), (2, 32, 37, 36), (1, 64, 592, 576), (1, 1024, 37, 36), (3, 96, 9, 50)):
-        x = torch.randn(*shape, device=dev)
+    # the last case starts the generator just below a multiple of 2^34: the low word of the Philox counter (offset / 4)
+    # wraps inside the call, which takes the centre kernel's plain loop instead of its split-round fast path
+    cases = [((1, 64, 128, 128), None), ((2, 32, 37, 36), None), ((1, 64, 592, 576), None), ((1, 1024, 37, 36), None),
+             ((3, 96, 9, 50), None), ((1, 64, 592, 576), 2 ** 34 - 8)]
+
+    def reseed(start):
         torch.manual_seed(1234)
-        _ = torch.rand(7, device=dev)                 # move the offset off zero
+        if start is None:
+            _ = torch.rand(7, device=dev)             # move the offset off zero
+        else:
+            torch.cuda.default_generators[0].set_offset(start)
+
+    for shape, start in cases:
+        x = torch.randn(*shape, device=dev)
+        reseed(start)
         rec = []
         ref = O.dropblock2d(x, 0.15, 7, True, record=rec)
         off_ref = torch.cuda.default_generators[0].get_offset()
-        torch.manual_seed(1234)
-        _ = torch.rand(7, device=dev)
+        reseed(start)
         db = DropBlock2D(0.15, 7)
         db.train()
         m, keep = db.block_mask(x)
         off_got = torch.cuda.default_generators[0].get_offset()
         mism = int((m != rec[0]).sum())
-        torch.manual_seed(1234)
-        _ = torch.rand(7, device=dev)
+        reseed(start)
         got = db(x)
         r, mx = rel(got, ref)
         print(f"  dropblock {shape}: mask mismatches {mism} / {m.numel()}  keep {int(keep)} vs {int(rec[0].sum())}  offset {off_got} vs {off_ref}  out rel {r:.2e}")

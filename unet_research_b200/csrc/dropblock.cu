@@ -26,10 +26,14 @@ __device__ __forceinline__ void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, ui
 #endif
 }
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+// rounds R0 .. 9 of Philox4x32-10; k0 / k1 are the ORIGINAL key words (round r uses key + r * Weyl constant)
+template <int R0>
+__device__ __forceinline__ void philox_rounds(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t (&out)[4]) {
+  k0 += static_cast<uint32_t>(R0) * 0x9E3779B9u;
+  k1 += static_cast<uint32_t>(R0) * 0xBB67AE85u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = R0; r < 10; ++r) {
     uint32_t h0, l0, h1, l1;
     mulhilo(0xD2511F53u, c0, h0, l0);
     mulhilo(0xCD9E8D57u, c2, h1, l1);
@@ -43,6 +47,10 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     k1 += 0xBB67AE85u;
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+  philox_rounds<0>(c0, c1, c2, c3, k0, k1, out);
 }
 
 // grid = (SMs * 8, n_calls) blocks of 256 threads: block b of call k, thread t IS torch's thread idx = 256*b + t for
@@ -75,6 +83,44 @@ __global__ void __launch_bounds__(256) dropblock_centers_kernel(const b2u_dropbl
   uint32_t* wp = center_bits + c.center_word_off + (first >> 5);
   const uint32_t wstep = tn >> 3;                              // words per trip (4 tn bits)
   const bool is1 = lane == 1u, is2 = lane == 2u, is3 = lane == 3u;
+  // The counter is (offset/4 + trip, idx): its first word is the same for EVERY thread of the call and its second word is
+  // fixed per thread, so the first two rounds split into a part that depends only on the trip (computed once per block
+  // into shared memory: 3 words per trip) and a part that depends only on the thread (hoisted out of the trip loop).
+  // Per trip that leaves 16 of the 20 wide multiplies -- the pipe the kernel is bound by.  Needs the low counter word
+  // not to wrap inside the call (otherwise, and for more than kMaxFastTrips trips, the plain loop below runs).
+  constexpr int kMaxFastTrips = 64;
+  __shared__ uint4 trip_u[kMaxFastTrips];
+  const uint32_t ctr_lo = static_cast<uint32_t>(ctr_base), ctr_hi = static_cast<uint32_t>(ctr_base >> 32);
+  const bool fast = trips <= static_cast<uint32_t>(kMaxFastTrips) && ctr_lo + (trips - 1u) >= ctr_lo;   // uniform per block
+  if (fast) {
+    if (threadIdx.x < trips) {
+      uint32_t h0, l0, h1, l1;
+      mulhilo(0xD2511F53u, ctr_lo + threadIdx.x, h0, l0);                 // round 1, counter word 0
+      const uint32_t c2p = h0 ^ k1;                                       // (c3 = 0)
+      mulhilo(0xCD9E8D57u, c2p, h1, l1);                                  // round 2, the trip-only product
+      trip_u[threadIdx.x] = make_uint4(h1 ^ (k0 + 0x9E3779B9u), l1, l0 ^ (k1 + 0xBB67AE85u), 0u);
+    }
+    __syncthreads();
+    uint32_t hi_i, lo_i, h0p, l0p;
+    mulhilo(0xCD9E8D57u, idx, hi_i, lo_i);                               // round 1, counter word 2 = idx
+    mulhilo(0xD2511F53u, hi_i ^ ctr_hi ^ k0, h0p, l0p);                  // round 2, the thread-only product
+#pragma unroll 1
+    for (uint32_t trip = 0; trip < trips; ++trip) {
+      const uint4 u = trip_u[trip];
+      uint32_t r[4];
+      philox_rounds<2>(u.x ^ lo_i, u.y, h0p ^ u.z, l0p, k0, k1, r);      // state after round 2, rounds 3..10 follow
+      uint32_t words[4];
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) words[ii] = __ballot_sync(0xffffffffu, r[ii] < lo_t || r[ii] >= hi_t);
+      uint32_t wsel = words[0];
+      wsel = is1 ? words[1] : wsel;
+      wsel = is2 ? words[2] : wsel;
+      wsel = is3 ? words[3] : wsel;
+      if (trip < my_trips) *wp = wsel;
+      wp += wstep;
+    }
+    return;
+  }
 #pragma unroll 1
   for (uint32_t trip = 0; trip < trips; ++trip) {
     const uint64_t ctr = ctr_base + trip;
