@@ -778,6 +778,72 @@ def sec_precision():
     return res
 
 
+def sec_libbar():
+    """The "library bar" of SURVEY 8(d): the reference algorithm (oracle = torch ops, cuDNN convs) on THIS GPU, timed for the
+    same workloads as bench.py: one MC-DropBlock forward of the 584x565 image (batch 1 and batch 10, fp32 with TF32 and
+    bf16 autocast) and one training step (fwd + bwd, bf16 autocast).  A diagnostic, not part of bench.py."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import unet_oracle as O
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    h, w = 584, 565
+    sd = {k: v.to(dev) for k, v in synthetic.make_state_dict(seed=1234).items()}
+    db = O.DropBlockCfg(0.15, 7, True)
+    torch.backends.cudnn.benchmark = True
+    out = {}
+
+    def timeit(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    for nb in (1, 10):
+        x = synthetic.make_image(h, w, seed=1234).to(dev).expand(nb, -1, -1, -1).contiguous()
+        for name, tf32, ac in (("fp32 + TF32 convs", True, None), ("bf16 autocast", False, torch.bfloat16)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+
+            def fwd():
+                with torch.no_grad():
+                    if ac is None:
+                        return O.unet_forward(sd, x, dropblock=db)
+                    with torch.autocast("cuda", dtype=ac):
+                        return O.unet_forward(sd, x, dropblock=db)
+
+            ms = timeit(fwd, 5)
+            out[f"mc forward batch {nb}, {name}"] = nb / ms * 1e3
+            print(f"  torch/cuDNN MC-DropBlock forward, batch {nb:2d}, {name:18s}: {ms:8.2f} ms = {nb / ms * 1e3:7.1f} passes/s", flush=True)
+    # training step
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    x = synthetic.make_image(h, w, seed=1234).to(dev)
+    gt = synthetic.make_gt(h, w).to(dev)
+    fov = synthetic.make_fov_mask(h, w).to(dev)
+
+    def step():
+        for p_ in params.values():
+            p_.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            seg = O.unet_forward(params, x, dropblock=db)
+        loss = F.binary_cross_entropy((seg.float() * fov).clamp(0, 1), gt * fov) * (fov.numel() / fov.sum())
+        loss.backward()
+
+    ms = timeit(step, 5)
+    out["train step bf16 autocast"] = 1e3 / ms
+    print(f"  torch/cuDNN train step (fwd + bwd, bf16 autocast, batch 1): {ms:8.2f} ms = {1e3 / ms:6.1f} imgs/s", flush=True)
+    torch.backends.cudnn.benchmark = False
+    return out
+
+
 def sec_forward():
     _forward_case(120, 116, 1, "bf16")
     _forward_case(120, 116, 3, "bf16")
