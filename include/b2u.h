@@ -263,6 +263,8 @@ int b2u_wgrad(const void* g, const void* x, float* workspace, float* dw, const b
 /* first layer (Cin 1 or 3): dW[co][ci][3][3] = sum_p g[p][co] * x_nchw[p + tap][ci], direct kernel on the fp32 input */
 int b2u_wgrad_first(const void* g, const float* x_nchw, float* workspace, float* dw, int n, int cin, int h0, int w0, int h,
                     int w, int cout, int dtype, void* stream);
+/* partial rows per image of b2u_wgrad_first: workspace = float[n][rows][cout][cin*9] */
+int b2u_wgrad_first_rows(void);
 /* plain 1x1 GEMM y[p][co] = sum_k x[p][k] * w[co][k] on the tcgen05 path (data gradient of the transposed conv:
  * x = dY in space-to-depth layout with k = 4*Cout, w packed [1][cin][4*Cout]) */
 int b2u_gemm1x1_fwd(const void* x, const void* wpacked, void* y, const b2u_conv_desc* d, void* stream);

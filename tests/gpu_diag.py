@@ -382,7 +382,7 @@ def sec_bwdk():
         n, h0, w0, hh, ww, co = 2, 29, 45, 32, 48, 64
         xin = torch.rand(n, cin, h0, w0, generator=gen).to(dev)
         g = torch.randn(n, hh, ww, co, generator=gen).to(dev).to(torch.bfloat16)
-        wsb = torch.empty(n * 64 * co * cin * 9, device=dev)
+        wsb = torch.empty(n * _lib.load().b2u_wgrad_first_rows() * co * cin * 9, device=dev)
         dw = torch.empty(co, cin, 3, 3, device=dev)
         call("b2u_wgrad_first", ptr(g), ptr(xin), ptr(wsb), ptr(dw), n, cin, h0, w0, hh, ww, co, _lib.BF16, stream_ptr())
         torch.cuda.synchronize()

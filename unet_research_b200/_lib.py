@@ -87,6 +87,7 @@ SIGNATURES = {
     "b2u_wgrad_workspace_floats": (_I, [C.POINTER(WgradDesc), C.POINTER(_LL)]),
     "b2u_wgrad": (_I, [_P, _P, _P, _P, C.POINTER(WgradDesc), _P]),
     "b2u_wgrad_first": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "b2u_wgrad_first_rows": (_I, []),
     "b2u_gemm1x1_fwd": (_I, [_P, _P, _P, C.POINTER(ConvDesc), _P]),
     "b2u_pack_convT2x2_dgrad_weight": (_I, [_P, _P, _I, _I, _I, _P]),
     "b2u_gn_apply": (_I, [_P, _P, _P, _P, _P, _P, C.POINTER(ApplyDesc), _P]),

@@ -53,7 +53,7 @@ class TrainBuffers:
         self.gcoef = torch.empty(n * eng.num_groups * 2, dtype=torch.float32, device=dev)
         self.wg_ws: Optional[torch.Tensor] = None
         self.reducer: Optional["GradReducer"] = None
-        self.first_ws = torch.empty(n * 64 * f * eng.init_channels * 9, dtype=torch.float32, device=dev)
+        self.first_ws = torch.empty(n * _lib.load().b2u_wgrad_first_rows() * f * eng.init_channels * 9, dtype=torch.float32, device=dev)
         self.flat: Optional[torch.Tensor] = None        # all parameter gradients in ONE fp32 buffer (named_parameters order)
         self.gviews: Dict[str, torch.Tensor] = {}
         self.goffsets: Dict[str, int] = {}
