@@ -177,6 +177,29 @@ def test_mc_full_size_properties():
     torch.testing.assert_close(outs[0][0], outs[1][0], rtol=0, atol=1e-6)
 
 
+def test_mc_remainder_batch_matches_single_batch():
+    """T not divisible by the iteration batch (what each rank sees at 8 GPUs: 125 = 12 x 10 + 5): the remainder runs through
+    a second runner with a smaller batch and is folded into the same accumulators; every iteration still sees the masks
+    of its global index."""
+    import unet_research_b200 as U
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    m, _ = D._build_model(dev, dropblock=True)
+    x = synthetic.make_image(120, 116, seed=1234).to(dev)
+    fov = synthetic.make_fov_mask(120, 116).to(dev)
+    outs = []
+    for ib in (5, 13, 4):                                # 2 x 5 + 3, one batch of 13, 3 x 4 + 1
+        ev = U.DropBlockEval(m, num_iterations=13, return_num=13, iter_batch=ib)
+        torch.manual_seed(7)
+        _, (mean, std, tens) = ev.predict_step((x, None, fov), 0)
+        outs.append((mean, std, tens, torch.cuda.default_generators[0].get_offset()))
+    for o in outs[1:]:
+        assert torch.equal(o[2], outs[0][2])             # all 13 samples identical
+        torch.testing.assert_close(o[0], outs[0][0], rtol=0, atol=1e-6)
+        torch.testing.assert_close(o[1], outs[0][1], rtol=0, atol=1e-6)
+        assert o[3] == outs[0][3]                        # generator left at the same offset
+
+
 def test_backward_kernels_vs_autograd():
     """Every backward kernel alone against torch autograd in fp64 on the same rounded operands: the tcgen05
     weight-gradient GEMM is exact up to fp32 accumulation order, the fused unit backward up to bf16 output rounding."""
