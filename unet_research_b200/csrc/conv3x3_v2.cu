@@ -32,6 +32,7 @@ struct ConvV2Params {
   int cout;
   int sa, sb;                 // pipeline depths of the patch ring and the weight ring
   int sgs_log2;               // statistics sub-group size (log2), -1 = none
+  int resident_b;             // 1: the whole filter (9 * kc_chunks stages, one N tile) stays in shared memory for the CTA's lifetime
   void* y;
   float* partials;            // [n][tiles_per_image][cout/sgs][2]
 };
@@ -152,6 +153,9 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int s = 0;
       uint32_t ph = 1;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        // resident filter (Cout = BLOCK_N, 9 * kc_chunks = SB stages): loaded once, by the CTA's first item -- every
+        // later item would fetch the same 9 * kc_chunks * BLOCK_N * 128 bytes again (0.98 GB per 64->64 launch)
+        if (p.resident_b && item != static_cast<int>(blockIdx.x)) break;
         const int n0 = (item / p.num_mgroups) * BLOCK_N;
         for (int kc = 0; kc < p.kc_chunks; ++kc) {
 #pragma unroll 1
@@ -186,7 +190,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t a_stage = a_lo0 + static_cast<uint32_t>((sa * MT * kPatchStride) >> 4);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&b_full[sb], pb);
+            if (!p.resident_b || item == static_cast<int>(blockIdx.x)) mbar_wait(&b_full[sb], pb);
             tc_fence_after();
             const uint32_t b_lo = b_lo0 + static_cast<uint32_t>((sb * kBBytes) >> 4);
             constexpr int kRowsPerGroup = 10;
@@ -198,7 +202,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const uint32_t accumulate = tap == 0 ? (kc != 0 ? 1u : 0u) : 1u;
               umma_ss_conv4<kTf32>(acc0 + t * BLOCK_N, a_lo, a_hi, b_lo, b_hi, kIdesc, accumulate, leader);
             }
-            umma_commit_conv(&b_empty[sb], leader);
+            if (!p.resident_b) umma_commit_conv(&b_empty[sb], leader);   // resident stages are never recycled
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
           umma_commit_conv(&a_empty[sa], leader);
@@ -280,7 +284,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // ----------------------------------------------------------------------------- host side
 struct V2Plan {
-  int block_n, mt, sa, sb, tiles_w, tiles_h, sgs;
+  int block_n, mt, sa, sb, tiles_w, tiles_h, sgs, resident_b;
   size_t smem;
 };
 
@@ -306,6 +310,16 @@ static int v2_make_plan(const b2u_conv_desc* d, V2Plan* pl) {
   while (bytes(sa + 1, sb) <= budget && sa < 3) ++sa;
   while (bytes(sa, sb + 1) <= budget && sb < 9) ++sb;
   if (d->reserved[1] >= 2 && d->reserved[1] <= 12) sb = d->reserved[1];
+  // whole filter resident: one N tile (every item uses the same weights) and all 9 * (Cin / 64-or-32) stages fit
+  {
+    const int kc = d->cin / (d->dtype == B2U_F32 ? 32 : 64);
+    pl->resident_b = (d->cout == bn && 9 * kc <= 12 && bytes(2, 9 * kc) <= budget && d->reserved[1] == 0) ? 1 : 0;
+    if (pl->resident_b) {
+      sb = 9 * kc;
+      sa = 2;
+      while (bytes(sa + 1, sb) <= budget && sa < 3) ++sa;
+    }
+  }
   B2U_REQUIRE(bytes(sa, sb) <= budget, "conv3x3 v2: pipeline does not fit shared memory (BLOCK_N %d MT %d)", bn, mt);
   pl->sa = sa;
   pl->sb = sb;
@@ -374,6 +388,7 @@ int conv3x3_v2_run(const void* x, const void* wpacked, void* y, float* partials,
   gp.cout = d->cout;
   gp.sa = pl.sa; gp.sb = pl.sb;
   gp.sgs_log2 = pl.sgs > 0 ? conv_ilog2(pl.sgs) : -1;
+  gp.resident_b = pl.resident_b;
   gp.y = y;
   gp.partials = partials;
   int grid = b2u_num_sms();
