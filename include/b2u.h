@@ -277,6 +277,20 @@ int b2u_pack_convT2x2_dgrad_weight(const float* w, void* packed, int cin, int co
  * angles_deg: host array of n angles (counter-clockwise degrees, as passed to TF.rotate). */
 int b2u_rotate_bilinear(const float* x, float* out, int n, int c, int h, int w, const double* angles_deg,
                         int x_batch_stride_is_zero, void* stream);
+/* CUDA-graph form of the rotation ensemble loop (Rotational_Uncertainty.py:51-63): the per-angle affine coefficients
+ * live in a DEVICE table (6 floats per angle, filled on the host by b2u_rotation_table with exactly the arithmetic of
+ * b2u_rotate_bilinear) indexed by the global angle index `*iter_base_dev + k`, so one captured graph serves every step.
+ *   b2u_rotation_table:         host helper, table_host[n][6] for angles_deg[n] (no launch);
+ *   b2u_rotate_in_table:        x [c][h][w] (ONE image) -> out [n][c][h][w], image k rotated by row min(base + k, len-1);
+ *   b2u_rotate_back_accumulate: seg [n][h][w] -> rotate back by row base + k, * fov (may be NULL), fp64 per-pixel
+ *                               (sum, sum of squares) into acc[2][h*w], the first return_num samples into
+ *                               samples[return_num][h*w] (may be NULL); images with base + k >= *iter_limit_dev are skipped. */
+int b2u_rotation_table(const double* angles_deg, int n, int h, int w, float* table_host);
+int b2u_rotate_in_table(const float* x, float* out, int n, int c, int h, int w, const float* table_dev, int table_len,
+                        const long long* iter_base_dev, void* stream);
+int b2u_rotate_back_accumulate(const float* seg, const float* fov, double* acc, float* samples, int n, int h, int w,
+                               int return_num, const float* table_dev, int table_len, const long long* iter_base_dev,
+                               const long long* iter_limit_dev, void* stream);
 
 /* ------------------------------------------------------------------ fused square_pad + TF.resize
  * (utils_general.py:32-43 + torchvision TF.resize on tensors = bilinear, align_corners=False, antialias=True; used by

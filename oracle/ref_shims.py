@@ -1,8 +1,10 @@
-"""ORACLE SUPPORT (test infrastructure): import the UNMODIFIED reference modules from
-/root/reference with in-memory shims for the five packages the image lacks (SURVEY.md
-section 8c).  None of the shims changes arithmetic.  /root/reference exists only in the
-build container, so this module is used solely by `tests/golden/make_golden.py` and by
-tests that are skipped when the reference tree is absent (e.g. on the GPU box).
+"""ORACLE SUPPORT (test infrastructure): import the UNMODIFIED reference modules with in-memory
+shims for the five packages the image lacks.  None of the shims changes
+arithmetic.  Two locations are tried: /root/reference (this container: the sources where they lie)
+and `oracle/_ref/` (the GPU box: sourceless byte-code compiled from those sources by
+`oracle/build_ref.py`; git-ignored, travels like the built `.so`).  Used by
+`tests/golden/make_golden.py`, by the tests that run the reference's own classes, and by
+`bench.py --impl reference` / its `cpu_baseline` leg.
 """
 from __future__ import annotations
 
@@ -15,12 +17,31 @@ import numpy as np
 import torch
 from torch import nn
 
-REF_ROOT = "/root/reference/Unet_research"
-REF_CODE = os.path.join(REF_ROOT, "unet_code")
+SRC_ROOT = "/root/reference/Unet_research"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PYC_ROOT = os.path.join(_HERE, "_ref")
+
+
+def _pyc_complete() -> bool:
+    from . import build_ref
+    return build_ref.built()
+
+
+def reference_location():
+    """("source" | "bytecode" | None, root directory that contains unet_code/)."""
+    if os.path.isdir(os.path.join(SRC_ROOT, "unet_code")):
+        return "source", SRC_ROOT
+    if _pyc_complete():
+        return "bytecode", PYC_ROOT
+    return None, None
 
 
 def reference_available() -> bool:
-    return os.path.isdir(REF_CODE)
+    return reference_location()[0] is not None
+
+
+REF_ROOT = reference_location()[1] or SRC_ROOT
+REF_CODE = os.path.join(REF_ROOT, "unet_code")
 
 
 def _install_shims():
@@ -116,22 +137,35 @@ def _install_shims():
                 sys.modules[name] = _Fake(name)
 
 
-def load_reference():
+_LOADED = {}
+
+
+def load_reference(prefer: str = None):
     """Returns a namespace with the reference's own classes: UNet, DropBlock2D,
     Dropblock2d_ichan, LinearScheduler, BaseUNetTraining, DropBlockEval, set_dropblock_on,
-    RotationEval, UNetTraining."""
-    if not reference_available():
-        raise RuntimeError("reference tree not present at " + REF_CODE)
+    RotationEval, UNetTraining (+ `.kind`: "source" or "bytecode", and the script modules `.mod_db`,
+    `.mod_rot`, `.mod_train` for import-swap tests).  prefer="bytecode" forces oracle/_ref."""
+    kind, root = reference_location()
+    if prefer == "bytecode" and _pyc_complete():
+        kind, root = "bytecode", PYC_ROOT
+    if kind is None:
+        raise RuntimeError("reference not available: neither " + SRC_ROOT + " nor a complete " + PYC_ROOT)
+    if kind in _LOADED:
+        return _LOADED[kind]
+    if _LOADED:
+        raise RuntimeError("the reference is already loaded from the other location in this process")
+    code = os.path.join(root, "unet_code")
+    ext = ".py" if kind == "source" else ".pyc"
     _install_shims()
-    if REF_CODE not in sys.path:
-        sys.path.insert(0, REF_CODE)
+    if code not in sys.path:
+        sys.path.insert(0, code)
     cwd = os.getcwd()
-    os.chdir(REF_ROOT)          # scripts do sys.path.append(os.getcwd() + '/unet_code')
+    os.chdir(root)              # scripts do sys.path.append(os.getcwd() + '/unet_code')
     try:
         from utils import utils_unet, utils_modules, utils_training  # type: ignore
 
         def load_script(name, rel):
-            spec = importlib.util.spec_from_file_location(name, os.path.join(REF_CODE, rel))
+            spec = importlib.util.spec_from_file_location(name, os.path.join(code, rel[:-3] + ext))
             mod = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(mod)
             return mod
@@ -145,7 +179,9 @@ def load_reference():
         UNet=utils_unet.UNet, DropBlock2D=utils_modules.DropBlock2D,
         Dropblock2d_ichan=utils_modules.Dropblock2d_ichan, LinearScheduler=utils_modules.LinearScheduler,
         BaseUNetTraining=utils_training.BaseUNetTraining, DropBlockEval=db.DropBlockEval,
-        set_dropblock_on=db.set_dropblock_on, RotationEval=rot.RotationEval, UNetTraining=tr.UNetTraining)
+        set_dropblock_on=db.set_dropblock_on, RotationEval=rot.RotationEval, UNetTraining=tr.UNetTraining, kind=kind,
+        mod_db=db, mod_rot=rot, mod_train=tr, mod_unet=utils_unet, mod_modules=utils_modules, mod_training=utils_training)
+    _LOADED[kind] = ns
     return ns
 
 

@@ -677,7 +677,7 @@ def sec_rotate():
     return res
 
 
-def _build_model(dev, dropblock=False, compute="bf16", init_channels=1):
+def _build_model(dev, dropblock=False, compute="auto", init_channels=1):
     import torch
     from torch import nn
     import unet_research_b200 as U
@@ -861,7 +861,7 @@ def sec_forward():
     print(f"  module forward vs reference golden: rel {r:.3e} max {mx:.3e}")
 
 
-def sec_mc():
+def sec_mc(h=120, w=116, T=6, iter_batch=2, compute="auto", graphs=(False, True)):
     import torch
     from oracle import unet_oracle as O
     import unet_research_b200 as U
@@ -869,14 +869,12 @@ def sec_mc():
     dev = torch.device("cuda")
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    h, w = 120, 116
-    m, sd = _build_model(dev, dropblock=True)
+    m, sd = _build_model(dev, dropblock=True, compute=compute)
     x = synthetic.make_image(h, w, seed=1234).to(dev)
     fov = synthetic.make_fov_mask(h, w).to(dev)
-    T = 6
     res = []
-    for graph in (False, True):
-        ev = U.DropBlockEval(m, num_iterations=T, return_num=4, iter_batch=2, use_cuda_graph=graph)
+    for graph in graphs:
+        ev = U.DropBlockEval(m, num_iterations=T, return_num=4, iter_batch=iter_batch, use_cuda_graph=graph)
         torch.manual_seed(77)
         _, (mean, std, tens) = ev.predict_step((x, None, fov), 0)
         off_got = torch.cuda.default_generators[0].get_offset()
@@ -1072,7 +1070,7 @@ def sec_trainbench():
     print("     dgrad launches (ms):", per)
 
 
-def sec_rot_ens():
+def sec_rot_ens(h=120, w=116, T=5, angle_batch=2, compute="auto", graph=True, resize=-1):
     import torch
     from oracle import unet_oracle as O
     import unet_research_b200 as U
@@ -1080,13 +1078,14 @@ def sec_rot_ens():
     dev = torch.device("cuda")
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    h, w = 120, 116
-    m, sd = _build_model(dev)
+    m, sd = _build_model(dev, compute=compute)
     x = synthetic.make_image(h, w, seed=1234).to(dev)
     fov = synthetic.make_fov_mask(h, w).to(dev)
-    ev = U.RotationEval(m, num_iterations=5, return_num=3, angle_batch=2)
+    ev = U.RotationEval(m, num_iterations=T, return_num=3, angle_batch=angle_batch, use_cuda_graph=graph, resize=resize)
     _, (mean, std, tens) = ev.predict_step((x, None, fov), 0)
-    rmean, rstd, rtens = O.rotation_ensemble(sd, x, fov, 5, 3)
+    if resize != -1:                                            # Rotational_Uncertainty.py:39-49
+        x, fov = O.square_pad_resize(x, resize), O.square_pad_resize(fov, resize)
+    rmean, rstd, rtens = O.rotation_ensemble(sd, x, fov, T, 3)
     print(f"  rotation ensemble: mean rel {rel(mean, rmean)[0]:.3e} std rel {rel(std, rstd)[0]:.3e} max|d| {rel(std, rstd)[1]:.3e} samples rel {rel(tens, rtens)[0]:.3e}")
     return {"mean": rel(mean, rmean)[0], "std_maxabs": rel(std, rstd)[1], "samples": rel(tens, rtens)[0]}
 

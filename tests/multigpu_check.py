@@ -37,9 +37,13 @@ def main():
     # ---- 1. MC sharding
     m, _ = D._build_model(dev, dropblock=True)
     T = 12
-    ev = U.DropBlockEval(m, num_iterations=T, return_num=5, iter_batch=2)
+    ev = U.DropBlockEval(m, num_iterations=T, return_num=5, iter_batch=2, gather_samples=True)
     torch.manual_seed(99)
     _, (mean, std, tens) = ev.predict_step((x, None, fov), 0)
+    # default (no sample exchange): rank 0 owns iterations [0, return_num) whenever return_num <= its share
+    ev0 = U.DropBlockEval(m, num_iterations=40, return_num=3, iter_batch=2)
+    torch.manual_seed(99)
+    _, (_, _, tens0) = ev0.predict_step((x, None, fov), 0)
     # single-rank reference: hide the process group from the loop
     real = UN._dist
     UN._dist = lambda: (None, 0, 1)
@@ -53,13 +57,15 @@ def main():
     e_m = float((mean - mean1).abs().max())
     e_d = float((std - std1).abs().max())
     good = e_s == 0.0 and e_m < 1e-6 and e_d < 1e-6
+    if rank == 0:
+        good = good and torch.equal(tens0, tens1[:3])
     ok &= good
     if rank == 0:
         print(f"[mc sharding x{world}] samples max|d| {e_s:.1e} mean {e_m:.1e} std {e_d:.1e} -> {'OK' if good else 'FAIL'}", flush=True)
 
     # ---- 2. rotation sharding
     m2, _ = D._build_model(dev)
-    rv = U.RotationEval(m2, num_iterations=7, return_num=3, angle_batch=2)
+    rv = U.RotationEval(m2, num_iterations=7, return_num=3, angle_batch=2, gather_samples=True)
     _, (rmean, rstd, rtens) = rv.predict_step((x, None, fov), 0)
     UN._dist = lambda: (None, 0, 1)
     try:
@@ -99,6 +105,8 @@ def main():
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.barrier()
+    if rank == 0 and int(t.item()) == 1:
+        print("MULTIGPU OK", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if int(t.item()) == 1 else 1)
 

@@ -6,8 +6,10 @@ Tolerances (stated per north_star; "rel" = ||a-b||_2 / ||b||_2):
   * integer / bit work (DropBlock masks, keep counts, Philox offsets, max-pool argmax): bit-exact;
   * one bf16 kernel vs fp64 math on the same rounded operands: rel <= 3e-3 (bf16 output rounding, 2^-9);
     one TF32 kernel: rel <= 1.5e-3 when operands are not pre-rounded (hardware truncation), fp32 stats 1e-4;
-  * whole forward, bf16: probabilities rel <= 1e-2, logits rel <= 2.5e-2 (measured 1.6e-2; 23 bf16 layers
-    with GroupNorm amplification -- see DESIGN.md "numerics"); TF32: logits rel <= 2e-3, probabilities <= 1e-3;
+  * whole forward in the DEFAULT inference mode (compute_dtype "auto" = fp16 operands, the mode bench.py times):
+    logits rel <= 1e-2 and probabilities rel <= 1e-2 -- north_star's 16-bit bar -- at every size incl. 584x565;
+    explicit bf16: probabilities rel <= 1e-2, logits no worse than 1.05 x PyTorch's own bf16-autocast run of the
+    reference (test_precision_floor...); TF32: logits rel <= 2e-3, probabilities <= 1e-3 (cuDNN-TF32 sits at 1.36e-3);
   * MC statistics: mean rel <= 5e-3, |std - ref| <= 1.5e-2 absolute (T = 6 samples), samples rel <= 1e-2.
 """
 import os
@@ -87,7 +89,16 @@ def test_rotate_matches_torchvision_restatement():
 # batched 8 / 4 / 8 / 2 images per call
 @pytest.mark.parametrize("h,w,n", [(120, 116, 1), (120, 116, 3), (584, 565, 1), (146, 141, 8), (292, 283, 4), (128, 128, 8),
                                    (256, 256, 2)])
+def test_forward_default_mode_vs_oracle(h, w, n):
+    """The mode `bench.py` times (compute_dtype "auto": fp16 operands for inference) meets north_star's 1e-2 logit bar."""
+    r = D._forward_case(h, w, n, "auto")
+    assert r["out_rel"] < 1e-2 and r["logits_rel"] < 1e-2
+
+
+@pytest.mark.parametrize("h,w,n", [(120, 116, 1), (584, 565, 1), (146, 141, 8)])
 def test_forward_bf16_vs_oracle(h, w, n):
+    """Explicit bf16 (the training dtype): probabilities inside the bar; bf16 LOGITS are bounded by the reference's own
+    bf16 floor (1.79e-2 under torch.autocast, test_precision_floor_vs_reference_at_equal_precision)."""
     r = D._forward_case(h, w, n, "bf16")
     assert r["out_rel"] < 1e-2 and r["logits_rel"] < 2.5e-2
 
@@ -100,7 +111,7 @@ def test_forward_tf32_vs_oracle():
 def test_module_forward_vs_reference_golden(golden_dir):
     from unet_research_b200 import synthetic
     dev = torch.device("cuda")
-    for compute, tol in (("bf16", 1e-2), ("tf32", 1e-3)):
+    for compute, tol in (("auto", 2e-3), ("bf16", 1e-2), ("tf32", 1e-3)):
         m, _ = D._build_model(dev, compute=compute)
         g = np.load(os.path.join(golden_dir, "unet_eval_120x116.npz"))
         with torch.no_grad():
@@ -121,9 +132,50 @@ def test_mc_dropblock_vs_oracle():
         assert r["offset"] == r["offset_ref"]           # generator left where the reference leaves it
 
 
-def test_rotation_ensemble_vs_oracle():
-    r = D.sec_rot_ens()
+@pytest.mark.parametrize("compute", ["bf16"])
+def test_mc_dropblock_bf16_vs_oracle(compute):
+    for r in D.sec_mc(compute=compute, graphs=(True,)):
+        assert r["samples"] < 1e-2 and r["mean"] < 5e-3 and r["std_maxabs"] < 1.5e-2
+        assert r["offset"] == r["offset_ref"]
+
+
+def test_mc_dropblock_full_size_vs_oracle():
+    """BASELINE configs[2] at its own size: DropBlockEval at 584x565, T = 10 (one graph-replayed step of 10 batched
+    iterations... run as 2 x 5 so the captured pair graph is exercised), against the oracle on the same GPU with the same
+    Philox stream (Dropblock_Uncertainty.py:64-67)."""
+    (r,) = D.sec_mc(h=584, w=565, T=10, iter_batch=5, graphs=(True,))
     assert r["samples"] < 1e-2 and r["mean"] < 5e-3 and r["std_maxabs"] < 1.5e-2
+    assert r["offset"] == r["offset_ref"]
+
+
+def test_rotation_ensemble_vs_oracle():
+    for graph in (False, True):
+        r = D.sec_rot_ens(graph=graph)
+        assert r["samples"] < 1e-2 and r["mean"] < 5e-3 and r["std_maxabs"] < 1.5e-2
+
+
+def test_rotation_ensemble_full_size_vs_oracle():
+    """BASELINE configs[3] at 584x565, 3 angles, against the oracle (Rotational_Uncertainty.py:51-66)."""
+    r = D.sec_rot_ens(h=584, w=565, T=3, angle_batch=2)
+    assert r["samples"] < 1e-2 and r["mean"] < 5e-3 and r["std_maxabs"] < 1.5e-2
+
+
+def test_rotation_ensemble_resize_vs_oracle():
+    """RotationEval(resize=128): square_pad + TF.resize of im / mask before the angle loop (Rotational_Uncertainty.py:39-49)."""
+    r = D.sec_rot_ens(h=200, w=180, T=4, angle_batch=3, resize=128)
+    assert r["samples"] < 1e-2 and r["mean"] < 5e-3 and r["std_maxabs"] < 1.5e-2
+
+
+def test_rotation_single_angle_std_is_nan():
+    """num_iterations = 1: torch.std of one sample is NaN, the mean is the sample (as DropBlockEval)."""
+    import unet_research_b200 as U
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    m, _ = D._build_model(dev)
+    x = synthetic.make_image(120, 116, seed=1234).to(dev)
+    fov = synthetic.make_fov_mask(120, 116).to(dev)
+    _, (mean, std, tens) = U.RotationEval(m, num_iterations=1, return_num=1).predict_step((x, None, fov), 0)
+    assert torch.isnan(std).all() and torch.equal(mean, tens[0])
 
 
 def test_rotation_full_size_properties():
@@ -136,7 +188,7 @@ def test_rotation_full_size_properties():
     x = synthetic.make_image(584, 565, seed=1234).to(dev)
     fov = synthetic.make_fov_mask(584, 565).to(dev)
     outs = []
-    for ab in (3, 2, 3):
+    for ab in (3, 4, 3):                                  # 4: the last step holds 2 valid angles + 2 skipped by the limit
         ev = U.RotationEval(m, num_iterations=6, return_num=6, angle_batch=ab)
         _, (mean, std, tens) = ev.predict_step((x, None, fov), 0)
         outs.append((mean, std, tens))
@@ -442,3 +494,153 @@ def test_training_reduces_loss_full_size():
         opt.step()
         losses.append(loss.item())
     assert all(l == l for l in losses) and losses[-1] < losses[0] - 0.05, losses
+
+
+def test_gradient_accumulation_and_stale_forward():
+    """Autograd's accumulate semantics on the aliased gradient buffer (two backwards without zero_grad sum up; an in-place
+    zero_grad(set_to_none=False) starts from zero), and a backward whose activations were overwritten by a later forward of
+    the same shape raises instead of returning wrong gradients."""
+    import unet_research_b200 as U
+    from torch import nn
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    m, _ = D._build_model(dev)
+    m.train()
+    x = synthetic.make_image(120, 116, seed=1234).to(dev)
+    gt = synthetic.make_gt(120, 116).to(dev)
+    fov = synthetic.make_fov_mask(120, 116).to(dev)
+    tm = U.BaseUNetTraining(m, nn.BCELoss(), None)
+    tm.training_step((x.clone(), gt, fov), 0).backward()
+    g1 = {k: p.grad.clone() for k, p in m.named_parameters()}
+    tm.training_step((x.clone(), gt, fov), 0).backward()           # no zero_grad: accumulate
+    for k, p in m.named_parameters():
+        torch.testing.assert_close(p.grad, 2 * g1[k], rtol=1e-5, atol=1e-7)
+    for p in m.parameters():
+        p.grad.zero_()                                              # zero_grad(set_to_none=False)
+    tm.training_step((x.clone(), gt, fov), 0).backward()
+    for k, p in m.named_parameters():
+        torch.testing.assert_close(p.grad, g1[k], rtol=1e-5, atol=1e-7)
+    m.zero_grad(set_to_none=True)
+    l1 = tm.training_step((x.clone(), gt, fov), 0)
+    l2 = tm.training_step((x.clone(), gt, fov), 0)                  # overwrites the workspace activations of l1
+    l2.backward()
+    with pytest.raises(RuntimeError, match="overwritten"):
+        l1.backward()
+
+
+def test_train_graphs_survive_mask_plan_churn():
+    """the captured training graphs must not read a DropBlock mask plan that an unrelated forward evicted --
+    TrainStep owns its plan.  Same model: train (graphs captured), DropBlock-active inference on six other shapes (more
+    than the eager plan cache holds), train again; losses and weights equal the all-eager run bit for bit."""
+    import unet_research_b200 as U
+    from torch import nn
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    x = synthetic.make_image(120, 116, seed=1234).to(dev)
+    gt = synthetic.make_gt(120, 116).to(dev)
+    fov = synthetic.make_fov_mask(120, 116).to(dev)
+    res = {}
+    for graphs in (False, True):
+        m, _ = D._build_model(dev, dropblock=True, compute="bf16")     # one engine for training and inference
+        m.use_cuda_graph = graphs
+        tm = U.BaseUNetTraining(m, nn.BCELoss(), None)
+        opt = torch.optim.SGD(m.parameters(), lr=1e-2, momentum=0.9)
+        torch.manual_seed(31)
+        losses = []
+
+        def train(k):
+            m.train()
+            for _ in range(k):
+                opt.zero_grad(set_to_none=True)
+                loss = tm.training_step((x.clone(), gt, fov), 0)
+                loss.backward()
+                opt.step()
+                losses.append(loss.item())
+
+        train(4)
+        m.eval()
+        m.apply(U.set_dropblock_on)
+        with torch.no_grad():
+            for k in range(6):
+                m(synthetic.make_image(112 + 16 * k, 112, seed=k).to(dev))
+        assert len(m._mask_plans) <= m.MAX_MASK_PLANS
+        train(3)
+        res[graphs] = (losses, torch.cat([p.detach().flatten() for p in m.parameters()]).clone())
+    assert res[False][0] == res[True][0], (res[False][0], res[True][0])
+    assert torch.equal(res[False][1], res[True][1])
+
+
+def test_multi_gpu_sharding_matches_single_rank():
+    """Driver-visible multi-GPU correctness: torchrun over the visible GPUs (2, 4 or 8) runs tests/multigpu_check.py --
+    MC-DropBlock and rotation statistics sharded over N ranks equal the 1-rank result, data-parallel gradients equal the
+    mean of the per-rank gradients."""
+    import subprocess
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 8 if n >= 8 else (4 if n >= 4 else 2)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tests", "multigpu_check.py")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0 and "MULTIGPU OK" in r.stdout, r.stdout[-4000:]
+
+
+def test_reference_own_loops_around_b200_unet():
+    """The literal drop-in claim, executed: the UNMODIFIED reference classes (`DropBlockEval`
+    Dropblock_Uncertainty.py:27-72, `RotationEval` Rotational_Uncertainty.py:21-68, `UNetTraining` training.py:23-51,
+    loaded from /root/reference here or from the byte-code in oracle/_ref on the GPU box) drive THIS package's `UNet`
+    after the one-line import swap of INTEGRATION.md (their `DropBlock2D` name bound to ours).  Results are compared
+    with our own fused loops (same Philox stream: samples bit-identical) and with the oracle."""
+    import unet_research_b200 as U
+    from oracle import ref_shims as R
+    from oracle import unet_oracle as O
+    from torch import nn
+    from unet_research_b200 import synthetic
+    if not R.reference_available():
+        pytest.skip("neither /root/reference nor oracle/_ref present")
+    ref = R.load_reference()
+    for mod in (ref.mod_db, ref.mod_rot):                       # the import swap
+        mod.DropBlock2D, mod.Dropblock2d_ichan = U.DropBlock2D, U.Dropblock2d_ichan
+    dev = torch.device("cuda")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    h, w = 120, 116
+    x = synthetic.make_image(h, w, seed=1234).to(dev)
+    gt = synthetic.make_gt(h, w).to(dev)
+    fov = synthetic.make_fov_mask(h, w).to(dev)
+    # ---- MC-DropBlock: reference loop (one forward per iteration, torch.vstack/mean/std) around our UNet
+    m, sd = D._build_model(dev, dropblock=True)
+    with torch.no_grad():
+        torch.manual_seed(5)
+        _, (rmean, rstd, rtens) = ref.DropBlockEval(m, num_iterations=4, return_num=4).predict_step((x, gt, fov), 0)
+        off_ref = torch.cuda.default_generators[0].get_offset()
+        torch.manual_seed(5)
+        _, (mean, std, tens) = U.DropBlockEval(m, num_iterations=4, return_num=4, iter_batch=2).predict_step((x, gt, fov), 0)
+        off = torch.cuda.default_generators[0].get_offset()
+        torch.manual_seed(5)
+        omean, ostd, otens = O.mc_dropblock(sd, x, fov, 4, 4, 0.15, 7)
+    assert tuple(rtens.shape) == (4, 1, 1, h, w) and off == off_ref
+    assert torch.equal(tens, rtens)                              # same masks, same kernels, batch-invariant: bit-identical
+    torch.testing.assert_close(mean, rmean, rtol=0, atol=1e-6)
+    torch.testing.assert_close(std, rstd, rtol=0, atol=1e-6)
+    assert D.rel(rtens, otens)[0] < 1e-2 and D.rel(rmean, omean)[0] < 5e-3
+    # ---- rotation ensemble: reference loop (TF.rotate in / out) around our UNet vs our fused loop
+    m2, _ = D._build_model(dev)
+    with torch.no_grad():
+        _, (rmean, rstd, rtens) = ref.RotationEval(m2, num_iterations=3, return_num=3).predict_step((x, gt, fov), 0)
+        _, (mean, std, tens) = U.RotationEval(m2, num_iterations=3, return_num=3, angle_batch=2).predict_step((x, gt, fov), 0)
+    assert D.rel(tens, rtens)[0] < 1e-3 and D.rel(mean, rmean)[0] < 1e-3 and float((std - rstd).abs().max()) < 1e-3
+    # ---- training: the reference LightningModule's training_step around our UNet == ours (same loss, same gradients)
+    m3, _ = D._build_model(dev)
+    m3.train()
+    loss_ref = ref.UNetTraining(m3, nn.BCELoss(), lr=1e-3, momentum=0.99).training_step((x.clone(), gt, fov), 1)
+    loss_ref.backward()
+    g_ref = torch.cat([p.grad.flatten() for p in m3.parameters()]).clone()
+    m3.zero_grad(set_to_none=True)
+    loss = U.BaseUNetTraining(m3, nn.BCELoss(), None).training_step((x.clone(), gt, fov), 1)
+    loss.backward()
+    g = torch.cat([p.grad.flatten() for p in m3.parameters()])
+    assert float(loss) == float(loss_ref) and torch.equal(g, g_ref)
+    loss_oracle = O.train_step_loss({k: v.to(dev) for k, v in synthetic.make_state_dict(seed=1234).items()}, x, gt, fov, None)
+    assert abs(float(loss) - float(loss_oracle)) < 1e-3 * abs(float(loss_oracle))

@@ -6,7 +6,7 @@ import torch
 from torch import nn
 
 
-def build_canonical(device, dropblock: bool = False, compute: str = "bf16", init_channels: int = 1, seed: int = 1234,
+def build_canonical(device, dropblock: bool = False, compute: str = "auto", init_channels: int = 1, seed: int = 1234,
                     drop_prob: float = 0.15, block_size: int = 7):
     """Canonical reference configuration (base_model_tests/training.py:171-192) with synthetic weights."""
     import unet_research_b200 as U

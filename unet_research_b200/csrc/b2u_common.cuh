@@ -40,6 +40,18 @@ void b2u_set_error(const char* fmt, ...);
   } while (0)
 
 int b2u_num_sms();
+// Opt a kernel into > 48 KB of dynamic shared memory once per (instantiation, device): function attributes are per
+// device, a process-wide flag would leave the second GPU of a multi-device process at the default limit.
+#define B2U_SET_MAX_SMEM_ONCE(kernel, bytes)                                                          \
+  do {                                                                                                \
+    static unsigned long long _done = 0;                                                              \
+    int _dev = 0;                                                                                     \
+    B2U_CHECK_CUDA(cudaGetDevice(&_dev));                                                             \
+    if (!((_done >> (_dev & 63)) & 1ull)) {                                                           \
+      B2U_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+      _done |= 1ull << (_dev & 63);                                                                   \
+    }                                                                                                 \
+  } while (0)
 int b2u_pdl_enabled();      // 1 unless the environment sets B2U_PDL=0
 
 #ifdef __CUDACC__

@@ -330,11 +330,7 @@ static int v2_make_plan(const b2u_conv_desc* d, V2Plan* pl) {
 
 template <int BN, int MT, int TF>
 static int v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Params& gp, int grid, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2U_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_v2_kernel<BN, MT, TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  B2U_SET_MAX_SMEM_ONCE((conv3x3_v2_kernel<BN, MT, TF>), 227 * 1024);
   B2U_PDL_LAUNCH((conv3x3_v2_kernel<BN, MT, TF>), grid, kV2Threads, smem, st, ta, tb, gp);
   B2U_LAUNCH_CHECK();
   return B2U_OK;

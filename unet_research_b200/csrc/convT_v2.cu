@@ -265,11 +265,7 @@ int convT_v2_stat_layout(const b2u_conv_desc* d, int* rows_per_image, int* subgr
 
 template <int TF>
 static int convT_v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvTParams& gp, int grid, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2U_CHECK_CUDA(cudaFuncSetAttribute(convT_v2_kernel<TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  B2U_SET_MAX_SMEM_ONCE((convT_v2_kernel<TF>), 227 * 1024);
   B2U_PDL_LAUNCH((convT_v2_kernel<TF>), grid, kTThreads, smem, st, ta, tb, gp);
   B2U_LAUNCH_CHECK();
   return B2U_OK;

@@ -345,12 +345,7 @@ static int make_plan(const b2u_conv_desc* d, bool conv_t, Plan* pl) {
 template <int BN, int TF>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& gp, dim3 grid, size_t smem,
                        cudaStream_t st) {
-  static bool attr_set = false;       // per instantiation; the value only ever grows to the device max
-  if (!attr_set) {
-    B2U_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, TF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        227 * 1024));
-    attr_set = true;
-  }
+  B2U_SET_MAX_SMEM_ONCE((conv_gemm_kernel<BN, TF>), 227 * 1024);
   B2U_PDL_LAUNCH((conv_gemm_kernel<BN, TF>), grid, kNumThreads, smem, st, ta, tb, gp);
   B2U_LAUNCH_CHECK();
   return B2U_OK;

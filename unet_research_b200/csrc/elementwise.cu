@@ -753,6 +753,99 @@ __global__ void rotate_kernel(const float* __restrict__ x, float* __restrict__ o
   }
 }
 
+// Bilinear sample of one rotated pixel (shared by the three rotation kernels): returns the blend weight m of the
+// ones channel and the four taps (offset, weight); out-of-image taps get weight 0 and offset 0.
+struct RotTaps {
+  int o[4];
+  float wgt[4];
+  float m;
+};
+__device__ __forceinline__ RotTaps rot_taps(const RotParams& r, int oh, int ow, int h, int w) {
+  const float bx = linspace_val(-w * 0.5f + 0.5f, w * 0.5f + 0.5f - 1.f, w, ow);
+  const float by = linspace_val(-h * 0.5f + 0.5f, h * 0.5f + 0.5f - 1.f, h, oh);
+  const float gx = bx * r.t00 + by * r.t01 + r.t02;
+  const float gy = bx * r.t10 + by * r.t11 + r.t12;
+  const float ix = ((gx + 1.f) * w - 1.f) * 0.5f;
+  const float iy = ((gy + 1.f) * h - 1.f) * 0.5f;
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+  const float ax = ix - fx, ay = iy - fy;
+  const bool inx0 = x0 >= 0 && x0 < w, inx1 = x0 + 1 >= 0 && x0 + 1 < w;
+  const bool iny0 = y0 >= 0 && y0 < h, iny1 = y0 + 1 >= 0 && y0 + 1 < h;
+  RotTaps t;
+  t.wgt[0] = (inx0 && iny0) ? (1.f - ax) * (1.f - ay) : 0.f;
+  t.wgt[1] = (inx1 && iny0) ? ax * (1.f - ay) : 0.f;
+  t.wgt[2] = (inx0 && iny1) ? (1.f - ax) * ay : 0.f;
+  t.wgt[3] = (inx1 && iny1) ? ax * ay : 0.f;
+  t.o[0] = (inx0 && iny0) ? y0 * w + x0 : 0;
+  t.o[1] = (inx1 && iny0) ? y0 * w + x0 + 1 : 0;
+  t.o[2] = (inx0 && iny1) ? (y0 + 1) * w + x0 : 0;
+  t.o[3] = (inx1 && iny1) ? (y0 + 1) * w + x0 + 1 : 0;
+  // same accumulation order as rotate_kernel / grid_sample: nw, ne, sw, se (skipped taps add nothing)
+  float m = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) m += t.wgt[k];
+  t.m = m;
+  return t;
+}
+
+// Rotation ensemble, CUDA-graph form (Rotational_Uncertainty.py:51-60): the per-angle coefficients come from a DEVICE
+// table indexed by the global angle index `*iter_base + k`, so one captured graph serves every step of the loop.
+// rotate_in:  x [c][h][w] (one image) -> out [n][c][h][w], image k rotated by table[min(*iter_base + k, table_len - 1)].
+__global__ void __launch_bounds__(256) rotate_in_table_kernel(const float* __restrict__ x, float* __restrict__ out, int n, int c, int h, int w,
+                                                            const RotParams* __restrict__ table, int table_len,
+                                                            const long long* __restrict__ iter_base) {
+  const long long base = *iter_base;
+  const int hw = h * w;
+  const long total = static_cast<long>(n) * hw;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += gridDim.x * 256L) {
+    const int img = static_cast<int>(i / hw);
+    const int pix = static_cast<int>(i - static_cast<long>(img) * hw);
+    long long ti = base + img;
+    if (ti > table_len - 1) ti = table_len - 1;
+    const RotTaps t = rot_taps(table[ti], pix / w, pix % w, h, w);
+    for (int ch = 0; ch < c; ++ch) {
+      const float* src = x + static_cast<long>(ch) * hw;
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (t.wgt[k] != 0.f) v += src[t.o[k]] * t.wgt[k];
+      out[(static_cast<long>(img) * c + ch) * hw + pix] = v * t.m;
+    }
+  }
+}
+// rotate_back + FOV mask + per-pixel fp64 (sum, sum of squares) + the first `return_num` samples in ONE pass
+// (Rotational_Uncertainty.py:58-63): seg [n][h][w]; image k is angle index *iter_base + k and is skipped when that index
+// is >= *iter_limit (the tail of the last batch).
+__global__ void __launch_bounds__(256) rotate_back_accumulate_kernel(const float* __restrict__ seg, const float* __restrict__ fov,
+                                                                   double* __restrict__ acc, float* __restrict__ samples, int n, int h,
+                                                                   int w, int return_num, const RotParams* __restrict__ table,
+                                                                   int table_len, const long long* __restrict__ iter_base,
+                                                                   const long long* __restrict__ iter_limit) {
+  const long long base = *iter_base, limit = *iter_limit;
+  const int hw = h * w;
+  for (int pix = blockIdx.x * 256 + threadIdx.x; pix < hw; pix += gridDim.x * 256) {
+    const float fv = fov ? fov[pix] : 1.f;
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < n; ++k) {
+      const long long it = base + k;
+      if (it >= limit || it >= table_len) break;
+      const RotTaps t = rot_taps(table[it], pix / w, pix % w, h, w);
+      const float* src = seg + static_cast<long>(k) * hw;
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (t.wgt[j] != 0.f) v += src[t.o[j]] * t.wgt[j];
+      v = v * t.m * fv;
+      s1 += static_cast<double>(v);
+      s2 += static_cast<double>(v) * static_cast<double>(v);
+      if (samples && it < return_num) samples[it * hw + pix] = v;
+    }
+    acc[pix] += s1;
+    acc[hw + pix] += s2;
+  }
+}
+
 static int grid_for(long work_items, int threads) {
   long blocks = (work_items + threads - 1) / threads;
   long cap = static_cast<long>(b2u_num_sms()) * 8;
@@ -813,7 +906,7 @@ extern "C" int b2u_conv_first_fwd(const float* x_nchw, const float* w, void* y, 
   B2U_REQUIRE(num_groups == 0 || partials, "partials required");
 #define B2U_LAUNCH_FIRST(T, CIN)                                                                                  \
   do {                                                                                                            \
-    B2U_CHECK_CUDA(cudaFuncSetAttribute(conv_first_kernel<T, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+    B2U_SET_MAX_SMEM_ONCE((conv_first_kernel<T, CIN>), 96 * 1024);                                                \
     B2U_PDL_LAUNCH((conv_first_kernel<T, CIN>), grid, threads, smem, st, x_nchw, w, static_cast<T*>(y), parts, h0, w0, h, wd, cout, sgs); \
   } while (0)
   if (dtype == B2U_F32) {
@@ -1037,32 +1130,68 @@ extern "C" int b2u_advance_counter(long long* counter, long long delta, void* st
   return B2U_OK;
 }
 
+// theta per torchvision functional.py:1006-1063 with angle -> -angle (functional.py:1130), evaluated in double, cast to
+// fp32, then rescaled by [0.5 w, 0.5 h] in fp32 (_functional_tensor.py:598).
+static b2u::RotParams rot_params_for(double angle_deg, int h, int w) {
+  const double rot = -angle_deg * 3.14159265358979323846 / 180.0;   // math.radians(-angle)
+  const double a = cos(rot), b = -sin(rot), cc = sin(rot), dd = cos(rot);
+  const float m0 = static_cast<float>(dd), m1 = static_cast<float>(-b), m2 = 0.f;
+  const float m3 = static_cast<float>(-cc), m4 = static_cast<float>(a), m5 = 0.f;
+  const float sx = 0.5f * w, sy = 0.5f * h;
+  // rescaled_theta = theta^T / [sx, sy]: column 0 (gx) divides by sx, column 1 (gy) by sy
+  b2u::RotParams r;
+  r.t00 = m0 / sx; r.t01 = m1 / sx; r.t02 = m2 / sx;
+  r.t10 = m3 / sy; r.t11 = m4 / sy; r.t12 = m5 / sy;
+  return r;
+}
+
 extern "C" int b2u_rotate_bilinear(const float* x, float* out, int n, int c, int h, int w, const double* angles_deg,
                                    int x_batch_stride_is_zero, void* stream) {
   B2U_REQUIRE(x && out && angles_deg && n > 0 && c > 0 && h > 0 && w > 0, "bad arguments");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long img_stride = static_cast<long>(c) * h * w;
-  // theta per torchvision functional.py:1006-1063 with angle -> -angle (functional.py:1130), evaluated in double,
-  // cast to fp32, then rescaled by [0.5 w, 0.5 h] in fp32 (_functional_tensor.py:598).  The per-angle
-  // coefficients travel by value as a kernel parameter: no allocation, CUDA-graph capturable.
+  // The per-angle coefficients travel by value as a kernel parameter: no allocation, CUDA-graph capturable.
   for (int base = 0; base < n; base += kMaxAnglesPerLaunch) {
     const int nb = n - base < kMaxAnglesPerLaunch ? n - base : kMaxAnglesPerLaunch;
     RotBatch rb;
-    for (int i = 0; i < nb; ++i) {
-      const double rot = -angles_deg[base + i] * 3.14159265358979323846 / 180.0;   // math.radians(-angle)
-      const double a = cos(rot), b = -sin(rot), cc = sin(rot), dd = cos(rot);
-      const float m0 = static_cast<float>(dd), m1 = static_cast<float>(-b), m2 = 0.f;
-      const float m3 = static_cast<float>(-cc), m4 = static_cast<float>(a), m5 = 0.f;
-      const float sx = 0.5f * w, sy = 0.5f * h;
-      // rescaled_theta = theta^T / [sx, sy]: column 0 (gx) divides by sx, column 1 (gy) by sy
-      rb.r[i].t00 = m0 / sx; rb.r[i].t01 = m1 / sx; rb.r[i].t02 = m2 / sx;
-      rb.r[i].t10 = m3 / sy; rb.r[i].t11 = m4 / sy; rb.r[i].t12 = m5 / sy;
-    }
+    for (int i = 0; i < nb; ++i) rb.r[i] = rot_params_for(angles_deg[base + i], h, w);
     const long total = static_cast<long>(nb) * h * w;
     rotate_kernel<<<grid_for(total, 256), 256, 0, st>>>(x + (x_batch_stride_is_zero ? 0 : base * img_stride),
                                                        out + base * img_stride, nb, c, h, w, rb,
                                                        x_batch_stride_is_zero ? 0 : img_stride);
     B2U_LAUNCH_CHECK();
   }
+  return B2U_OK;
+}
+
+extern "C" int b2u_rotation_table(const double* angles_deg, int n, int h, int w, float* table_host) {
+  B2U_REQUIRE(angles_deg && table_host && n > 0 && h > 0 && w > 0, "bad arguments");
+  static_assert(sizeof(b2u::RotParams) == 6 * sizeof(float), "table row = 6 floats");
+  for (int i = 0; i < n; ++i) {
+    const b2u::RotParams r = rot_params_for(angles_deg[i], h, w);
+    memcpy(table_host + 6 * static_cast<size_t>(i), &r, sizeof(r));
+  }
+  return B2U_OK;
+}
+
+extern "C" int b2u_rotate_in_table(const float* x, float* out, int n, int c, int h, int w, const float* table_dev, int table_len,
+                                   const long long* iter_base_dev, void* stream) {
+  B2U_REQUIRE(x && out && table_dev && iter_base_dev && n > 0 && c > 0 && h > 0 && w > 0 && table_len > 0, "bad arguments");
+  B2U_REQUIRE(static_cast<long>(h) * w < (1L << 31), "image too large");
+  rotate_in_table_kernel<<<grid_for(static_cast<long>(n) * h * w, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, out, n, c, h, w, reinterpret_cast<const b2u::RotParams*>(table_dev), table_len, iter_base_dev);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_rotate_back_accumulate(const float* seg, const float* fov, double* acc, float* samples, int n, int h, int w,
+                                          int return_num, const float* table_dev, int table_len, const long long* iter_base_dev,
+                                          const long long* iter_limit_dev, void* stream) {
+  B2U_REQUIRE(seg && acc && table_dev && iter_base_dev && iter_limit_dev && n > 0 && h > 0 && w > 0 && table_len > 0, "bad arguments");
+  B2U_REQUIRE(static_cast<long>(h) * w < (1L << 31), "image too large");
+  rotate_back_accumulate_kernel<<<grid_for(static_cast<long>(h) * w, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      seg, fov, acc, samples, n, h, w, return_num, reinterpret_cast<const b2u::RotParams*>(table_dev), table_len, iter_base_dev,
+      iter_limit_dev);
+  B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

@@ -390,12 +390,11 @@ extern "C" int b2u_wgrad(const void* g, const void* x, float* workspace, float* 
   p.ws = workspace;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(pl.slices, pl.mblks * pl.xchunks, pl.groups);
-  static bool attr9 = false, attr1 = false;
   if (d->taps == 9) {
-    if (!attr9) { B2U_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr9 = true; }
+    B2U_SET_MAX_SMEM_ONCE((wgrad_kernel<9>), 227 * 1024);
     B2U_PDL_LAUNCH((wgrad_kernel<9>), grid, kWgThreads, pl.smem, st, tg, tx, p);
   } else {
-    if (!attr1) { B2U_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr1 = true; }
+    B2U_SET_MAX_SMEM_ONCE((wgrad_kernel<1>), 227 * 1024);
     B2U_PDL_LAUNCH((wgrad_kernel<1>), grid, kWgThreads, pl.smem, st, tg, tx, p);
   }
   B2U_LAUNCH_CHECK();

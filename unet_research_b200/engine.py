@@ -420,12 +420,19 @@ class UNetEngine:
         d.dtype, d.num_groups, d.x_cstride = self.dtype, self.num_groups, x_cstride
         return d
 
+    MAX_WORKSPACES = 6        # multi-GB each at DRIVE size; multi-fidelity sweeps touch ~6 shapes
+
     def workspace(self, n: int, h0: int, w0: int) -> Workspace:
+        """Least-recently-used cache.  Everything that bakes a workspace's device pointers into a CUDA graph (its
+        `train_step`, an `MCRunner`) holds a reference to the Workspace object itself, so an evicted workspace stays
+        alive exactly as long as those graphs do and is freed with them."""
         key = (n, h0, w0)
-        ws = self._workspaces.get(key)
+        ws = self._workspaces.pop(key, None)
         if ws is None:
+            while len(self._workspaces) >= self.MAX_WORKSPACES:
+                self._workspaces.pop(next(iter(self._workspaces)))
             ws = Workspace(self, n, h0, w0)
-            self._workspaces[key] = ws
+        self._workspaces[key] = ws                    # most recently used last
         return ws
 
     # ---- kernel wrappers

@@ -61,23 +61,31 @@ class FusedSGD(torch.optim.Optimizer):
             plist = [p for p in group["params"] if p.grad is not None]
             if not plist:
                 continue
-            for p in plist:
-                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()
-                        and p.grad.dtype == torch.float32):
-                    raise _lib.B2uError("FusedSGD needs contiguous fp32 CUDA parameters and gradients (no CPU path)")
-            first = any("momentum_buffer" not in self.state[p] for p in plist)
-            mlist = []
-            for p in plist:
-                st = self.state[p]
-                if "momentum_buffer" not in st:
-                    st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                mlist.append(st["momentum_buffer"])
-            t_dev, c_dev, n_chunks, partial, norm = self._table(gi, plist, mlist)
-            mgn = group.get("max_grad_norm")
-            call("b2u_sgd_step", ptr(t_dev), ptr(c_dev), n_chunks, ptr(partial), float(group["lr"]), float(group["momentum"]),
-                 float(mgn) if mgn else 0.0, int(first), ptr(norm), stream_ptr())
-            self.last_grad_norm = norm if mgn else None
-            # the kernels wrote the parameters (and the clipped gradients) behind autograd's back: bump the version
-            # counters so every consumer that caches by version (UNet's packed-weight cache) sees the update
-            torch.autograd.graph.increment_version(plist)
+            if not plist[0].is_cuda:
+                raise _lib.B2uError("FusedSGD needs contiguous fp32 CUDA parameters and gradients (no CPU path)")
+            with torch.cuda.device(plist[0].device):      # libb2u launches on the current device's current stream
+                self._step_group(gi, group, plist)
         return loss
+
+    def _step_group(self, gi, group, plist):
+        for p in plist:
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()
+                    and p.grad.dtype == torch.float32):
+                raise _lib.B2uError("FusedSGD needs contiguous fp32 CUDA parameters and gradients (no CPU path)")
+        # new momentum buffers are zero-initialised, so the regular update m = momentum * m + g gives torch's first-step
+        # result (m = g) exactly, per tensor -- no group-wide "first step" flag that would reset existing buffers
+        first = False
+        mlist = []
+        for p in plist:
+            st = self.state[p]
+            if "momentum_buffer" not in st:
+                st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            mlist.append(st["momentum_buffer"])
+        t_dev, c_dev, n_chunks, partial, norm = self._table(gi, plist, mlist)
+        mgn = group.get("max_grad_norm")
+        call("b2u_sgd_step", ptr(t_dev), ptr(c_dev), n_chunks, ptr(partial), float(group["lr"]), float(group["momentum"]),
+             float(mgn) if mgn else 0.0, int(first), ptr(norm), stream_ptr())
+        self.last_grad_norm = norm if mgn else None
+        # the kernels wrote the parameters (and the clipped gradients) behind autograd's back: bump the version
+        # counters so every consumer that caches by version (UNet's packed-weight cache) sees the update
+        torch.autograd.graph.increment_version(plist)

@@ -48,10 +48,13 @@ class TrainStep:
         self.fwd_graph = None
         self.bwd_graphs = None
         self.masks = None
+        self.plan = None                                   # the MaskPlan this step's CUDA graphs read: owned here, never evicted
+        self.plan_key = None
         self.seed = 0
+        self.generation = 0                                # forwards run on this workspace (a backward must match the latest)
 
-    def _signature(self, active, bs, seed):
-        return (active, bs, seed if active else 0, tuple(p.data_ptr() for _, p in self.named))
+    def _signature(self, active, bs, seed, mode):
+        return (active, bs, mode, seed if active else 0, tuple(p.data_ptr() for _, p in self.named))
 
     def _fwd_body(self):
         self.eng.load_weights(self.sd, sync=False)
@@ -65,13 +68,22 @@ class TrainStep:
         idx = xin.device.index if xin.device.index is not None else torch.cuda.current_device()
         gen = torch.cuda.default_generators[idx]
         seed = gen.initial_seed()
-        sig = self._signature(active, bs, seed)
+        mode = model._dropblock_mode()
+        sig = self._signature(active, bs, seed, mode)
         if sig != self.sig:
             self.sig, self.calls, self.fwd_graph, self.bwd_graphs = sig, 0, None, None
             self.sd = {k: q.detach() for k, q in self.named}
         self.masks, self.seed = None, seed
+        self.generation += 1
         if active:
-            self.masks = model._mask_plan(eng, 1, ws.n, ws, p, bs)
+            if self.plan is None or self.plan_key != (bs, mode):
+                # a new plan means new device pointers: the signature above changed with (bs, mode), so the graphs that
+                # captured the old plan are already dropped
+                from .engine import MaskPlan
+                self.plan = MaskPlan(1, ws.n, ws.h, ws.w, eng.filters, eng.depth, p, bs, eng.device, mode=mode)
+                self.plan_key = (bs, mode)
+            self.plan.set_drop_prob(p)
+            self.masks = self.plan
             self.masks.set_stream_position(gen.get_offset())
             gen.set_offset(gen.get_offset() + self.masks.offset_per_call)
         self.x.copy_(xin)
@@ -87,7 +99,7 @@ class TrainStep:
         else:
             self._fwd_body()
         self.calls += 1
-        model._engine_key = model._engine_signature(eng.device)     # the packed weights now match the live parameters
+        model._mark_weights_current(eng)                             # the packed weights now match the live parameters
         return ws.out.clone()
 
     def backward(self, model, grad_out: torch.Tensor):
@@ -131,7 +143,7 @@ class _UNetFunction(torch.autograd.Function):
     def forward(ctx, model, x, *params):
         from .backward import TrainBuffers
         n, _, h0, w0 = x.shape
-        eng = model._get_engine(x.device, repack=False)
+        eng = model._get_engine(x.device, repack=False, training=True)
         if not eng.training_weights:
             eng.enable_training()
         model._original_size = (h0, w0)
@@ -146,18 +158,36 @@ class _UNetFunction(torch.autograd.Function):
             ws.train_step = ts
         xin = x.detach().to(torch.float32).contiguous()
         out = ts.forward(model, xin)
-        ctx.model, ctx.ts = model, ts
+        ctx.model, ctx.ts, ctx.generation = model, ts, ts.generation
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         """The parameter gradients live in ONE flat fp32 buffer owned by the workspace (TrainBuffers.flat).  They are
         delivered by aliasing: `p.grad` becomes a view of that buffer (no 124 MB accumulate-copy per step, stable
-        pointers for the fused optimiser and the NCCL buckets).  A gradient that already exists and is NOT that view
-        (another loss term, another workspace) is accumulated into, as autograd would.  Like every framework that
-        owns its gradient buffers this assumes `zero_grad()` between steps (Lightning and the reference's loops do)."""
+        pointers for the fused optimiser and the NCCL buckets).  Autograd's accumulate semantics are kept: a gradient
+        that already exists and is NOT that view (another loss term, another workspace) is added to; one that IS the
+        view (no `zero_grad(set_to_none=True)` since the last backward: gradient accumulation, or an in-place
+        `zero_grad(set_to_none=False)`) is staged before the buffer is overwritten and added back afterwards.
+        Only `model.data_parallel = True` averages gradients over ranks; parameter hooks / a DistributedDataParallel
+        wrapper never see these gradients (they are returned as None to autograd)."""
         ts = ctx.ts
+        if ctx.generation != ts.generation:
+            raise RuntimeError("UNet backward: the activations of this forward were overwritten by a later training forward "
+                               "of the same (batch, H, W) -- forward and backward share one workspace per shape, run them "
+                               "as pairs (the reference's checkpointed blocks hold one set of activations, too)")
+        flat = ts.tb.flat
+        lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size()
+        staged = None
+        if any(p.grad is not None and lo <= p.grad.data_ptr() < hi for _, p in ts.named):
+            staged = flat.clone()                          # unconsumed (or in-place zeroed) gradients of earlier backwards
         grads = ts.backward(ctx.model, grad_out)
+        if staged is not None:
+            # only the views that are still bound as p.grad carry over; the others were consumed (set to None)
+            for (_, p), g in zip(ts.named, grads):
+                if p.grad is not None and p.grad.data_ptr() == g.data_ptr():
+                    off = (g.data_ptr() - lo) // flat.element_size()
+                    g.add_(staged[off:off + g.numel()].view_as(g))
         for (_, p), g in zip(ts.named, grads):
             if p.grad is None:
                 p.grad = g
@@ -169,8 +199,8 @@ class _UNetFunction(torch.autograd.Function):
 def unet_autograd_forward(model, x):
     """The workspace is shared between forward and backward: one forward/backward pair at a time per
     (batch, H, W), exactly like the reference's activation-checkpointed blocks hold one set of activations."""
-    if model.compute_dtype != "bf16":
-        raise NotImplementedError("training runs with compute_dtype='bf16'")
+    if model._resolve_dtype(True) != _lib.BF16:
+        raise NotImplementedError("training runs with compute_dtype='bf16' (or 'auto')")
     params = [p for _, p in model.named_parameters()]
     return _UNetFunction.apply(model, x, *params)
 

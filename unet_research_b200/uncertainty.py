@@ -106,7 +106,8 @@ class MCRunner:
         # shared-memory-bound conv CTAs leave idle.  Graph kernel nodes inherit the capture stream's priority.
         self.main = torch.cuda.Stream(device=device, priority=-1)
         self.side = torch.cuda.Stream(device=device, priority=0) if self.overlap else None
-        self.graph = None
+        self.graph = None                                  # two steps (one pair)
+        self.graph_single = None                           # one step (odd tail / one-step remainder batches)
         self.launches_per_step = 0
         self.seed = 0
         # Where in the forward the mask build of the next step is forked (engine.forward hook points).  The mask
@@ -155,8 +156,8 @@ class MCRunner:
         self.acc.zero_()
         self.samples.zero_()
         self.iter_base.fill_(t0)
-        if self.graph is not None and seed != self.seed:
-            self.graph = None                              # the Philox key is a captured kernel argument
+        if seed != self.seed:
+            self.graph = self.graph_single = None          # the Philox key is a captured kernel argument
         self.seed = seed
         if self.active:
             base = stream_start + t0 * self.per_iter
@@ -174,37 +175,54 @@ class MCRunner:
             self._run_steps(steps)
         cur.wait_stream(self.main)
 
+    def _capture(self, body):
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.main):
+            body()
+        return g
+
+    def _single(self):
+        # masks[0] already hold this step's masks (built by the prologue or by the previous pair)
+        self._forward(0)
+        if self.active and not self.overlap:
+            self._generate(0, 1)
+
     def _run_steps(self, steps: int):
+        """Replays the captured graphs; the FIRST pair / single step of a runner's life runs eagerly (sets kernel
+        attributes, counts launches) and is captured right after, so later calls -- including one-step remainder
+        batches (125 = 12 x 10 + 5 iterations per rank at 8 GPUs) -- never launch kernel by kernel."""
         pairs, odd = divmod(steps, 2)
-        if pairs:
-            if self.use_graph and self.graph is None and pairs >= 2:
-                l0 = _lib.launch_count
-                self._pair()                              # eager warm-up pair (sets kernel attributes)
-                self.launches_per_step = (_lib.launch_count - l0) // 2
-                pairs -= 1
-                torch.cuda.synchronize(self.dev)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=self.main):
-                    self._pair()
-                self.graph = g
-            for _ in range(pairs):
-                if self.graph is not None:
-                    self.graph.replay()
-                else:
-                    self._pair()
+        for _ in range(pairs):
+            if self.graph is not None:
+                self.graph.replay()
+                continue
+            l0 = _lib.launch_count
+            self._pair()
+            self.launches_per_step = (_lib.launch_count - l0) // 2
+            if self.use_graph:
+                self.graph = self._capture(self._pair)
         if odd:
-            # masks[0] already hold this step's masks (built by the prologue or by the previous pair)
-            self._forward(0)
-            if self.active and not self.overlap:
-                self._generate(0, 1)
+            if self.graph_single is not None:
+                self.graph_single.replay()
+            else:
+                l0 = _lib.launch_count
+                self._single()
+                if not self.launches_per_step:
+                    self.launches_per_step = _lib.launch_count - l0
+                if self.use_graph:
+                    self.graph_single = self._capture(self._single)
 
 
 class DropBlockEval(_MCBase):
+    MAX_RUNNERS = 4
+
     def __init__(self, model, num_iterations=1000, return_num=25, mode='save', resize=-1, iter_batch: int = 10,
-                 use_cuda_graph: bool = True, overlap_masks: bool = True):
+                 use_cuda_graph: bool = True, overlap_masks: bool = True, gather_samples: bool = False):
         super().__init__(model)
         self.num_iterations = num_iterations
         self.return_num = min(return_num, num_iterations)
+        self.gather_samples = gather_samples           # distributed runs: also deliver `tensors` on ranks != 0
         self.set_mode(mode)
         self.resize = resize
         self.iter_batch = iter_batch
@@ -219,10 +237,12 @@ class DropBlockEval(_MCBase):
     def _runner(self, nb, h0, w0, dev, active, p, bs) -> MCRunner:
         eng = self._model._get_engine(dev)              # re-packs weights if the parameters changed
         key = (nb, h0, w0, str(dev), active, p, bs, self.return_num, id(eng), self._model._dropblock_mode())
-        r = self._runners.get(key)
+        r = self._runners.pop(key, None)
         if r is None:
+            while len(self._runners) >= self.MAX_RUNNERS:      # least recently used first; a runner owns its workspace + graphs
+                self._runners.pop(next(iter(self._runners)))
             r = MCRunner(self._model, nb, h0, w0, dev, active, p, bs, self.return_num, self.use_cuda_graph, self.overlap_masks)
-            self._runners[key] = r
+        self._runners[key] = r
         return r
 
     # -------------------------------------------------------------------------------------------
@@ -234,6 +254,11 @@ class DropBlockEval(_MCBase):
             raise _lib.B2uError("MC-DropBlock runs on CUDA only")
         if im.shape[0] != 1:
             raise NotImplementedError("the reference loop is batch 1 (Dropblock_Uncertainty.py:84-85)")
+        with torch.cuda.device(im.device):             # libb2u launches on the current device's current stream
+            return self._mc_statistics(im, mask, num_iterations)
+
+    def _mc_statistics(self, im, mask, num_iterations):
+        model = self._model
         T = int(num_iterations if num_iterations is not None else self.num_iterations)
         active, p, bs = model._dropblock_state()
         dist, rank, world = _dist()
@@ -271,8 +296,10 @@ class DropBlockEval(_MCBase):
             gen.set_offset(stream_start + T * per_iter)
         if dist is not None and world > 1:
             dist.all_reduce(acc)                       # the ONE exchange step of the path (fp64 [2,H,W])
-            if R > 0:
+            if R > shard_range(T, 0, world)[1] or self.gather_samples:
                 dist.all_reduce(samples)               # disjoint writers (zeros elsewhere): a sum is a gather
+            # else: rank 0 owns iterations [0, R) -- the block partition puts them there -- so `tensors` is
+            # complete on rank 0, the rank that saves it, and the 33 MB exchange is skipped (other ranks return zeros)
         mean = torch.empty(1, 1, h0, w0, dtype=torch.float32, device=dev)
         std = torch.empty(1, 1, h0, w0, dtype=torch.float32, device=dev)
         if T > 1:
@@ -298,67 +325,152 @@ class DropBlockEval(_MCBase):
         return batch_idx, mean, im, gt, mask
 
 
-class RotationEval(_MCBase):
-    """Angles 1..num_iterations degrees: rotate in -> eval forward -> rotate back -> * mask -> mean/std."""
+class RotationRunner:
+    """Persistent state of the rotation-ensemble loop for one (model, angle batch, image size): workspace, rotated-input
+    buffer, device angle tables, accumulators and ONE CUDA graph per step
 
-    def __init__(self, model, num_iterations=1000, return_num=25, resize=-1, angle_batch: int = 5):
+        rotate-in (angles from the device table at *iter_base) -> eval forward -> rotate-back * fov -> fp64 accumulate
+        (+ the first return_num samples) -> advance iter_base
+
+    so the 359-angle loop of BASELINE configs[3] is 72 graph replays with nothing allocated and no host tables built."""
+
+    def __init__(self, model, nb: int, cin: int, h0: int, w0: int, device, return_num: int, use_cuda_graph: bool = True):
+        self.model, self.nb, self.cin, self.h0, self.w0, self.dev = model, nb, cin, h0, w0, device
+        self.eng: UNetEngine = model._get_engine(device)
+        self.ws = self.eng.workspace(nb, h0, w0)
+        self.R = return_num
+        self.use_graph = use_cuda_graph
+        self.x1 = torch.zeros(cin, h0, w0, dtype=torch.float32, device=device)
+        self.rot_in = torch.zeros(nb, cin, h0, w0, dtype=torch.float32, device=device)
+        self.fov = torch.zeros(h0, w0, dtype=torch.float32, device=device)
+        self.acc = torch.zeros(2, h0, w0, dtype=torch.float64, device=device)
+        self.samples = torch.zeros(max(return_num, 1), h0, w0, dtype=torch.float32, device=device)
+        self.iter_base = torch.zeros(1, dtype=torch.int64, device=device)
+        self.iter_limit = torch.zeros(1, dtype=torch.int64, device=device)
+        self.table_len = 0
+        self.tab_in = self.tab_out = None
+        self.graph = None
+        self.launches_per_step = 0
+
+    def _tables(self, total: int):
+        """Rows i = 0..total-1 hold angle (i + 1) degrees (Rotational_Uncertainty.py:51: range(1, T + 1)) for the
+        rotate-in and angle -(i + 1) for the rotate-back."""
+        import ctypes as C
+        if total <= self.table_len:
+            return
+        n = max(total, 360)
+        host = (C.c_float * (6 * n))()
+        for sign, name in ((1.0, "tab_in"), (-1.0, "tab_out")):
+            ang = (C.c_double * n)(*[sign * float(i + 1) for i in range(n)])
+            call("b2u_rotation_table", ang, n, self.h0, self.w0, host)
+            t = torch.frombuffer(bytearray(host), dtype=torch.float32).clone().to(self.dev)
+            setattr(self, name, t)
+        self.table_len = n
+        self.graph = None                                  # table pointers are captured kernel arguments
+
+    def begin(self, im: torch.Tensor, fov: torch.Tensor, t0: int, t1: int, total: int):
+        self._tables(total)
+        self.x1.copy_(im.detach().to(torch.float32).reshape(self.cin, self.h0, self.w0))
+        self.fov.copy_(fov.reshape(self.h0, self.w0))
+        self.acc.zero_()
+        self.samples.zero_()
+        self.iter_base.fill_(t0)
+        self.iter_limit.fill_(t1)
+
+    def _step(self):
+        st = stream_ptr()
+        call("b2u_rotate_in_table", ptr(self.x1), ptr(self.rot_in), self.nb, self.cin, self.h0, self.w0, ptr(self.tab_in),
+             self.table_len, ptr(self.iter_base), st)
+        seg = self.eng.forward(self.rot_in, self.ws, None)      # eval forward, DropBlock is Identity (:122)
+        call("b2u_rotate_back_accumulate", ptr(seg), ptr(self.fov), ptr(self.acc), ptr(self.samples) if self.R > 0 else None,
+             self.nb, self.h0, self.w0, self.R, ptr(self.tab_out), self.table_len, ptr(self.iter_base), ptr(self.iter_limit), st)
+        call("b2u_advance_counter", ptr(self.iter_base), self.nb, st)
+
+    def run_steps(self, steps: int):
+        for _ in range(steps):
+            if self.graph is not None:
+                self.graph.replay()
+                continue
+            l0 = _lib.launch_count
+            self._step()
+            self.launches_per_step = _lib.launch_count - l0
+            if self.use_graph:
+                torch.cuda.synchronize(self.dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step()
+                self.graph = g
+
+
+class RotationEval(_MCBase):
+    """Angles 1..num_iterations degrees: rotate in -> eval forward -> rotate back -> * mask -> mean/std
+    (Rotational_Uncertainty.py:21-68), angles sharded over torch.distributed ranks like the MC iterations."""
+    MAX_RUNNERS = 3
+
+    def __init__(self, model, num_iterations=1000, return_num=25, resize=-1, angle_batch: int = 5, use_cuda_graph: bool = True,
+                 gather_samples: bool = False):
         super().__init__(model)
         self.num_iterations = num_iterations
         self.return_num = min(return_num, num_iterations)
         self.resize = resize
         self.angle_batch = angle_batch
+        self.use_cuda_graph = use_cuda_graph
+        self.gather_samples = gather_samples
+        self._runners = {}
+
+    def _runner(self, nb, cin, h0, w0, dev) -> RotationRunner:
+        eng = self._model._get_engine(dev)              # re-packs weights if the parameters changed
+        key = (nb, cin, h0, w0, str(dev), self.return_num, id(eng))
+        r = self._runners.pop(key, None)
+        if r is None:
+            while len(self._runners) >= self.MAX_RUNNERS:
+                self._runners.pop(next(iter(self._runners)))
+            r = RotationRunner(self._model, nb, cin, h0, w0, dev, self.return_num, self.use_cuda_graph)
+        self._runners[key] = r
+        return r
 
     def rotation_statistics(self, im: torch.Tensor, mask: torch.Tensor, num_iterations: Optional[int] = None):
-        import ctypes as C
-        model = self._model
         if not im.is_cuda:
             raise _lib.B2uError("the rotation ensemble runs on CUDA only")
         if im.shape[0] != 1:
             raise NotImplementedError("the reference loop is batch 1")
+        with torch.cuda.device(im.device):
+            return self._rotation_statistics(im, mask, num_iterations)
+
+    def _rotation_statistics(self, im, mask, num_iterations):
         T = int(num_iterations if num_iterations is not None else self.num_iterations)
         dist, rank, world = _dist()
         t0, t1 = shard_range(T, rank, world)
         dev = im.device
-        eng: UNetEngine = model._get_engine(dev)
         _, cin, h0, w0 = im.shape
         npix = h0 * w0
-        acc = torch.zeros(2, h0, w0, dtype=torch.float64, device=dev)
         R = self.return_num
-        samples = torch.zeros(max(R, 1), h0, w0, dtype=torch.float32, device=dev)
-        fov = mask.reshape(h0, w0).to(torch.float32).contiguous()
-        iter_base = torch.full((1,), t0, dtype=torch.int64, device=dev)
-        x1 = im.detach().to(torch.float32).contiguous()
-        done = t0
-        while done < t1:
-            nb = min(self.angle_batch, t1 - done)
-            ws = eng.workspace(nb, h0, w0)
-            rot_in = torch.empty(nb, cin, h0, w0, dtype=torch.float32, device=dev)
-            rot_out = torch.empty(nb, 1, h0, w0, dtype=torch.float32, device=dev)
-            steps = (t1 - done) // nb
-            for s in range(steps):
-                first = done + s * nb + 1                                   # angles are 1-based (:51)
-                ang_in = (C.c_double * nb)(*[float(first + k) for k in range(nb)])
-                ang_out = (C.c_double * nb)(*[-float(first + k) for k in range(nb)])
-                call("b2u_rotate_bilinear", ptr(x1), ptr(rot_in), nb, cin, h0, w0, ang_in, 1, stream_ptr())
-                seg = eng.forward(rot_in, ws, None)                          # eval forward, DropBlock is Identity (:122)
-                call("b2u_rotate_bilinear", ptr(seg), ptr(rot_out), nb, 1, h0, w0, ang_out, 0, stream_ptr())
-                call("b2u_mc_accumulate", ptr(rot_out), ptr(fov), ptr(acc), ptr(samples) if R > 0 else None, ptr(iter_base),
-                     nb, npix, R, stream_ptr())
-                call("b2u_advance_counter", ptr(iter_base), nb, stream_ptr())
-            done += steps * nb
+        nb = max(1, min(self.angle_batch, -(-T // world)))
+        r = self._runner(nb, cin, h0, w0, dev)
+        r.begin(im, mask.to(torch.float32), t0, t1, T)
+        r.run_steps(-(-(t1 - t0) // nb))               # the tail images of the last step are skipped by *iter_limit
+        acc, samples = r.acc, r.samples
         if dist is not None and world > 1:
             dist.all_reduce(acc)
-            if R > 0:
+            if R > shard_range(T, 0, world)[1] or self.gather_samples:
                 dist.all_reduce(samples)
         mean = torch.empty(1, 1, h0, w0, dtype=torch.float32, device=dev)
         std = torch.empty(1, 1, h0, w0, dtype=torch.float32, device=dev)
-        call("b2u_mc_finalize", ptr(acc), ptr(mean), ptr(std), npix, T, stream_ptr())
+        if T > 1:
+            call("b2u_mc_finalize", ptr(acc), ptr(mean), ptr(std), npix, T, stream_ptr())
+        else:
+            mean.copy_(acc[0].view(1, 1, h0, w0))
+            std.fill_(float("nan"))                    # torch.std of one sample
         tensors = samples[:R].view(R, 1, 1, h0, w0).clone()
         return mean, std, tensors
 
     def predict_step(self, batch, batch_idx):
         im, gt, mask = batch
         if self.resize != -1:
-            raise NotImplementedError("on-the-fly resize is a 'next' row (SURVEY 8f)")
+            # Rotational_Uncertainty.py:39-49: pad to square, resize im / gt / mask on the fly (one fused kernel each)
+            from .resize import square_pad_resize
+            im = square_pad_resize(im, self.resize)
+            gt = square_pad_resize(gt, self.resize) if gt is not None else None
+            mask = square_pad_resize(mask, self.resize)
         mean, std, tensors = self.rotation_statistics(im, mask)
         return batch_idx, (mean, std, tensors)
