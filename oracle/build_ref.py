@@ -3,10 +3,11 @@
 imported on the GPU box, where /root/reference does not exist.
 
 Recipe (run by `__graft_entry__.build()` whenever /root/reference is present): `py_compile` of the files listed below,
-read where they lie under /root/reference, outputs ONLY under `oracle/_ref/unet_code/...` as sourceless `.pyc` files
-(CPython imports `module.pyc` next to a missing `module.py`).  No reference SOURCE is copied: `oracle/_ref/` holds
-compiled artefacts, is git-ignored, and travels to the GPU box like the repo's own built `.so`.  The bytecode is tied to
-the interpreter that built it (same image here and on the box: CPython 3.12); a mismatch makes the import fail loudly.
+read where they lie under /root/reference, outputs ONLY under `oracle/_ref/unet_code/...` as CPython byte-code files
+(`<module>.bytecode` = the .pyc format; loaded by `oracle/ref_shims.py` with `SourcelessFileLoader`; the `.pyc` suffix is
+avoided because snapshot tools commonly drop it).  No reference SOURCE is copied: `oracle/_ref/` holds compiled
+artefacts, is git-ignored, and travels to the GPU box like the repo's own built `.so`.  The bytecode is tied to the
+interpreter that built it (same image here and on the box: CPython 3.12); a mismatch makes the import fail loudly.
 """
 from __future__ import annotations
 
@@ -17,6 +18,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_CODE = "/root/reference/Unet_research/unet_code"
 OUT_CODE = os.path.join(HERE, "_ref", "unet_code")
+EXT = ".bytecode"
 
 # the files on the hot path plus the helper modules they import at module level
 FILES = [
@@ -32,7 +34,7 @@ def ref_available() -> bool:
 
 
 def built() -> bool:
-    return all(os.path.exists(os.path.join(OUT_CODE, f[:-3] + ".pyc")) for f in FILES)
+    return all(os.path.exists(os.path.join(OUT_CODE, f[:-3] + EXT)) for f in FILES)
 
 
 def build_ref(force: bool = False) -> bool:
@@ -41,7 +43,7 @@ def build_ref(force: bool = False) -> bool:
         return built()
     for rel in FILES:
         src = os.path.join(REF_CODE, rel)
-        dst = os.path.join(OUT_CODE, rel[:-3] + ".pyc")
+        dst = os.path.join(OUT_CODE, rel[:-3] + EXT)
         if not force and os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(src):
             continue
         os.makedirs(os.path.dirname(dst), exist_ok=True)

@@ -2,7 +2,7 @@
 shims for the five packages the image lacks.  None of the shims changes
 arithmetic.  Two locations are tried: /root/reference (this container: the sources where they lie)
 and `oracle/_ref/` (the GPU box: sourceless byte-code compiled from those sources by
-`oracle/build_ref.py`; git-ignored, travels like the built `.so`).  Used by
+`oracle/build_ref.py`; git-ignored, travels like the built `.so`; loaded module by module with SourcelessFileLoader).  Used by
 `tests/golden/make_golden.py`, by the tests that run the reference's own classes, and by
 `bench.py --impl reference` / its `cpu_baseline` leg.
 """
@@ -155,26 +155,53 @@ def load_reference(prefer: str = None):
     if _LOADED:
         raise RuntimeError("the reference is already loaded from the other location in this process")
     code = os.path.join(root, "unet_code")
-    ext = ".py" if kind == "source" else ".pyc"
     _install_shims()
-    if code not in sys.path:
-        sys.path.insert(0, code)
     cwd = os.getcwd()
-    os.chdir(root)              # scripts do sys.path.append(os.getcwd() + '/unet_code')
-    try:
-        from utils import utils_unet, utils_modules, utils_training  # type: ignore
+    if kind == "source":
+        if code not in sys.path:
+            sys.path.insert(0, code)
+        os.chdir(root)          # scripts do sys.path.append(os.getcwd() + '/unet_code')
+        try:
+            from utils import utils_unet, utils_modules, utils_training  # type: ignore
 
-        def load_script(name, rel):
-            spec = importlib.util.spec_from_file_location(name, os.path.join(code, rel[:-3] + ext))
+            def load_script(name, rel):
+                spec = importlib.util.spec_from_file_location(name, os.path.join(code, rel))
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                return mod
+
+            db = load_script("ref_dropblock_uncertainty", "uncertainty_tests/Dropblock_Uncertainty.py")
+            rot = load_script("ref_rotational_uncertainty", "uncertainty_tests/Rotational_Uncertainty.py")
+            tr = load_script("ref_training", "base_model_tests/training.py")
+        finally:
+            os.chdir(cwd)
+    else:
+        # byte-code: no path finder involved -- every module is loaded explicitly, in dependency order, under the name
+        # the reference's own `from utils.utils_x import ...` statements expect
+        from importlib.machinery import SourcelessFileLoader
+        from . import build_ref
+
+        def load_bc(name, rel):
+            path = os.path.join(code, rel[:-3] + build_ref.EXT)
+            loader = SourcelessFileLoader(name, path)
+            spec = importlib.util.spec_from_loader(name, loader, origin=path)
             mod = importlib.util.module_from_spec(spec)
-            spec.loader.exec_module(mod)
+            sys.modules[name] = mod
+            loader.exec_module(mod)
             return mod
 
-        db = load_script("ref_dropblock_uncertainty", "uncertainty_tests/Dropblock_Uncertainty.py")
-        rot = load_script("ref_rotational_uncertainty", "uncertainty_tests/Rotational_Uncertainty.py")
-        tr = load_script("ref_training", "base_model_tests/training.py")
-    finally:
-        os.chdir(cwd)
+        if "utils" not in sys.modules:
+            pkg = types.ModuleType("utils")
+            pkg.__path__ = []                       # a package without a search path: only what is registered below
+            sys.modules["utils"] = pkg
+        mods = {}
+        for leaf in ("utils_modules", "utils_unet", "utils_training", "utils_general", "utils_dataset", "utils_metrics"):
+            mods[leaf] = load_bc("utils." + leaf, f"utils/{leaf}.py")
+            setattr(sys.modules["utils"], leaf, mods[leaf])
+        utils_unet, utils_modules, utils_training = mods["utils_unet"], mods["utils_modules"], mods["utils_training"]
+        db = load_bc("ref_dropblock_uncertainty", "uncertainty_tests/Dropblock_Uncertainty.py")
+        rot = load_bc("ref_rotational_uncertainty", "uncertainty_tests/Rotational_Uncertainty.py")
+        tr = load_bc("ref_training", "base_model_tests/training.py")
     ns = types.SimpleNamespace(
         UNet=utils_unet.UNet, DropBlock2D=utils_modules.DropBlock2D,
         Dropblock2d_ichan=utils_modules.Dropblock2d_ichan, LinearScheduler=utils_modules.LinearScheduler,

@@ -13,6 +13,7 @@ from oracle import unet_oracle as O
 from unet_research_b200 import synthetic
 
 H, W = 120, 116
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _load(golden_dir, name):
@@ -212,3 +213,27 @@ def test_square_pad_resize_restatement_matches_torchvision():
     assert sp.shape[-2:] == (584, 584) and float(sp[..., :, :10].abs().max()) == 0.0 and float(sp[..., :, -9:].abs().max()) == 0.0
     for s in (128, 256, 584):
         np.testing.assert_allclose(O.square_pad_resize(x, s).numpy(), TF.resize(sp, size=(s, s)).numpy(), rtol=0, atol=1e-6)
+
+
+def test_reference_bytecode_matches_source(golden_dir):
+    """oracle/_ref (byte-code of the unmodified reference, built by oracle/build_ref.py: what the GPU box imports) is
+    complete and, loaded in a fresh process, reproduces the golden eval forward bit for bit."""
+    import subprocess
+    import sys
+    from oracle import build_ref
+    if not build_ref.built():
+        if not build_ref.ref_available():
+            pytest.skip("oracle/_ref not built and /root/reference absent")
+        assert build_ref.build_ref()
+    code = (
+        "import sys, numpy as np, torch; sys.path.insert(0, %r)\n"
+        "from oracle import ref_shims as R\n"
+        "from unet_research_b200 import synthetic\n"
+        "ref = R.load_reference(prefer='bytecode'); assert ref.kind == 'bytecode'\n"
+        "u = R.build_reference_unet(ref); u.load_state_dict(synthetic.make_state_dict(seed=1234)); u.eval()\n"
+        "g = np.load(%r)\n"
+        "with torch.no_grad(): y = u(synthetic.make_image(120, 116, seed=1234))\n"
+        "assert np.array_equal(y.numpy(), g['output']), float(np.abs(y.numpy() - g['output']).max())\n"
+        "print('BYTECODE OK')\n") % (ROOT, os.path.join(golden_dir, "unet_eval_120x116.npz"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd="/tmp")
+    assert r.returncode == 0 and "BYTECODE OK" in r.stdout, r.stderr[-2000:]
