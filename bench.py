@@ -786,7 +786,7 @@ def time_conv_kernels(runner, dev, reps):
     for name, s, e in records:
         tot[name] = tot.get(name, 0.0) + s.elapsed_time(e)
     per_step = {k: v / reps for k, v in tot.items()}
-    conv = per_step.pop("b2u_conv3x3_fwd", 0.0) + per_step.pop("b2u_convT2x2_fwd", 0.0)
+    conv = per_step.pop("b2u_conv3x3_fwd", 0.0) + per_step.pop("b2u_conv3x3_pro_fwd", 0.0) + per_step.pop("b2u_convT2x2_fwd", 0.0)
     return conv, per_step
 
 

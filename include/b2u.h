@@ -76,6 +76,16 @@ int b2u_convT2x2_stat_layout(const b2u_conv_desc* d, int* rows_per_image, int* s
 /* x: [n,h,w,x_cstride]; wpacked: [9][cout][cin]; y: [n,h,w,cout]; partials may be NULL iff num_groups==0 */
 int b2u_conv3x3_fwd(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d,
                     void* stream);
+/* The same convolution with the producer's normalisation fused into its A-operand path (north_star: "Norm, ReLU,
+ * DropBlock mask-apply ... fused into the conv prologues"; reference order Conv -> GroupNorm -> DropBlock -> ReLU -> next
+ * Conv, utils_unet.py:166-182): x_raw is the RAW output of the producing conv (or max-pool) [n,h,w,cin]; transform warps
+ * rewrite every TMA-landed halo patch in shared memory as  act = [relu]((a*x + b) * keep)  -- coef float2[n][cin] from
+ * b2u_gn_finalize (DropBlock rescale folded in), mask_bits the NHWC keep bits of that unit's DropBlock site or NULL --
+ * before the tensor core reads it; pixels outside the image stay zero (the zero padding applies to the ACTIVATED
+ * tensor).  Bit-identical to b2u_gn_apply followed by b2u_conv3x3_fwd; the activated tensor is never written to HBM.
+ * 16-bit formats only.  x_shared != 0: all n images read the raw tensor of image 0 (shared first conv of the MC loop). */
+int b2u_conv3x3_pro_fwd(const void* x_raw, const float* coef, const void* mask_bits, const void* wpacked, void* y,
+                        float* partials, const b2u_conv_desc* d, int relu, int x_shared, void* stream);
 /* x: [n,h,w,x_cstride]; wpacked: [4][cout][cin]; y: [n,2h,2w,cout] */
 int b2u_convT2x2_fwd(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d,
                      void* stream);

@@ -86,6 +86,70 @@ def _conv_case(n, h, w, cin, cout, dtype, conv_t=False, block_n=0, stages=0, ver
     return {"rel": r, "stats_rel": sr, "nan": nan}
 
 
+def _conv_pro_case(n, h, w, cin, cout, dtype, relu=True, masked=True, x_shared=False, block_n=0, mt=0):
+    """Fused conv prologue (b2u_conv3x3_pro_fwd) against the two-pass schedule it replaces (b2u_gn_apply -> b2u_conv3x3_fwd)
+    on the same raw tensor, coefficients and keep bits: outputs and GroupNorm partials must be BIT-IDENTICAL (same operand
+    values, same MMA order); border tiles, ragged sizes and the zero-padding-after-affine rule are covered by h, w not
+    being tile multiples and by coefficients with b != 0 (a padded pixel must contribute 0, not relu(b))."""
+    import torch
+    from unet_research_b200 import _lib
+    from unet_research_b200._lib import ApplyDesc, ConvDesc, call, ptr, stream_ptr
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(cin * 7 + cout + h + w)
+    tdt = torch.float16 if dtype == _lib.F16 else torch.bfloat16
+    nx = 1 if x_shared else n
+    raw = torch.randn(nx, h, w, cin, generator=g).to(dev).to(tdt)
+    coef = torch.stack([0.5 + torch.rand(n, cin, generator=g), torch.rand(n, cin, generator=g) - 0.3], -1).to(dev).contiguous()
+    mask = None
+    if masked:
+        mask = torch.randint(-2 ** 31, 2 ** 31 - 1, (n, h, w, cin // 32), generator=g, dtype=torch.int64).to(torch.int32).to(dev)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / ((9 * cin) ** 0.5)).to(dev)
+    packed = torch.empty(9, cout, cin, dtype=tdt, device=dev)
+    call("b2u_pack_conv3x3_weight", ptr(wt), ptr(packed), cout, cin, dtype, 0, stream_ptr())
+    d = ConvDesc()
+    d.n, d.h, d.w, d.cin, d.cout, d.dtype, d.num_groups, d.x_cstride = n, h, w, cin, cout, dtype, 32, cin
+    d.reserved[0], d.reserved[3] = block_n, mt
+    rows, sgs = C.c_int(0), C.c_int(0)
+    call("b2u_conv3x3_stat_layout", C.byref(d), C.byref(rows), C.byref(sgs))
+    outs = []
+    for fused in (False, True):
+        y = torch.full((n, h, w, cout), float("nan"), dtype=tdt, device=dev)
+        parts = torch.full((n, rows.value, cout // sgs.value, 2), float("nan"), dtype=torch.float32, device=dev)
+        if fused:
+            call("b2u_conv3x3_pro_fwd", ptr(raw), ptr(coef), ptr(mask), ptr(packed), ptr(y), ptr(parts), C.byref(d), int(relu),
+                 int(x_shared), stream_ptr())
+        else:
+            act = torch.empty(n, h, w, cin, dtype=tdt, device=dev)
+            a = ApplyDesc()
+            a.n, a.h, a.w, a.c, a.dtype, a.relu, a.out_cstride, a.out_coffset = n, h, w, cin, dtype, int(relu), cin, 0
+            a.images_per_call2, a.numel_per_call2 = 1, 0.0
+            a.reserved[0] = 1 if x_shared else 0
+            call("b2u_gn_apply", ptr(raw), ptr(coef), ptr(mask), None, None, ptr(act), C.byref(a), stream_ptr())
+            call("b2u_conv3x3_fwd", ptr(act), ptr(packed), ptr(y), ptr(parts), C.byref(d), stream_ptr())
+        torch.cuda.synchronize()
+        outs.append((y, parts))
+    (y0, p0), (y1, p1) = outs
+    nan = int(torch.isnan(y1.float()).sum())
+    same = bool(torch.equal(y0, y1)) and bool(torch.equal(p0, p1))
+    dmax = float((y0.float() - y1.float()).abs().max())
+    print(f"  conv3-pro n{n} {h}x{w} {cin}->{cout} dt{dtype} relu{int(relu)} mask{int(masked)} shared{int(x_shared)} bn{block_n} mt{mt}: "
+          f"identical {same} max|d| {dmax:.3e} nan {nan}")
+    return {"identical": same, "max": dmax, "nan": nan}
+
+
+def sec_convpro():
+    from unet_research_b200 import _lib
+    for dt in (_lib.BF16, _lib.F16):
+        _conv_pro_case(1, 16, 16, 64, 64, dt)
+        _conv_pro_case(2, 33, 47, 64, 64, dt)
+        _conv_pro_case(3, 24, 40, 64, 64, dt, x_shared=True)
+        _conv_pro_case(2, 37, 36, 128, 128, dt)
+        _conv_pro_case(2, 20, 24, 64, 128, dt, relu=False, masked=False)
+        _conv_pro_case(1, 37, 36, 512, 1024, dt)
+        _conv_pro_case(1, 74, 72, 256, 256, dt)
+        _conv_pro_case(1, 33, 47, 128, 256, dt, block_n=128, mt=1)
+
+
 def sec_conv():
     from unet_research_b200 import _lib
     _conv_case(1, 16, 16, 64, 64, _lib.BF16)

@@ -35,6 +35,39 @@ def test_conv3x3_bf16(case):
     assert r["nan"] == 0 and r["rel"] < 3e-3 and r["stats_rel"] < 1e-4
 
 
+@pytest.mark.parametrize("case", [
+    dict(n=1, h=16, w=16, cin=64, cout=64), dict(n=2, h=33, w=47, cin=64, cout=64), dict(n=3, h=24, w=40, cin=64, cout=64, x_shared=True),
+    dict(n=2, h=37, w=36, cin=128, cout=128), dict(n=2, h=20, w=24, cin=64, cout=128, relu=False, masked=False),
+    dict(n=1, h=37, w=36, cin=512, cout=1024), dict(n=1, h=74, w=72, cin=256, cout=256), dict(n=1, h=33, w=47, cin=128, cout=256, block_n=128, mt=1),
+    dict(n=1, h=592, w=576, cin=64, cout=64)])
+@pytest.mark.parametrize("dtype", [_lib.BF16, _lib.F16])
+def test_conv3x3_fused_prologue_bit_identical(case, dtype):
+    """b2u_conv3x3_pro_fwd (GroupNorm affine + DropBlock mask + ReLU applied to the TMA-landed patch in shared memory)
+    == b2u_gn_apply followed by b2u_conv3x3_fwd, bit for bit -- incl. border pixels (zero padding re-imposed AFTER the
+    affine: reference order Conv -> GroupNorm -> DropBlock -> ReLU -> zero-padded Conv, utils_unet.py:166-182)."""
+    r = D._conv_pro_case(dtype=dtype, **case)
+    assert r["nan"] == 0 and r["identical"], r
+
+
+def test_fused_and_unfused_schedules_agree():
+    """The whole MC forward with the fused prologue (default) and with B2U_FUSED=0 semantics (engine.fused_prologue = False):
+    same Philox stream, bit-identical samples."""
+    import unet_research_b200 as U
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    x = synthetic.make_image(146, 141, seed=1234).to(dev)
+    fov = synthetic.make_fov_mask(146, 141).to(dev)
+    outs = []
+    for fused in (True, False):
+        m, _ = D._build_model(dev, dropblock=True)
+        m._get_engine(dev).fused_prologue = fused
+        ev = U.DropBlockEval(m, num_iterations=4, return_num=4, iter_batch=2)
+        torch.manual_seed(3)
+        _, (mean, std, tens) = ev.predict_step((x, None, fov), 0)
+        outs.append(tens)
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("bn,stages", [(64, 0), (128, 2), (64, 3)])
 def test_conv3x3_tile_overrides(bn, stages):
     r = D._conv_case(1, 33, 47, 128, 256, _lib.BF16, block_n=bn, stages=stages)

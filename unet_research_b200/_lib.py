@@ -75,6 +75,7 @@ SIGNATURES = {
     "b2u_conv3x3_stat_layout": (_I, [C.POINTER(ConvDesc), C.POINTER(_I), C.POINTER(_I)]),
     "b2u_convT2x2_stat_layout": (_I, [C.POINTER(ConvDesc), C.POINTER(_I), C.POINTER(_I)]),
     "b2u_conv3x3_fwd": (_I, [_P, _P, _P, _P, C.POINTER(ConvDesc), _P]),
+    "b2u_conv3x3_pro_fwd": (_I, [_P, _P, _P, _P, _P, _P, C.POINTER(ConvDesc), _I, _I, _P]),
     "b2u_convT2x2_fwd": (_I, [_P, _P, _P, _P, C.POINTER(ConvDesc), _P]),
     "b2u_conv_first_stat_layout": (_I, [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I)]),
     "b2u_conv_first_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
@@ -114,7 +115,7 @@ SIGNATURES = {
 
 _lib: Optional[C.CDLL] = None
 launch_count = 0          # kernels launched through this binding (bench.py reports it as gpu_launches)
-_LAUNCHERS = {"b2u_conv3x3_fwd": 1, "b2u_convT2x2_fwd": 1, "b2u_conv_first_fwd": 1, "b2u_gn_finalize": 1, "b2u_gn_finalize_ex": 1,
+_LAUNCHERS = {"b2u_conv3x3_fwd": 1, "b2u_conv3x3_pro_fwd": 1, "b2u_convT2x2_fwd": 1, "b2u_conv_first_fwd": 1, "b2u_gn_finalize": 1, "b2u_gn_finalize_ex": 1,
               "b2u_gn_apply": 1, "b2u_gn_apply_pool": 1, "b2u_head_fwd": 1, "b2u_mc_finalize": 1,
               "b2u_mc_accumulate": 1, "b2u_advance_counter": 1, "b2u_dropblock_centers": 1,
               "b2u_dropblock_dilate": 1, "b2u_dropblock_centers_ichan": 1, "b2u_dropblock_centers_from_uniform": 1, "b2u_rotate_bilinear": 1, "b2u_rotate_in_table": 1, "b2u_rotate_back_accumulate": 1,

@@ -91,6 +91,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---- explicit shared-space 16-byte accesses (a pointer re-derived through an integer cast makes nvcc emit GENERIC
+// LD.E / ST.E for shared memory; these stay LDS.128 / STS.128)
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ---- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -321,7 +332,17 @@ template <> __device__ __forceinline__ float to_operand<float>(float x) { return
 // fp16 operands (kind::f16 with the F16 format): 11-bit mantissa at bf16 speed; values are saturated to the finite
 // range instead of overflowing to inf (post-GroupNorm activations and kaiming-scale weights are O(1))
 __device__ __forceinline__ float sat_f16(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
-template <> __device__ __forceinline__ __half to_operand<__half>(float x) { return __float2half_rn(sat_f16(x)); }
+// two floats -> packed fp16x2, round-to-nearest-even, saturated to +-65504 in ONE instruction (F2FP.SATFINITE): the
+// explicit fmin / fmax pair per element cost the fp16 mode 64 extra instructions per 32-column epilogue chunk
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <> __device__ __forceinline__ __half to_operand<__half>(float x) {
+  const uint32_t r = pack_half2_sat(x, 0.f);
+  return __ushort_as_half(static_cast<unsigned short>(r & 0xFFFFu));
+}
 
 // Storage format of a tensor-core kernel: 0 = bf16, 1 = fp32 storage / tf32 math, 2 = fp16 (== the B2U_* dtype codes)
 template <int F> struct FmtTraits;
@@ -356,15 +377,11 @@ template <> __device__ __forceinline__ void store_chunk32<__half>(__half* dst, c
   uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    __half2 a = __floats2half2_rn(sat_f16(x[8 * i]), sat_f16(x[8 * i + 1]));
-    __half2 b = __floats2half2_rn(sat_f16(x[8 * i + 2]), sat_f16(x[8 * i + 3]));
-    __half2 c = __floats2half2_rn(sat_f16(x[8 * i + 4]), sat_f16(x[8 * i + 5]));
-    __half2 d = __floats2half2_rn(sat_f16(x[8 * i + 6]), sat_f16(x[8 * i + 7]));
     uint4 v;
-    v.x = *reinterpret_cast<uint32_t*>(&a);
-    v.y = *reinterpret_cast<uint32_t*>(&b);
-    v.z = *reinterpret_cast<uint32_t*>(&c);
-    v.w = *reinterpret_cast<uint32_t*>(&d);
+    v.x = pack_half2_sat(x[8 * i], x[8 * i + 1]);
+    v.y = pack_half2_sat(x[8 * i + 2], x[8 * i + 3]);
+    v.z = pack_half2_sat(x[8 * i + 4], x[8 * i + 5]);
+    v.w = pack_half2_sat(x[8 * i + 6], x[8 * i + 7]);
     d4[i] = v;
   }
 }
@@ -434,9 +451,10 @@ template <> struct Vec8<__half> {
     }
   }
   __device__ __forceinline__ void from_float(const float (&f)[8]) {
-    __half2* h = reinterpret_cast<__half2*>(&raw);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(sat_f16(f[2 * i]), sat_f16(f[2 * i + 1]));
+    raw.x = pack_half2_sat(f[0], f[1]);
+    raw.y = pack_half2_sat(f[2], f[3]);
+    raw.z = pack_half2_sat(f[4], f[5]);
+    raw.w = pack_half2_sat(f[6], f[7]);
   }
 };
 template <> struct Vec8<float> {

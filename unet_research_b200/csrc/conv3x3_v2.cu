@@ -22,6 +22,14 @@
 
 namespace b2u {
 
+// Division by a launch-invariant divisor as one IMAD.HI: q = (n * mul) >> 32 with mul = floor(2^32 / d) + 1, exact for
+// n * d < 2^32 (the host checks it).  The transform warps locate a patch with three of them instead of three ~30
+// instruction software divisions.
+__device__ __forceinline__ int fd_div(int n, uint32_t mul) {      // mul == 0 encodes d == 1
+  return mul ? static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul)) : n;
+}
+static inline uint32_t fd_make(int d) { return d <= 1 ? 0u : static_cast<uint32_t>((1ull << 32) / static_cast<unsigned>(d)) + 1u; }
+
 struct ConvV2Params {
   int n, h, w;                // image grid
   int tiles_w, tiles_h;       // 8 x 16 tiles per image
@@ -35,12 +43,42 @@ struct ConvV2Params {
   int resident_b;             // 1: the whole filter (9 * kc_chunks stages, one N tile) stays in shared memory for the CTA's lifetime
   void* y;
   float* partials;            // [n][tiles_per_image][cout/sgs][2]
+  // fused A-operand prologue (kPro kernels): x is the RAW output of the producing conv / pool; the transform warps rewrite
+  // every TMA-landed patch in shared memory as act = [relu]((a * x + b) * keep) before the MMA warp may read it
+  const float2* pro_coef;     // [n][cin] (a, b) of the producer's GroupNorm (DropBlock rescale folded in)
+  const uint8_t* pro_mask;    // NHWC keep bits of the producer's DropBlock site, [n][h][w][cin / 8] bytes, or nullptr
+  int pro_relu;
+  int x_shared;               // 1: every image reads the activation tensor of image 0 (Monte-Carlo: shared first conv)
+  int cin;
+  uint32_t fd_mgroups, fd_tpi, fd_tw;   // fd_make(num_mgroups), fd_make(tiles per image), fd_make(tiles_w)
 };
 
 constexpr int kPatchRows = 180;                      // (16 + 2) * (8 + 2)
 constexpr int kPatchBytes = kPatchRows * 128;        // 23040
 constexpr int kPatchStride = 23552;                  // rounded up to the 1024 B swizzle-atom alignment
 constexpr int kV2Threads = 224;
+constexpr int kProWarps = 4;                         // transform warps of the fused-prologue kernels (warps 7 .. 10)
+constexpr int kV2ThreadsPro = kV2Threads + 32 * kProWarps;
+
+// ---- fused prologue: one 16-byte vector (8 channels of one patch pixel) through GroupNorm affine, DropBlock, ReLU.
+// Same arithmetic, in the same order and precision, as gn_apply_kernel (fp32 fma -> mask -> relu -> storage rounding), so
+// the MMA consumes bit-identical operands whether the apply ran as its own pass or here.
+template <int kFmt>
+__device__ __forceinline__ uint4 pro_transform(uint4 raw, const float (&a)[8], const float (&b)[8], uint32_t mbits, float lo_clamp) {
+  using T = typename FmtTraits<kFmt>::T;
+  Vec8<T> v;
+  v.raw = raw;
+  float f[8];
+  v.to_float(f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float t = fmaf(f[i], a[i], b[i]);
+    t = ((mbits >> i) & 1u) ? t : 0.f;
+    f[i] = fmaxf(t, lo_clamp);
+  }
+  v.from_float(f);
+  return v.raw;
+}
 
 template <int NV>
 __device__ __forceinline__ void v2_epilogue_stats(const float (&x)[32], bool valid, int lane, float* scratch) {
@@ -64,10 +102,14 @@ __device__ __forceinline__ void v2_epilogue_stats(const float (&x)[32], bool val
   if (lane % LPV == 0) scratch[lane / LPV] = v[0];
 }
 
-template <int BLOCK_N, int MT, int kFmt>
-__global__ void __launch_bounds__(kV2Threads, 1)
+template <int BLOCK_N, int MT, int kFmt, bool kPro>
+// kPro kernels launch 352 threads but are compiled for a 512-thread bound = 128 registers per thread (a few bytes of
+// spills): 352 x 168 registers would own 59 k of the SM's 64 k registers and evict the co-resident DropBlock mask-build
+// blocks (8 k registers each) that the Monte-Carlo step overlaps with the forward -- measured: +0.5 ms per step.
+__global__ void __launch_bounds__(kPro ? 512 : kV2Threads, 1)
 conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvV2Params p) {
   constexpr bool kTf32 = kFmt == 1;
+  static_assert(!(kPro && kTf32), "the fused prologue is built for the 16-bit storage formats");
   using OutT = typename FmtTraits<kFmt>::T;
   constexpr int kBBytes = BLOCK_N * 128;
   constexpr int kKElems = kTf32 ? 32 : 64;
@@ -90,6 +132,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* t_empty = t_full + 2;                              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
   float* stat_scratch = reinterpret_cast<float*>(tmem_slot + 2);   // [4 warps][128]
+  uint64_t* a_ready = reinterpret_cast<uint64_t*>(stat_scratch + 4 * 128);   // [SA] (kPro): patch transformed, MMA may read
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -101,6 +144,8 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+    if (kPro)
+      for (int s = 0; s < SA; ++s) mbar_init(&a_ready[s], kProWarps);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -133,7 +178,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int img = tile / tiles_per_image;
           const int r = tile - img * tiles_per_image;
           const int ty = r / p.tiles_w;
-          cn[t] = img;
+          cn[t] = p.x_shared ? 0 : img;
           ch[t] = ty * 16 - 1;
           cw[t] = (r - ty * p.tiles_w) * 8 - 1;
         }
@@ -186,7 +231,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
         const uint32_t acc0 = tmem_u + buf * kAccCols;
         for (int kc = 0; kc < p.kc_chunks; ++kc) {
-          mbar_wait(&a_full[sa], pa);
+          mbar_wait(kPro ? &a_ready[sa] : &a_full[sa], pa);
           const uint32_t a_stage = a_lo0 + static_cast<uint32_t>((sa * MT * kPatchStride) >> 4);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
@@ -213,6 +258,124 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
     __syncwarp();
+  } else if (kPro && warp >= 7) {
+    // ===================== prologue transform (warps 7 .. 10) =====================
+    // Thread tt owns the 16-byte channel chunk j = tt & 7 of patch rows r0 + 16 k (k = 0 .. 11): its 8 (a, b) pairs live
+    // in registers for a whole patch, a quarter warp touches one full 128-byte row per access (conflict-free under the
+    // 128-byte swizzle: physical chunk = j ^ (r & 7)).  Pixels outside the image keep TMA's zero fill: the conv's zero
+    // padding applies to the ACTIVATED tensor (reference utils_unet.py:166-182: Conv -> GroupNorm -> DropBlock -> ReLU,
+    // the next Conv2d pads its input), so the affine must not touch them.
+    if constexpr (kPro) {
+      const int tt = threadIdx.x - kV2Threads;
+      const int j = tt & 7;
+      const int r0 = tt >> 3;                                    // 0 .. 15
+      const int cvs = p.cin >> 3;                                // 16-byte vectors (= mask bytes) per pixel
+      const float lo_clamp = p.pro_relu ? 0.f : -3.0e38f;        // storage conversion saturates fp16 on its own
+      // Per-thread constants: the 12 rows this thread owns, as (py, px) inside the 18 x 10 patch and as mask-byte offsets
+      // relative to the patch origin pixel.  Row r0 + 176 exists only for r0 < 4 (180 rows).
+      int rel[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const int row = r0 + 16 * k;
+        const int py = (row * 205) >> 11, px = row - py * 10;        // row / 10, row % 10 for row < 192
+        rel[k] = (py * p.w + px) * cvs;
+      }
+      const uint32_t rows_mask = r0 < 4 ? 0xFFFu : 0x7FFu;
+      // Patch metadata (8 coefficient pairs, 12 mask bytes, in-image flags) comes straight from global memory (L2 hits)
+      // and is fetched ONE PATCH AHEAD, so its latency overlaps the transform of the current patch.
+      struct Meta {
+        float ca[8], cb[8];
+        uint32_t mb[12];                                         // mask bytes, consumed one patch later: never packed or
+        uint32_t inb;                                            // touched before, so the HBM latency stays hidden
+      };                                                         // inb bit k: patch row r0 + 16 k is a real pixel
+      auto fetch = [&](int item, int kc, int t, Meta& m) {
+        const int mg = item - fd_div(item, p.fd_mgroups) * p.num_mgroups;
+        const int tile = mg * MT + t;
+        const bool tile_ok = item < p.num_items && tile < p.total_tiles;
+        const int img = tile_ok ? fd_div(tile, p.fd_tpi) : 0;
+        const int r = tile_ok ? tile - img * tiles_per_image : 0;
+        const int ty = fd_div(r, p.fd_tw);
+        const int h0 = ty * 16 - 1, w0 = (r - ty * p.tiles_w) * 8 - 1;
+        const float4* cf = reinterpret_cast<const float4*>(p.pro_coef + static_cast<size_t>(img) * p.cin + kc * 64 + j * 8);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 c4 = __ldg(cf + i);
+          m.ca[2 * i] = c4.x; m.cb[2 * i] = c4.y; m.ca[2 * i + 1] = c4.z; m.cb[2 * i + 1] = c4.w;
+        }
+        // interior patches (92 % at 592x576): every row is a real pixel, no per-row tests
+        uint32_t inb = rows_mask;
+        if (!(h0 >= 0 && h0 + 17 < p.h && w0 >= 0 && w0 + 9 < p.w)) {       // warp-uniform
+#pragma unroll
+          for (int k = 0; k < 12; ++k) {
+            const int row = r0 + 16 * k;
+            const int py = (row * 205) >> 11, px = row - py * 10;
+            const int hh = h0 + py, ww = w0 + px;
+            if (!(hh >= 0 && hh < p.h && ww >= 0 && ww < p.w)) inb &= ~(1u << k);
+          }
+        }
+        if (!tile_ok) inb = 0;
+        m.inb = inb;
+        if (p.pro_mask) {
+          const uint8_t* mbase = p.pro_mask + (static_cast<size_t>(img) * p.h * p.w + static_cast<long>(h0) * p.w + w0) * cvs + kc * 8 + j;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) {
+            m.mb[k] = 0xFFu;
+            if ((inb >> k) & 1u) m.mb[k] = __ldg(mbase + rel[k]);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 12; ++k) m.mb[k] = 0xFFu;
+        }
+      };
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t smA_u32 = smem_u32(smA);
+      Meta cur, nxt;
+      int n_item = blockIdx.x, n_kc = 0, n_t = 0;                // the patch `nxt` describes
+      auto advance = [&]() {
+        if (++n_t == MT) {
+          n_t = 0;
+          if (++n_kc == p.kc_chunks) { n_kc = 0; n_item += gridDim.x; }
+        }
+      };
+      fetch(n_item, n_kc, n_t, nxt);
+      advance();
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        for (int kc = 0; kc < p.kc_chunks; ++kc) {
+#pragma unroll 1
+          for (int t = 0; t < MT; ++t) {
+            cur = nxt;
+            fetch(n_item, n_kc, n_t, nxt);                       // next patch's metadata in flight during this transform
+            advance();
+            if (t == 0) mbar_wait(&a_full[s], ph);               // TMA bytes of all MT patches of this stage have landed
+            // row r0 + 16 k: (row & 7) = (r0 & 7) for every k, so the swizzled chunk offset is a per-thread constant
+            const uint32_t patch = smA_u32 + static_cast<uint32_t>((s * MT + t) * kPatchStride + r0 * 128 + ((j ^ (r0 & 7)) << 4));
+            // two halves of six rows: loads first (unconditional: rows outside the image hold TMA's zeros; only row
+            // 176 + r0 may not exist), then the arithmetic, then predicated stores -- no branches, six independent
+            // vectors for the scheduler, 24 live data registers
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint4 v[6];
+#pragma unroll
+              for (int i = 0; i < 6; ++i) {
+                const int k = half * 6 + i;
+                v[i] = (k < 11 || r0 < 4) ? lds128(patch + k * 2048) : make_uint4(0u, 0u, 0u, 0u);
+              }
+#pragma unroll
+              for (int i = 0; i < 6; ++i) v[i] = pro_transform<kFmt>(v[i], cur.ca, cur.cb, cur.mb[half * 6 + i], lo_clamp);
+#pragma unroll
+              for (int i = 0; i < 6; ++i)
+                if ((cur.inb >> (half * 6 + i)) & 1u) sts128(patch + (half * 6 + i) * 2048, v[i]);
+            }
+          }
+          // generic-proxy writes -> visible to the tensor core's async-proxy reads, then one arrive per warp
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[s]);
+          if (++s == SA) { s = 0; ph ^= 1; }
+        }
+      }
+    }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;
@@ -288,7 +451,7 @@ struct V2Plan {
   size_t smem;
 };
 
-static int v2_make_plan(const b2u_conv_desc* d, V2Plan* pl) {
+static int v2_make_plan(const b2u_conv_desc* d, V2Plan* pl, bool pro = false) {
   pl->tiles_w = (d->w + 7) / 8;
   pl->tiles_h = (d->h + 15) / 16;
   int bn = d->cout % 256 == 0 ? 256 : (d->cout % 128 == 0 ? 128 : 64);
@@ -306,9 +469,18 @@ static int v2_make_plan(const b2u_conv_desc* d, V2Plan* pl) {
   const size_t budget = 222 * 1024 - 4096;
   int sa = 2, sb = 3;
   auto bytes = [&](int a, int b) { return static_cast<size_t>(a) * mt * kPatchStride + static_cast<size_t>(b) * bn * 128; };
-  while (bytes(sa, sb + 1) <= budget && sb < 6) ++sb;
-  while (bytes(sa + 1, sb) <= budget && sa < 3) ++sa;
-  while (bytes(sa, sb + 1) <= budget && sb < 9) ++sb;
+  if (pro) {
+    // fused prologue: a patch stage lives through TMA -> transform -> MMA, one more hop than the plain kernel: the patch
+    // ring gets its third (and, if it fits, fourth) stage before the weight ring grows past four
+    while (bytes(sa + 1, sb) <= budget && sa < 3) ++sa;
+    while (bytes(sa, sb + 1) <= budget && sb < 4) ++sb;
+    while (bytes(sa + 1, sb) <= budget && sa < 4) ++sa;
+    while (bytes(sa, sb + 1) <= budget && sb < 9) ++sb;
+  } else {
+    while (bytes(sa, sb + 1) <= budget && sb < 6) ++sb;
+    while (bytes(sa + 1, sb) <= budget && sa < 3) ++sa;
+    while (bytes(sa, sb + 1) <= budget && sb < 9) ++sb;
+  }
   if (d->reserved[1] >= 2 && d->reserved[1] <= 12) sb = d->reserved[1];
   // whole filter resident: one N tile (every item uses the same weights) and all 9 * (Cin / 64-or-32) stages fit
   {
@@ -317,21 +489,21 @@ static int v2_make_plan(const b2u_conv_desc* d, V2Plan* pl) {
     if (pl->resident_b) {
       sb = 9 * kc;
       sa = 2;
-      while (bytes(sa + 1, sb) <= budget && sa < 3) ++sa;
+      while (bytes(sa + 1, sb) <= budget && sa < (pro ? 4 : 3)) ++sa;
     }
   }
   B2U_REQUIRE(bytes(sa, sb) <= budget, "conv3x3 v2: pipeline does not fit shared memory (BLOCK_N %d MT %d)", bn, mt);
   pl->sa = sa;
   pl->sb = sb;
-  pl->smem = bytes(sa, sb) + 1024 + (2 * sa + 2 * sb + 4) * 8 + 16 + 4 * 128 * 4;
+  pl->smem = bytes(sa, sb) + 1024 + (2 * sa + 2 * sb + 4) * 8 + 16 + 4 * 128 * 4 + sa * 8;
   pl->sgs = conv_stat_subgroup(d->cout, d->num_groups);
   return B2U_OK;
 }
 
-template <int BN, int MT, int TF>
+template <int BN, int MT, int TF, bool PRO>
 static int v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Params& gp, int grid, size_t smem, cudaStream_t st) {
-  B2U_SET_MAX_SMEM_ONCE((conv3x3_v2_kernel<BN, MT, TF>), 227 * 1024);
-  B2U_PDL_LAUNCH((conv3x3_v2_kernel<BN, MT, TF>), grid, kV2Threads, smem, st, ta, tb, gp);
+  B2U_SET_MAX_SMEM_ONCE((conv3x3_v2_kernel<BN, MT, TF, PRO>), 227 * 1024);
+  B2U_PDL_LAUNCH((conv3x3_v2_kernel<BN, MT, TF, PRO>), grid, PRO ? kV2ThreadsPro : kV2Threads, smem, st, ta, tb, gp);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -347,11 +519,12 @@ int conv3x3_v2_stat_layout(const b2u_conv_desc* d, int* rows_per_image, int* sub
   return B2U_OK;
 }
 
-int conv3x3_v2_run(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d, void* stream) {
+int conv3x3_v2_run(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d, void* stream,
+                   const V2Prologue* pro) {
   int rc = conv_validate_desc(d);
   if (rc) return rc;
   V2Plan pl;
-  rc = v2_make_plan(d, &pl);
+  rc = v2_make_plan(d, &pl, pro != nullptr);
   if (rc) return rc;
   B2U_REQUIRE(x && wpacked && y, "null tensor pointer");
   B2U_REQUIRE(d->num_groups == 0 || partials != nullptr, "partials required when num_groups > 0");
@@ -387,14 +560,34 @@ int conv3x3_v2_run(const void* x, const void* wpacked, void* y, float* partials,
   gp.resident_b = pl.resident_b;
   gp.y = y;
   gp.partials = partials;
+  gp.pro_coef = pro ? reinterpret_cast<const float2*>(pro->coef) : nullptr;
+  gp.pro_mask = pro ? reinterpret_cast<const uint8_t*>(pro->mask) : nullptr;
+  gp.pro_relu = pro ? pro->relu : 0;
+  gp.x_shared = pro ? pro->x_shared : 0;
+  gp.cin = d->cin;
+  gp.fd_mgroups = fd_make(gp.num_mgroups);
+  gp.fd_tpi = fd_make(pl.tiles_w * pl.tiles_h);
+  gp.fd_tw = fd_make(pl.tiles_w);
+  if (pro) {
+    B2U_REQUIRE(static_cast<double>(gp.num_items) * gp.num_mgroups < 4.0e9 && static_cast<double>(gp.total_tiles + 2) * pl.tiles_w * pl.tiles_h < 4.0e9,
+                "fused prologue: tile count out of range for the fast division");
+    B2U_REQUIRE(static_cast<double>(d->h) * d->w * (d->cin / 8) < 2.0e9, "fused prologue: image too large for 32-bit mask offsets");
+    B2U_REQUIRE(d->dtype != B2U_F32, "the fused conv prologue supports the 16-bit storage formats (bf16 / fp16)");
+    B2U_REQUIRE(pro->coef != nullptr, "fused prologue: coefficient pointer is NULL");
+    B2U_REQUIRE(d->x_cstride == d->cin, "fused prologue: the input tensor must be dense in channels");
+  }
   int grid = b2u_num_sms();
   if (grid > gp.num_items) grid = gp.num_items;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define B2U_V2_CASE(BN, MTV)                                                                        \
   if (pl.block_n == BN && pl.mt == MTV) {                                                            \
-    if (d->dtype == B2U_F32) return v2_launch<BN, MTV, 1>(ta, tb, gp, grid, pl.smem, st);            \
-    if (d->dtype == B2U_F16) return v2_launch<BN, MTV, 2>(ta, tb, gp, grid, pl.smem, st);            \
-    return v2_launch<BN, MTV, 0>(ta, tb, gp, grid, pl.smem, st);                                     \
+    if (pro) {                                                                                       \
+      if (d->dtype == B2U_F16) return v2_launch<BN, MTV, 2, true>(ta, tb, gp, grid, pl.smem, st);    \
+      return v2_launch<BN, MTV, 0, true>(ta, tb, gp, grid, pl.smem, st);                             \
+    }                                                                                                \
+    if (d->dtype == B2U_F32) return v2_launch<BN, MTV, 1, false>(ta, tb, gp, grid, pl.smem, st);     \
+    if (d->dtype == B2U_F16) return v2_launch<BN, MTV, 2, false>(ta, tb, gp, grid, pl.smem, st);     \
+    return v2_launch<BN, MTV, 0, false>(ta, tb, gp, grid, pl.smem, st);                              \
   }
   B2U_V2_CASE(64, 1) B2U_V2_CASE(64, 2) B2U_V2_CASE(128, 1) B2U_V2_CASE(128, 2) B2U_V2_CASE(256, 1) B2U_V2_CASE(256, 2)
 #undef B2U_V2_CASE

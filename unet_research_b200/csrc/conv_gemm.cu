@@ -498,6 +498,16 @@ extern "C" int b2u_conv3x3_fwd(const void* x, const void* wpacked, void* y, floa
   if (!use_v1(d)) return conv3x3_v2_run(x, wpacked, y, partials, d, stream);
   return run_gemm(x, wpacked, y, partials, d, 0, stream);
 }
+extern "C" int b2u_conv3x3_pro_fwd(const void* x_raw, const float* coef, const void* mask_bits, const void* wpacked, void* y,
+                                   float* partials, const b2u_conv_desc* d, int relu, int x_shared, void* stream) {
+  B2U_REQUIRE(d != nullptr, "null descriptor");
+  V2Prologue pro;
+  pro.coef = coef;
+  pro.mask = mask_bits;
+  pro.relu = relu;
+  pro.x_shared = x_shared;
+  return conv3x3_v2_run(x_raw, wpacked, y, partials, d, stream, &pro);
+}
 extern "C" int b2u_convT2x2_fwd(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d,
                                 void* stream) {
   if (!use_v1(d)) return convT_v2_run(x, wpacked, y, partials, d, stream);

@@ -5,6 +5,7 @@
 #include "b2u_common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace b2u {
 
@@ -944,6 +945,19 @@ extern "C" int b2u_gn_finalize_ex(const float* partials, int rows_per_image, int
   return B2U_OK;
 }
 
+// Occupancy limiter for the memory-bound forward kernels: B2U_APPLY_SMEM_KB (dynamic shared memory requested per
+// block, unused by the kernel) caps the resident blocks per SM so that registers stay free for the DropBlock mask-build
+// blocks of the NEXT step, which the Monte-Carlo loop runs concurrently on a low-priority stream.
+static size_t apply_pad_smem() {
+  static long v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2U_APPLY_SMEM_KB");
+    v = e ? atol(e) * 1024 : 0;
+    if (v < 0 || v > 200 * 1024) v = 0;
+  }
+  return static_cast<size_t>(v);
+}
+
 static int fill_apply(const b2u_apply_desc* d, ApplyParams* p) {
   B2U_REQUIRE(d, "null descriptor");
   B2U_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->c % 8 == 0, "bad tensor shape");
@@ -979,10 +993,14 @@ extern "C" int b2u_gn_apply(const void* x, const float* coef, const uint32_t* ma
   if (bpi < 1) bpi = 1;
   dim3 grid(static_cast<unsigned>(bpi), d->n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t pad = apply_pad_smem();
 #define B2U_APPLY_TM(T, A, B)                                                                                       \
-  B2U_PDL_LAUNCH((gn_apply_kernel<T, A, B>), grid, threads, 0, st, static_cast<const T*>(x), reinterpret_cast<const float2*>(coef), \
-                 reinterpret_cast<const uint8_t*>(mask1), reinterpret_cast<const uint8_t*>(mask2), keep_counts2,        \
-                 static_cast<T*>(out), p)
+  do {                                                                                                              \
+    if (pad > 48 * 1024) B2U_SET_MAX_SMEM_ONCE((gn_apply_kernel<T, A, B>), 200 * 1024);                             \
+    B2U_PDL_LAUNCH((gn_apply_kernel<T, A, B>), grid, threads, pad, st, static_cast<const T*>(x),                    \
+                   reinterpret_cast<const float2*>(coef), reinterpret_cast<const uint8_t*>(mask1),                  \
+                   reinterpret_cast<const uint8_t*>(mask2), keep_counts2, static_cast<T*>(out), p);                 \
+  } while (0)
 #define B2U_APPLY_T(T)                                                                                              \
   do {                                                                                                              \
     if (mask1 && mask2) B2U_APPLY_TM(T, true, true);                                                                \

@@ -345,6 +345,14 @@ class UNetEngine:
         self._aliased = set()
         self._workspaces: Dict[Tuple[int, int, int], Workspace] = {}
         self.training_weights = False          # set by enable_training(): also keep the dgrad-packed weights
+        # Fused conv prologue (16-bit inference schedules): the GroupNorm affine + DropBlock mask + ReLU of a unit is applied
+        # by the CONSUMING 3x3 conv on the TMA-landed patch in shared memory (b2u_conv3x3_pro_fwd) instead of a stand-alone
+        # gn_apply pass that writes and re-reads the activated tensor.  Training keeps the unfused schedule: the weight
+        # gradients read the activated tensors.  `fuse_levels`: encoder/decoder resolutions (0 = full size) that fuse.
+        import os
+        self.fused_prologue = dtype != _lib.F32 and os.environ.get("B2U_FUSED", "1") != "0"
+        lv = os.environ.get("B2U_FUSE_LEVELS")
+        self.fuse_levels = set(int(t) for t in lv.split(",") if t != "") if lv is not None else set(range(depth + 1))
         self._sd_ref = state_dict
         self.load_weights(state_dict)
 
@@ -441,6 +449,12 @@ class UNetEngine:
         call("b2u_convT2x2_fwd" if conv_t else "b2u_conv3x3_fwd", ptr(ws.buf[xname]), ptr(self.w[wkey]), ptr(ws.buf[yname]),
              ptr(ws.stat[sname].partials), C.byref(d), stream_ptr())
 
+    def _conv_pro(self, ws, xname, sname_in, mask_ptr, relu, x_shared, wkey, yname, sname, n, h, w, cin, cout):
+        """conv3x3 over act = [relu]((a * raw + b) * keep), the activation applied in the conv's own prologue."""
+        d = self._conv_desc(n, h, w, cin, cout, cin)
+        call("b2u_conv3x3_pro_fwd", ptr(ws.buf[xname]), ptr(ws.stat[sname_in].coef), mask_ptr, ptr(self.w[wkey]), ptr(ws.buf[yname]),
+             ptr(ws.stat[sname].partials), C.byref(d), int(relu), int(x_shared), stream_ptr())
+
     def enable_training(self):
         if not self.training_weights:
             if self.dtype != _lib.BF16:
@@ -488,6 +502,10 @@ class UNetEngine:
         st = stream_ptr()
         B = ws.buf
         m = masks
+        fuse_on = self.fused_prologue and argmax is None     # training (argmax requested) materialises the activations
+
+        def fuse(lvl):
+            return fuse_on and lvl in self.fuse_levels
 
         def mptr(site):
             return m.mask_ptr(site) if m is not None else None
@@ -507,15 +525,24 @@ class UNetEngine:
             if lvl == 0:
                 call("b2u_conv_first_fwd", ptr(x), ptr(self.w[p + ".0.weight"]), ptr(B["d0.raw1"]), ptr(ws.stat["d0.c1"].partials),
                      1 if shared else n, self.init_channels, ws.h0, ws.w0, hh, ww, c, G, self.dtype, st)
+            elif fuse(lvl):
+                # the pooled tensor's GroupNorm (no ReLU, no DropBlock) rides in this conv's prologue
+                self._conv_pro(ws, f"d{lvl - 1}.praw", f"d{lvl - 1}.pool", None, False, False, p + ".0.weight", f"d{lvl}.raw1", f"d{lvl}.c1",
+                               n, hh, ww, c // 2, c)
             else:
                 self._conv(ws, f"d{lvl - 1}.pact", p + ".0.weight", f"d{lvl}.raw1", f"d{lvl}.c1", n, hh, ww, c // 2, c)
             self._finalize(ws, f"d{lvl}.c1", p + ".1", n, c, hh * ww, m, s1, shared=shared)
-            a = self._apply_desc(n, hh, ww, c, True, c, 0, None, None)
-            a.reserved[0] = 1 if shared else 0
-            call("b2u_gn_apply", ptr(B[f"d{lvl}.raw1"]), ptr(ws.stat[f"d{lvl}.c1"].coef), mptr(s1), None, None,
-                 ptr(B[f"d{lvl}.act1"]), C.byref(a), st)
-            # conv 2 + pool + skip store
-            self._conv(ws, f"d{lvl}.act1", p + ".4.weight", f"d{lvl}.raw2", f"d{lvl}.c2", n, hh, ww, c, c)
+            if fuse(lvl):
+                # conv 2 applies unit 1's GroupNorm + DropBlock + ReLU in its prologue
+                self._conv_pro(ws, f"d{lvl}.raw1", f"d{lvl}.c1", mptr(s1), True, shared, p + ".4.weight", f"d{lvl}.raw2", f"d{lvl}.c2",
+                               n, hh, ww, c, c)
+            else:
+                a = self._apply_desc(n, hh, ww, c, True, c, 0, None, None)
+                a.reserved[0] = 1 if shared else 0
+                call("b2u_gn_apply", ptr(B[f"d{lvl}.raw1"]), ptr(ws.stat[f"d{lvl}.c1"].coef), mptr(s1), None, None,
+                     ptr(B[f"d{lvl}.act1"]), C.byref(a), st)
+                # conv 2 + pool + skip store
+                self._conv(ws, f"d{lvl}.act1", p + ".4.weight", f"d{lvl}.raw2", f"d{lvl}.c2", n, hh, ww, c, c)
             self._finalize(ws, f"d{lvl}.c2", p + ".5", n, c, hh * ww, m, s2)
             a = self._apply_desc(n, hh, ww, c, True, 2 * c, c, m, scat, 2 * c, c)
             call("b2u_gn_apply_pool", ptr(B[f"d{lvl}.raw2"]), ptr(ws.stat[f"d{lvl}.c2"].coef), mptr(s2), mptr(scat), kptr(scat),
@@ -523,22 +550,31 @@ class UNetEngine:
                  ptr(argmax[lvl]) if argmax is not None else None, G, C.byref(a), st)
             # GroupNorm after the pool (no ReLU, no DropBlock)
             self._finalize(ws, f"d{lvl}.pool", f"down_blocks.{lvl}.1.1", n, c, (hh // 2) * (ww // 2), None, None)
-            a = self._apply_desc(n, hh // 2, ww // 2, c, False, c, 0, None, None)
-            call("b2u_gn_apply", ptr(B[f"d{lvl}.praw"]), ptr(ws.stat[f"d{lvl}.pool"].coef), None, None, None,
-                 ptr(B[f"d{lvl}.pact"]), C.byref(a), st)
+            if not fuse(lvl + 1):
+                a = self._apply_desc(n, hh // 2, ww // 2, c, False, c, 0, None, None)
+                call("b2u_gn_apply", ptr(B[f"d{lvl}.praw"]), ptr(ws.stat[f"d{lvl}.pool"].coef), None, None, None,
+                     ptr(B[f"d{lvl}.pact"]), C.byref(a), st)
             c *= 2
         # bottleneck
         if hook is not None:
             hook("bottleneck")
         hh, ww = ws.h >> d, ws.w >> d
         prev = f"d{d - 1}.pact"
+        fb = fuse(d)
         for j, (idx, site) in enumerate(((0, 2 * d), (4, 2 * d + 1)), start=1):
             cin = c // 2 if j == 1 else c
-            self._conv(ws, prev, f"conn_block.{idx}.weight", f"b.raw{j}", f"b.c{j}", n, hh, ww, cin, c)
+            if fb and j == 1:
+                self._conv_pro(ws, f"d{d - 1}.praw", f"d{d - 1}.pool", None, False, False, f"conn_block.{idx}.weight", "b.raw1", "b.c1",
+                               n, hh, ww, cin, c)
+            elif fb:
+                self._conv_pro(ws, "b.raw1", "b.c1", mptr(2 * d), True, False, f"conn_block.{idx}.weight", "b.raw2", "b.c2", n, hh, ww, cin, c)
+            else:
+                self._conv(ws, prev, f"conn_block.{idx}.weight", f"b.raw{j}", f"b.c{j}", n, hh, ww, cin, c)
             self._finalize(ws, f"b.c{j}", f"conn_block.{idx + 1}", n, c, hh * ww, m, site)
-            a = self._apply_desc(n, hh, ww, c, True, c, 0, None, None)
-            call("b2u_gn_apply", ptr(B[f"b.raw{j}"]), ptr(ws.stat[f"b.c{j}"].coef), mptr(site), None, None,
-                 ptr(B[f"b.act{j}"]), C.byref(a), st)
+            if not (fb and j == 1):                      # unit 2's activation feeds the up-conv (plain GEMM): materialised
+                a = self._apply_desc(n, hh, ww, c, True, c, 0, None, None)
+                call("b2u_gn_apply", ptr(B[f"b.raw{j}"]), ptr(ws.stat[f"b.c{j}"].coef), mptr(site), None, None,
+                     ptr(B[f"b.act{j}"]), C.byref(a), st)
             prev = f"b.act{j}"
         # decoder
         for u in range(d):
@@ -558,11 +594,15 @@ class UNetEngine:
             # conv 1 over the concat buffer
             self._conv(ws, f"cat{lvl}", f"up_blocks.{u}.1.0.weight", f"u{u}.raw1", f"u{u}.c1", n, hh, ww, 2 * c, c)
             self._finalize(ws, f"u{u}.c1", f"up_blocks.{u}.1.1", n, c, hh * ww, m, s1)
-            a = self._apply_desc(n, hh, ww, c, True, c, 0, None, None)
-            call("b2u_gn_apply", ptr(B[f"u{u}.raw1"]), ptr(ws.stat[f"u{u}.c1"].coef), mptr(s1), None, None,
-                 ptr(B[f"u{u}.act1"]), C.byref(a), st)
-            # conv 2
-            self._conv(ws, f"u{u}.act1", f"up_blocks.{u}.1.4.weight", f"u{u}.raw2", f"u{u}.c2", n, hh, ww, c, c)
+            if fuse(lvl):
+                self._conv_pro(ws, f"u{u}.raw1", f"u{u}.c1", mptr(s1), True, False, f"up_blocks.{u}.1.4.weight", f"u{u}.raw2", f"u{u}.c2",
+                               n, hh, ww, c, c)
+            else:
+                a = self._apply_desc(n, hh, ww, c, True, c, 0, None, None)
+                call("b2u_gn_apply", ptr(B[f"u{u}.raw1"]), ptr(ws.stat[f"u{u}.c1"].coef), mptr(s1), None, None,
+                     ptr(B[f"u{u}.act1"]), C.byref(a), st)
+                # conv 2
+                self._conv(ws, f"u{u}.act1", f"up_blocks.{u}.1.4.weight", f"u{u}.raw2", f"u{u}.c2", n, hh, ww, c, c)
             self._finalize(ws, f"u{u}.c2", f"up_blocks.{u}.1.5", n, c, hh * ww, m, s2)
             if u < d - 1:
                 a = self._apply_desc(n, hh, ww, c, True, c, 0, None, None)
