@@ -21,11 +21,14 @@ for r in rows:
 out = {"source": f"{tag}: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, python tests/prof_step.py {nb} 2",
        "iter_batch": nb, "per_family": {}}
 conv = 0.0
+step_total = 0.0
 for name, f in sorted(fam.items(), key=lambda kv: -(kv[1]["read"] + kv[1]["write"])):
     tot = f["read"] + f["write"]
     out["per_family"][name] = {"launches_per_step": len(f["launches"]), "dram_read_mb": round(f["read"] / 1e6, 1),
                                "dram_write_mb": round(f["write"] / 1e6, 1)}
+    step_total += tot
     if name.startswith("conv3x3_v2") or name.startswith("convT_v2"):
         conv += tot
 out["conv_family_dram_bytes_per_step"] = conv
+out["step_dram_bytes"] = step_total
 print(json.dumps(out, indent=1))

@@ -19,7 +19,7 @@ for r in rows:
     a[1] += v
 tot = sum(v[1] for v in agg.values())
 with open(f"profiles/{tag}_launches.md", "w") as f:
-    f.write(f"# {tag}: ncu launch list of `python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-train` (first {len(rows)} launches)\n\n")
+    f.write(f"# {tag}: ncu launch list of `python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-train --no-alt` (first {len(rows)} launches)\n\n")
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` -- per-launch times are cold-cache and serialised: compare SHARES.\n\n")
     f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):

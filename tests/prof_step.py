@@ -1,4 +1,4 @@
-"""One eager Monte-Carlo step (mask build + batched forward) for ncu:  python tests/prof_step.py [iter_batch] [reps]
+"""One eager Monte-Carlo step (mask build + batched forward) for ncu:  python tests/prof_step.py [iter_batch] [reps] [dtype]
 
 Prints nothing interesting; meant to be run under
     ncu --set full --clock-control none --profile-from-start off ...   (captures the last repetition only)
@@ -17,7 +17,7 @@ nb = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 dev = torch.device("cuda")
 H0, W0 = 584, 565
-model, _ = build_canonical(dev, dropblock=True, compute="bf16")
+model, _ = build_canonical(dev, dropblock=True, compute=sys.argv[3] if len(sys.argv) > 3 else "auto")
 model.apply(U.set_dropblock_on)
 x = synthetic.make_image(H0, W0, seed=1234).to(dev)
 fov = synthetic.make_fov_mask(H0, W0).to(dev).reshape(H0, W0).contiguous()
