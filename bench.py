@@ -682,7 +682,7 @@ def bench_train(dev, rank, world, steps, warmup, peaks=None):
             "value": world / (ms / 1000.0), "unit": "imgs/s", "ms_per_step": ms, "steps": steps, "global_batch": world,
             "tflops": 1501.4e9 * world / (ms / 1000.0) / 1e12, "flop_per_image": 1501.4e9, "cuda_graphs": graphs,
             "optimizer": "fused SGD-momentum + global-norm clip (one multi-tensor kernel pair)" if fused else "torch.optim.SGD + clip_grad_norm_",
-            "gradient_allreduce_bytes": (124.16e6 if world > 1 else 0), "allreduce": "NCCL AVG, 2 buckets, decoder bucket overlapped with the encoder backward" if world > 1 else None,
+            "gradient_allreduce_bytes": (124.16e6 if world > 1 else 0), "allreduce": "NCCL AVG, 3 buckets of the flat gradient buffer (decoder + bottleneck | deep encoder | shallow encoder), each reduced while the next backward graph segment runs" if world > 1 else None,
             "loss_first": first, "loss_last": float(loss.item())}
 
 

@@ -281,6 +281,19 @@ int b2u_gemm1x1_fwd(const void* x, const void* wpacked, void* y, const b2u_conv_
 /* nn.ConvTranspose2d weight [Cin,Cout,2,2] fp32 -> [1][Cin][4*Cout] (k = tap*Cout + co) for b2u_gemm1x1_fwd */
 int b2u_pack_convT2x2_dgrad_weight(const float* w, void* packed, int cin, int cout, int dtype, void* stream);
 
+/* ------------------------------------------------------------------ fused masked BCE loss of the training step
+ * (utils_training.py:28-33 with nn.BCELoss(), base_model_tests/training.py:195):
+ *   seg = out*mask; gt = gt*mask; loss = mean(BCE(seg, gt)) * numel / count_nonzero(mask)
+ * b2u_masked_bce_fwd: one pass over the three fp32 maps [n elements] -> loss (scalar), scale (scalar: d loss / d sum of
+ *   BCE terms) and grad_unscaled[n] = d BCE_i / d out_i (ATen's clamps: log >= -100, denominator >= 1e-12);
+ *   partials: double[2 * b2u_masked_bce_blocks()] scratch; deterministic (fixed-order reduction).
+ * b2u_masked_bce_bwd: grad_out[i] = grad_unscaled[i] * (*upstream) * (*scale)  (upstream = d L / d loss, a device scalar). */
+int b2u_masked_bce_blocks(void);
+int b2u_masked_bce_fwd(const float* out, const float* gt, const float* mask, long long n, float* grad_unscaled,
+                       double* partials, float* loss, float* scale, void* stream);
+int b2u_masked_bce_bwd(const float* grad_unscaled, const float* upstream, const float* scale, float* grad_out, long long n,
+                       void* stream);
+
 /* ------------------------------------------------------------------ rotation (torchvision TF.rotate, BILINEAR,
  * fill 0, as called at Rotational_Uncertainty.py:54,58): affine grid in fp32, grid_sample(bilinear, zeros,
  * align_corners=False) of the image and of a ones channel, result img*m.  x,out: [n][c][h][w] fp32;

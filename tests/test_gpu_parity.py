@@ -674,6 +674,37 @@ def test_reference_own_loops_around_b200_unet():
     loss = U.BaseUNetTraining(m3, nn.BCELoss(), None).training_step((x.clone(), gt, fov), 1)
     loss.backward()
     g = torch.cat([p.grad.flatten() for p in m3.parameters()])
-    assert float(loss) == float(loss_ref) and torch.equal(g, g_ref)
+    # ours fuses the five-line masked BCE into one kernel pair: the loss is equal, the upstream gradient equal to ~1e-7
+    # (test_fused_masked_bce_matches_torch); the bf16 backward re-rounds it at every layer, so last-bit differences of
+    # the upstream gradient grow to ~1e-3 of the parameter gradient (23 layers; the loss landscape is the same)
+    assert abs(float(loss) - float(loss_ref)) <= 1e-6 * abs(float(loss_ref)) and D.rel(g, g_ref)[0] < 5e-3
     loss_oracle = O.train_step_loss({k: v.to(dev) for k, v in synthetic.make_state_dict(seed=1234).items()}, x, gt, fov, None)
     assert abs(float(loss) - float(loss_oracle)) < 1e-3 * abs(float(loss_oracle))
+
+
+def test_fused_masked_bce_matches_torch():
+    """b2u_masked_bce_{fwd,bwd} == the reference's five-line masked loss (utils_training.py:28-33) with nn.BCELoss and
+    torch autograd: loss to 1e-6 relative, gradient to 1e-6 relative, incl. saturated predictions (0 and 1: ATen's -100 log
+    clamp and 1e-12 denominator clamp) and an empty-FOV border."""
+    from torch import nn
+    from unet_research_b200.training import _MaskedBCE
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(3)
+    for (n, h, w) in ((1, 584, 565), (2, 120, 116)):
+        out = torch.rand(n, 1, h, w, generator=g)
+        out[0, 0, 0, :7] = torch.tensor([0.0, 1.0, 1e-30, 1 - 1e-7, 0.5, 1e-8, 1.0])
+        gt = (torch.rand(n, 1, h, w, generator=g) < 0.1).float()
+        fov = synthetic.make_fov_mask(h, w, batch=n)
+        fov[0, 0, 0, :7] = 1.0
+        o1 = out.to(dev).requires_grad_(True)
+        o2 = out.to(dev).requires_grad_(True)
+        gt_d, fov_d = gt.to(dev), fov.to(dev)
+        seg = o1 * fov_d
+        ref = nn.BCELoss()(seg, gt_d * fov_d) * (seg.numel() / fov_d.count_nonzero())
+        (ref * 1.7).backward()
+        got = _MaskedBCE.apply(o2, gt_d, fov_d)
+        (got * 1.7).backward()
+        assert abs(float(got) - float(ref)) <= 1e-6 * abs(float(ref)), (float(got), float(ref))
+        assert D.rel(o2.grad, o1.grad)[0] < 1e-6
+        assert float(o2.grad[fov_d == 0].abs().max()) == 0.0

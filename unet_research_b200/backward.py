@@ -185,12 +185,16 @@ def _dgrad3x3(eng, key, g: torch.Tensor, out: torch.Tensor, n, h, w, cout_fwd, c
     call("b2u_conv3x3_fwd", ptr(g), ptr(eng.w[key + "#dgrad"]), ptr(out), None, C.byref(d), stream_ptr())
 
 
+SPLIT_LEVEL = 2        # encoder levels >= SPLIT_LEVEL hold 94 % of the encoder's parameters and finish first
+
+
 def unet_backward(eng: UNetEngine, ws: Workspace, tb: TrainBuffers, masks: Optional[MaskPlan], xin: torch.Tensor,
                   out: torch.Tensor, grad_out: torch.Tensor, data_parallel: bool = False,
                   phase: Optional[int] = None) -> Dict[str, torch.Tensor]:
     """Returns {state-dict key: fp32 gradient in the PyTorch parameter layout}.  Launches only (plus, with
     data_parallel, NCCL all-reduces overlapped with the remaining backward kernels).
-    phase: None = everything; 0 = head + decoder + bottleneck; 1 = encoder (the two CUDA-graph segments of
+    phase: None = everything; 0 = head + decoder + bottleneck; 1 = encoder; 11 = deep encoder levels (>= SPLIT_LEVEL);
+    12 = shallow encoder levels (< SPLIT_LEVEL) (the CUDA-graph segments of
     training.TrainStep: the decoder-side gradients travel over NVLink while the encoder segment runs)."""
     tb.reducer = GradReducer() if data_parallel else None
     n, f, dpt = ws.n, eng.filters, eng.depth
@@ -247,7 +251,9 @@ def unet_backward(eng: UNetEngine, ws: Workspace, tb: TrainBuffers, masks: Optio
         _dgrad3x3(eng, "conn_block.0.weight", tb.gY[dpt], tb.gPA[dpt - 1], n, hh, ww, c, c // 2)
 
     # ---------------- encoder, deepest level first
-    for lvl in (range(dpt - 1, -1, -1) if phase in (None, 1) else ()):
+    enc_levels = {None: range(dpt - 1, -1, -1), 1: range(dpt - 1, -1, -1), 11: range(dpt - 1, SPLIT_LEVEL - 1, -1),
+                  12: range(min(SPLIT_LEVEL, dpt) - 1, -1, -1)}.get(phase, ())
+    for lvl in enc_levels:
         c = f << lvl
         hh, ww = ws.h >> lvl, ws.w >> lvl
         s1, s2, scat = 2 * lvl, 2 * lvl + 1, 2 * dpt + 2 + 3 * (dpt - 1 - lvl)

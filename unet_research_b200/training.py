@@ -21,7 +21,7 @@ class TrainStep:
     is launch-bound when ~290 kernels are issued one by one from Python):
 
       forward  graph: repack the conv weights from the live parameters -> build the DropBlock masks -> forward schedule
-      backward graph 0: head + decoder + bottleneck          backward graph 1: encoder
+      backward graph 0: head + decoder + bottleneck     graph 1: encoder levels 3, 2     graph 2: encoder levels 1, 0
 
     Everything step-dependent lives in device memory the graphs read: the input copy, the upstream gradient copy,
     the Philox offset and the DropBlock thresholds (the scheduler changes drop_prob every step).  With
@@ -43,6 +43,12 @@ class TrainStep:
         self.tail = min(o for k, o in offs.items() if not k.startswith("down_blocks"))
         if any(o >= self.tail for k, o in offs.items() if k.startswith("down_blocks")):
             self.tail = 0                                  # unexpected parameter order: one all-reduce over everything
+        # second bucket boundary inside the encoder: levels >= SPLIT_LEVEL (94 % of the encoder's bytes) are reduced while
+        # the shallow, full-resolution levels -- most of the encoder backward's TIME -- still run
+        from .backward import SPLIT_LEVEL
+        deep = [o for k, o in offs.items() if k.startswith("down_blocks.") and int(k.split(".")[1]) >= SPLIT_LEVEL]
+        shallow = [o for k, o in offs.items() if k.startswith("down_blocks.") and int(k.split(".")[1]) < SPLIT_LEVEL]
+        self.mid = min(deep) if deep and shallow and self.tail > 0 and max(shallow) < min(deep) else 0
         self.sig = None
         self.calls = 0
         self.fwd_graph = None
@@ -113,26 +119,37 @@ class TrainStep:
             return tuple(grads[k] for k in self.keys)
         if self.bwd_graphs is None:
             torch.cuda.synchronize(eng.device)
-            g0, g1 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            g0, g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g0):
                 unet_backward(eng, ws, tb, self.masks, self.x, ws.out, self.go, phase=0)
             with torch.cuda.graph(g1, pool=g0.pool()):
-                unet_backward(eng, ws, tb, self.masks, self.x, ws.out, self.go, phase=1)
-            self.bwd_graphs = (g0, g1)
-        g0, g1 = self.bwd_graphs
+                unet_backward(eng, ws, tb, self.masks, self.x, ws.out, self.go, phase=11)
+            with torch.cuda.graph(g2, pool=g0.pool()):
+                unet_backward(eng, ws, tb, self.masks, self.x, ws.out, self.go, phase=12)
+            self.bwd_graphs = (g0, g1, g2)
+        g0, g1, g2 = self.bwd_graphs
         if dp:
+            # three NCCL buckets of the flat gradient buffer, each all-reduced (AVG) while the next graph segment runs:
+            # decoder + bottleneck (85 % of the bytes) | deep encoder | shallow encoder (1 MB: the only exposed exchange)
             import torch.distributed as dist
+            avg = dist.ReduceOp.AVG
+            handles = []
             g0.replay()
-            h0 = dist.all_reduce(tb.flat[self.tail:], op=dist.ReduceOp.AVG, async_op=True) if self.tail > 0 else None
+            if self.tail > 0:
+                handles.append(dist.all_reduce(tb.flat[self.tail:], op=avg, async_op=True))
             g1.replay()
-            h1 = dist.all_reduce(tb.flat[:self.tail] if self.tail > 0 else tb.flat, op=dist.ReduceOp.AVG, async_op=True)
-            if h0 is not None:
-                h0.wait()
-            h1.wait()
+            if self.tail > 0 and self.mid > 0:
+                handles.append(dist.all_reduce(tb.flat[self.mid:self.tail], op=avg, async_op=True))
+            g2.replay()
+            last = tb.flat[:self.mid] if (self.tail > 0 and self.mid > 0) else (tb.flat[:self.tail] if self.tail > 0 else tb.flat)
+            handles.append(dist.all_reduce(last, op=avg, async_op=True))
+            for h in handles:
+                h.wait()
             tb.last_allreduce_bytes = tb.flat.numel() * 4
         else:
             g0.replay()
             g1.replay()
+            g2.replay()
         return tuple(tb.gviews[k] for k in self.keys)
 
 
@@ -205,6 +222,45 @@ def unet_autograd_forward(model, x):
     return _UNetFunction.apply(model, x, *params)
 
 
+class _MaskedBCE(torch.autograd.Function):
+    """loss = mean(BCE(out * mask, gt * mask)) * numel / count_nonzero(mask) (utils_training.py:28-33 with nn.BCELoss) as
+    one fused kernel pair; the backward is one scaled copy of the gradient the forward already computed."""
+
+    @staticmethod
+    def forward(ctx, out, gt, mask):
+        from ._lib import call, ptr, stream_ptr
+        n = out.numel()
+        o, g, m = out.detach().contiguous(), gt.detach().contiguous(), mask.detach().contiguous()
+        grad_u = torch.empty_like(o)
+        loss = torch.empty((), dtype=torch.float32, device=out.device)
+        scale = torch.empty((), dtype=torch.float32, device=out.device)
+        import ctypes as C
+        lib = _lib.load()
+        partials = torch.empty(2 * lib.b2u_masked_bce_blocks(), dtype=torch.float64, device=out.device)
+        with torch.cuda.device(out.device):
+            call("b2u_masked_bce_fwd", ptr(o), ptr(g), ptr(m), C.c_longlong(n), ptr(grad_u), ptr(partials), ptr(loss), ptr(scale),
+                 stream_ptr())
+        ctx.save_for_backward(grad_u, scale)
+        return loss
+
+    @staticmethod
+    def backward(ctx, upstream):
+        from ._lib import call, ptr, stream_ptr
+        import ctypes as C
+        grad_u, scale = ctx.saved_tensors
+        up = upstream.detach().to(torch.float32).contiguous()
+        grad = torch.empty_like(grad_u)
+        with torch.cuda.device(grad_u.device):
+            call("b2u_masked_bce_bwd", ptr(grad_u), ptr(up), ptr(scale), ptr(grad), C.c_longlong(grad_u.numel()), stream_ptr())
+        return grad, None, None
+
+
+def _fusable_bce(loss_fcn, seg, gt, mask) -> bool:
+    return (type(loss_fcn) is nn.BCELoss and loss_fcn.reduction == "mean" and loss_fcn.weight is None
+            and seg.is_cuda and seg.dtype == torch.float32 and gt.dtype == torch.float32 and mask.dtype == torch.float32
+            and seg.shape == gt.shape == mask.shape and not gt.requires_grad and not mask.requires_grad)
+
+
 class BaseUNetTraining(nn.Module):
     """LightningModule-shaped shell: `self._model` (so checkpoints keep the `_model.` key prefix),
     `forward`, `training_step`, `validation_step`, `test_step`, `predict_step` with the reference's
@@ -225,6 +281,8 @@ class BaseUNetTraining(nn.Module):
     def _masked_loss(self, batch):
         im_batch, gt, mask = batch
         segmentation = self._model(im_batch)
+        if _fusable_bce(self._loss_fcn, segmentation, gt, mask):
+            return _MaskedBCE.apply(segmentation, gt, mask)      # the same arithmetic as the five lines below, fused
         segmentation = segmentation * mask
         gt = gt * mask
         loss = self._loss_fcn(segmentation, gt)
