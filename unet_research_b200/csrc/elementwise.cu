@@ -168,11 +168,13 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partials, int rows,
     s += static_cast<double>(v.x);
     q += static_cast<double>(v.y);
   }
-  __shared__ double sh[2][128];
+  // fixed-shape tree over the block (128 or 512 threads; the thread -> row assignment and the tree depend on the block
+  // size only, which the launcher derives from the row count alone: per-image results never depend on the batch)
+  __shared__ double sh[2][512];
   sh[0][threadIdx.x] = s;
   sh[1][threadIdx.x] = q;
   __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
     if (threadIdx.x < o) {
       sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
       sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
@@ -940,7 +942,10 @@ extern "C" int b2u_gn_finalize_ex(const float* partials, int rows_per_image, int
               subgroup_size, c / num_groups);
   B2U_REQUIRE(!keep_counts || images_per_call > 0, "images_per_call must be positive");
   dim3 grid(num_groups, n);
-  B2U_PDL_LAUNCH((gn_finalize_kernel), grid, 128, 0, reinterpret_cast<cudaStream_t>(stream), partials, rows_per_image, subgroup_size, gamma, beta, reinterpret_cast<float2*>(coef), c, num_groups, count, eps, keep_counts, images_per_call > 0 ? images_per_call : 1, numel_per_call, reinterpret_cast<float2*>(mean_rstd), shared_partials);
+  // the reduction is a chain of L2-latency-bound trips (4 loads in flight per thread): 512 threads for the long partial
+  // lists of the shallow levels (2664 tile rows at 592x576: 2 trips instead of 6), 128 for the short ones
+  const int fin_threads = static_cast<long>(rows_per_image) * ((c / num_groups) / subgroup_size) >= 1024 ? 512 : 128;
+  B2U_PDL_LAUNCH((gn_finalize_kernel), grid, fin_threads, 0, reinterpret_cast<cudaStream_t>(stream), partials, rows_per_image, subgroup_size, gamma, beta, reinterpret_cast<float2*>(coef), c, num_groups, count, eps, keep_counts, images_per_call > 0 ? images_per_call : 1, numel_per_call, reinterpret_cast<float2*>(mean_rstd), shared_partials);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
