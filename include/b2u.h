@@ -192,7 +192,7 @@ typedef struct {
   int32_t block_size;         /* odd, <= 31                                                           */
   int32_t count_index;        /* slot of keep_counts this call adds to                                */
   int32_t dilate_first_block; /* first block of this call in the flat dilate grid: filled by b2u_dropblock_plan */
-  int32_t reserved;
+  int32_t reserved;           /* first block of this call in the v2 (NHWC) dilate grid: filled by b2u_dropblock_plan */
 } b2u_dropblock_call;
 /* Fills dilate_first_block of every descriptor of a HOST table (prefix sum of the blocks each call needs in
  * b2u_dropblock_dilate's flat 1-D grid) and returns the total in *total_blocks.  Call it once, after the shapes are
@@ -214,6 +214,12 @@ int b2u_dropblock_centers_ichan(const b2u_dropblock_call* table, int n_calls, co
 int b2u_dropblock_dilate(const b2u_dropblock_call* table, int n_calls, const b2u_dropblock_call* host_table,
                          const uint32_t* center_bits, uint32_t* mask_bits, unsigned long long* keep_counts,
                          void* stream);
+/* The same dilation for block_size 7 without the 32x32 bit transpose: the (sparse, gamma ~ 0.3 %) centres are scattered
+ * with atomicOr into a zeroed NHWC word bitmap `scatter_bits` (same size and offsets as mask_bits: mask_words_total uint32
+ * words, zeroed by this call), then keep = ~(7x7 box OR) runs word-parallel over 32 channels.  Bit-identical output. */
+int b2u_dropblock_dilate_v2(const b2u_dropblock_call* table, int n_calls, const b2u_dropblock_call* host_table,
+                            const uint32_t* center_bits, uint32_t* scatter_bits, long long mask_words_total,
+                            uint32_t* mask_bits, unsigned long long* keep_counts, void* stream);
 /* centre bitmap from caller-supplied uniforms (parity mode: feed the oracle's captured torch.rand values) */
 int b2u_dropblock_centers_from_uniform(const float* u, uint32_t* center_bits, long long numel, float gamma,
                                        void* stream);

@@ -106,7 +106,10 @@ def test_head_and_mc_accumulate():
     assert D.sec_head() < 1e-6
 
 
-def test_dropblock_masks_bit_exact_vs_torch_rand():
+@pytest.mark.parametrize("dilate", ["v2", "v1"])
+def test_dropblock_masks_bit_exact_vs_torch_rand(dilate, monkeypatch):
+    """v2 = sparse NHWC scatter + word-parallel 7x7 OR (default for block size 7), v1 = 32x32 bit-transpose kernel."""
+    monkeypatch.setenv("B2U_DILATE", dilate)
     for r in D.sec_dropblock():
         assert r["mismatches"] == 0
         assert r["keep"] == r["keep_ref"]
@@ -708,3 +711,25 @@ def test_fused_masked_bce_matches_torch():
         assert abs(float(got) - float(ref)) <= 1e-6 * abs(float(ref)), (float(got), float(ref))
         assert D.rel(o2.grad, o1.grad)[0] < 1e-6
         assert float(o2.grad[fov_d == 0].abs().max()) == 0.0
+
+
+def test_dilate_v2_matches_v1_on_the_unet_call_table():
+    """The whole 22-site x n_calls table of a Monte-Carlo step: keep masks and keep counts of the v2 dilation (sparse NHWC
+    scatter) equal the v1 kernel's bit for bit, for one and for several images per call, and for the ichan centres."""
+    from unet_research_b200.engine import MaskPlan
+    dev = torch.device("cuda")
+    for (n_calls, ipc, h, w, mode) in ((3, 1, 144, 128, "dropblock2d"), (1, 2, 160, 176, "dropblock2d"), (2, 1, 592, 576, "dropblock2d"),
+                                        (2, 1, 144, 128, "ichan")):
+        outs = []
+        for ver in ("v1", "v2"):
+            os.environ["B2U_DILATE"] = ver
+            try:
+                mp = MaskPlan(n_calls, ipc, h, w, 64, 4, 0.15, 7, dev, mode=mode)
+            finally:
+                os.environ.pop("B2U_DILATE", None)
+            assert mp.dilate_v2 == (ver == "v2")
+            mp.set_stream_position(1000)
+            mp.generate(1234)
+            torch.cuda.synchronize()
+            outs.append((mp.mask_bits.clone(), mp.keep_counts.clone()))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), (n_calls, ipc, h, w, mode)

@@ -342,6 +342,178 @@ __global__ void __launch_bounds__(128) dropblock_dilate_kernel(const b2u_dropblo
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// v2 of the dilation (round 2): no 32x32 bit transpose.  Only gamma ~ 0.3 % of the draws are centres, so
+//   1. scatter : every set bit of the compact NCHW centre bitmap is OR-ed (atomicOr: order-independent) into a zeroed
+//                NHWC WORD bitmap P[img][y + bs/2][x + bs/2][c / 32] (bit c % 32) -- the zero-padded centre map of
+//                utils_modules.py:51-53 in the layout the keep mask is wanted in;
+//   2. dilate  : keep = ~(bs x bs box OR of P) is then word-parallel over 32 channels: a thread owns one (pixel, channel
+//                word) column of a 32-row band, ORs its bs horizontal neighbours per row and keeps the last bs row
+//                results in a register ring (unrolled by bs, so the ring is static).
+// ~35 instructions per output word instead of ~100; the flat call table is reused (`reserved` = first block of a call in
+// the v2 grid).
+constexpr int kD2Threads = 128;
+constexpr int kD2Band = 32;
+
+static inline int dilate2_blocks(const b2u_dropblock_call& c) {
+  const int cgs = c.c / 32;
+  return c.n_img * ((c.h + kD2Band - 1) / kD2Band) * ((c.w * cgs + kD2Threads - 1) / kD2Threads);
+}
+
+__global__ void __launch_bounds__(256) dropblock_scatter_kernel(const b2u_dropblock_call* __restrict__ table,
+                                                                const uint32_t* __restrict__ center_bits, uint32_t* __restrict__ pbits) {
+  pdl_wait();
+  pdl_trigger();
+  const b2u_dropblock_call c = table[blockIdx.y];
+  const int bs = c.block_size, ex = bs >> 1;
+  const uint32_t hc = c.h - bs + 1, wc = c.w - bs + 1;
+  const uint32_t plane = hc * wc;
+  const uint32_t nbits = static_cast<uint32_t>(c.n_img) * c.c * plane;     // < 2^32 (checked by the host)
+  const uint32_t nchunks = (nbits + 127u) >> 7;                            // 128-bit chunks (the bitmap is padded)
+  if (blockIdx.x * 256u >= nchunks) return;                                // the grid is sized for the largest call
+  // A lane scans 128 consecutive bits per trip (one LDG.128): ~0.4 centres per chunk, so the decode below runs ~2.5
+  // times per warp trip of 4096 bits instead of ~6 times with one word per lane.  The decode locates the chunk's first
+  // bit with ONE fp64 reciprocal division (exact after a one-step correction) and walks from there; row / channel
+  // splits use 32-bit multiply-high reciprocals (dividends < 2^20 and < 2^16: floor(2^32 / d) + 1 is exact there).
+  const double inv_plane = 1.0 / static_cast<double>(plane);
+  const uint32_t mw = wc > 1 ? static_cast<uint32_t>((1ull << 32) / wc) + 1u : 0u;
+  const uint32_t mc = c.c > 1 ? static_cast<uint32_t>((1ull << 32) / static_cast<uint32_t>(c.c)) + 1u : 0u;
+  const uint4* cb = reinterpret_cast<const uint4*>(center_bits + c.center_word_off);
+  uint32_t* pb = pbits + c.mask_word_off;
+  const uint32_t cgs = c.c >> 5;
+  const uint32_t prow = static_cast<uint32_t>(c.w) * cgs, pimg = static_cast<uint32_t>(c.h) * prow;   // < 2^31 words per call (host)
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < nchunks; i += gridDim.x * 256u) {
+    const uint4 q = __ldg(cb + i);
+    uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+    if ((q.x | q.y | q.z | q.w) == 0u) continue;
+    const uint32_t e0 = i << 7;
+    uint32_t pl0 = __double2uint_rz(static_cast<double>(e0) * inv_plane);
+    uint32_t rem0 = e0 - pl0 * plane;
+    if (static_cast<int32_t>(rem0) < 0) { --pl0; rem0 += plane; }
+    else if (rem0 >= plane) { ++pl0; rem0 -= plane; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t wd = wds[k];
+      while (wd) {
+        const uint32_t b = __ffs(wd) - 1;
+        wd &= wd - 1u;
+        const uint32_t e = e0 + 32u * k + b;
+        if (e >= nbits) break;                                             // padding bits of the last chunk
+        uint32_t pl = pl0, rem = rem0 + 32u * k + b;
+        while (rem >= plane) { rem -= plane; ++pl; }
+        const uint32_t y = mw ? __umulhi(rem, mw) : rem, x = rem - y * wc;
+        const uint32_t img = mc ? __umulhi(pl, mc) : pl, ch = pl - img * c.c;
+        atomicOr(pb + (img * pimg + (y + ex) * prow + (x + ex) * cgs + (ch >> 5)), 1u << (ch & 31u));
+      }
+    }
+  }
+}
+
+// One (image, 32-row band, 128-word strip) per block; CGS = channel words per pixel when it is one of the U-Net's
+// (compile-time neighbour offsets: the seven loads of a row need no address arithmetic), 0 = generic.
+template <int BS, int CGS>
+__device__ __forceinline__ void dilate_nhwc_block(const b2u_dropblock_call& c, int local, const uint32_t* __restrict__ pbits,
+                                                  uint32_t* __restrict__ mask_bits, unsigned long long* __restrict__ keep_counts) {
+  constexpr int EX = BS / 2;
+  const int cgs = CGS > 0 ? CGS : (c.c >> 5);
+  const int roww = c.w * cgs;                                 // words per image row
+  const int strips = (roww + kD2Threads - 1) / kD2Threads;
+  const int bands = (c.h + kD2Band - 1) / kD2Band;
+  const int strip = local % strips;
+  local /= strips;
+  const int band = local % bands;
+  const int img = local / bands;
+  const int j = strip * kD2Threads + threadIdx.x;             // word column inside the row: (pixel, channel word)
+  const bool col_ok = j < roww;
+  const int px = col_ok ? j / cgs : 0;
+  const int h_begin = band * kD2Band;
+  const int h_end = min(h_begin + kD2Band, c.h);
+  const size_t base = c.mask_word_off + static_cast<size_t>(img) * c.h * roww + j;
+  const uint32_t* pcol = pbits + base;                        // this column, row 0
+  uint32_t* mcol = mask_bits + base;
+  // interior columns (all BS horizontal neighbours exist) take the unpredicated path; a warp holds 32 / cgs pixels, so
+  // only the warps at the two ends of a row diverge
+  const bool interior = col_ok && px >= EX && px + EX < c.w;
+  bool nb_ok[BS];
+#pragma unroll
+  for (int t = 0; t < BS; ++t) nb_ok[t] = col_ok && px + t - EX >= 0 && px + t - EX < c.w;
+  auto hsmear = [&](int r) -> uint32_t {
+    uint32_t v = 0u;
+    if (r >= 0 && r < c.h) {                                  // uniform per block
+      const uint32_t* rowp = pcol + static_cast<size_t>(r) * roww;
+      if (interior) {
+        uint32_t q[BS];
+#pragma unroll
+        for (int t = 0; t < BS; ++t) q[t] = __ldg(rowp + (t - EX) * cgs);
+#pragma unroll
+        for (int t = 0; t < BS; ++t) v |= q[t];
+      } else {
+#pragma unroll
+        for (int t = 0; t < BS; ++t)
+          if (nb_ok[t]) v |= __ldg(rowp + (t - EX) * cgs);
+      }
+    }
+    return v;
+  };
+  uint32_t ring[BS];
+#pragma unroll
+  for (int t = 0; t < BS - 1; ++t) ring[t] = hsmear(h_begin - EX + t);      // rows h_begin - EX .. h_begin + EX - 1
+  unsigned int keep = 0;
+  // output row r needs rows r - EX .. r + EX; the loop is unrolled by BS so that the ring slot is a compile-time index
+  for (int r0 = h_begin; r0 < h_end; r0 += BS) {
+#pragma unroll
+    for (int u = 0; u < BS; ++u) {
+      const int r = r0 + u;
+      if (r < h_end) {
+        ring[(u + BS - 1) % BS] = hsmear(r + EX);
+        uint32_t drop = 0u;
+#pragma unroll
+        for (int t = 0; t < BS; ++t) drop |= ring[t];
+        if (col_ok) {
+          const uint32_t kw = ~drop;
+          keep += __popc(kw);
+          mcol[static_cast<size_t>(r) * roww] = kw;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+  __shared__ unsigned int wsum[kD2Threads / 32];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = keep;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tot = 0;
+    for (int wv = 0; wv < kD2Threads / 32; ++wv) tot += wsum[wv];
+    if (tot) atomicAdd(keep_counts + c.count_index, tot);       // integer atomics: order-independent, deterministic
+  }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(kD2Threads) dropblock_dilate_nhwc_kernel(const b2u_dropblock_call* __restrict__ table, int n_calls,
+                                                                         int total_blocks, const uint32_t* __restrict__ pbits,
+                                                                         uint32_t* __restrict__ mask_bits,
+                                                                         unsigned long long* __restrict__ keep_counts) {
+  pdl_wait();
+  pdl_trigger();
+  int k = 0, hi_k = n_calls - 1;
+  while (k < hi_k) {                                          // last call whose first v2 block is <= blockIdx.x
+    const int mid = (k + hi_k + 1) >> 1;
+    if (__ldg(&table[mid].reserved) <= static_cast<int>(blockIdx.x)) k = mid;
+    else hi_k = mid - 1;
+  }
+  const b2u_dropblock_call c = table[k];
+  const int local = static_cast<int>(blockIdx.x) - c.reserved;
+  switch (c.c >> 5) {                                         // uniform per block
+    case 2: dilate_nhwc_block<BS, 2>(c, local, pbits, mask_bits, keep_counts); break;
+    case 4: dilate_nhwc_block<BS, 4>(c, local, pbits, mask_bits, keep_counts); break;
+    case 8: dilate_nhwc_block<BS, 8>(c, local, pbits, mask_bits, keep_counts); break;
+    case 16: dilate_nhwc_block<BS, 16>(c, local, pbits, mask_bits, keep_counts); break;
+    case 32: dilate_nhwc_block<BS, 32>(c, local, pbits, mask_bits, keep_counts); break;
+    default: dilate_nhwc_block<BS, 0>(c, local, pbits, mask_bits, keep_counts); break;
+  }
+}
+
 }  // namespace b2u
 
 using namespace b2u;
@@ -389,6 +561,12 @@ extern "C" int b2u_dropblock_plan(b2u_dropblock_call* host_table, int n_calls, l
     c.dilate_first_block = static_cast<int32_t>(total);
     total += dilate_blocks(c);
   }
+  long long total2 = 0;                                       // v2 (NHWC) dilation grid: `reserved` = first block of the call
+  for (int i = 0; i < n_calls; ++i) {
+    host_table[i].reserved = static_cast<int32_t>(total2);
+    total2 += dilate2_blocks(host_table[i]);
+    B2U_REQUIRE(total2 < 0x7fffffffll, "too many dilate blocks");
+  }
   B2U_REQUIRE(total < 0x7fffffffll, "too many dilate blocks");
   if (total_blocks) *total_blocks = total;
   return B2U_OK;
@@ -430,6 +608,39 @@ extern "C" int b2u_dropblock_centers_from_uniform(const float* u, uint32_t* cent
   long long blocks = (warps + 7) / 8;
   if (blocks > b2u_num_sms() * 8) blocks = b2u_num_sms() * 8;
   dropblock_centers_from_uniform_kernel<<<static_cast<int>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(u, center_bits, numel, gamma);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+
+extern "C" int b2u_dropblock_dilate_v2(const b2u_dropblock_call* table, int n_calls, const b2u_dropblock_call* host_table,
+                                       const uint32_t* center_bits, uint32_t* scatter_bits, long long mask_words_total,
+                                       uint32_t* mask_bits, unsigned long long* keep_counts, void* stream) {
+  B2U_REQUIRE(table && host_table && center_bits && scatter_bits && mask_bits && keep_counts && n_calls > 0 && mask_words_total > 0,
+              "bad arguments");
+  long long total = 0;
+  uint32_t max_words = 0;
+  for (int i = 0; i < n_calls; ++i) {
+    const b2u_dropblock_call& c = host_table[i];
+    B2U_REQUIRE(c.block_size == 7, "b2u_dropblock_dilate_v2 is built for block_size 7 (got %d): use b2u_dropblock_dilate", c.block_size);
+    B2U_REQUIRE(c.c % 32 == 0 && c.c > 0, "channels must be a multiple of 32 (got %d)", c.c);
+    B2U_REQUIRE(c.reserved == total, "call table was not planned (b2u_dropblock_plan) or changed shape afterwards");
+    total += dilate2_blocks(c);
+    const double nbits = static_cast<double>(c.n_img) * c.c * (c.h - c.block_size + 1) * (c.w - c.block_size + 1);
+    B2U_REQUIRE(nbits < 4294967295.0, "one DropBlock call is limited to 2^32 - 1 centre positions");
+    const uint32_t words = static_cast<uint32_t>((static_cast<unsigned long long>(nbits) + 31ull) >> 5);
+    if (words > max_words) max_words = words;
+    B2U_REQUIRE(static_cast<double>(c.n_img) * c.h * c.w * (c.c / 32) < 2147483648.0, "one DropBlock call is limited to 2^31 mask words");
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  B2U_CHECK_CUDA(cudaMemsetAsync(scatter_bits, 0, static_cast<size_t>(mask_words_total) * 4, st));
+  const unsigned max_chunks = (max_words + 3u) / 4u;
+  unsigned bx = (max_chunks + 256u * 4u - 1u) / (256u * 4u);            // ~4 chunks of 128 bits per thread (grid-stride)
+  if (bx < 1u) bx = 1u;
+  dim3 sgrid(bx, n_calls);
+  dropblock_scatter_kernel<<<sgrid, 256, 0, st>>>(table, center_bits, scatter_bits);
+  B2U_LAUNCH_CHECK();
+  B2U_PDL_LAUNCH((dropblock_dilate_nhwc_kernel<7>), dim3(static_cast<unsigned>(total)), kD2Threads, 0, st, table, n_calls,
+                 static_cast<int>(total), scatter_bits, mask_bits, keep_counts);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

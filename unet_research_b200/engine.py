@@ -190,7 +190,7 @@ class MaskPlan:
                 d.n_img, d.c, d.h, d.w = images_per_call, c, hh, ww
                 d.block_size = block_size
                 d.count_index = s * n_calls + b
-                center_words += (numel + 31) // 32 + 2
+                center_words += ((numel + 31) // 32 + 2 + 3) // 4 * 4     # 16-byte aligned: the v2 scatter reads uint4 chunks
             mask_words += n_img * hh * ww * (c // 32)
         self.host_table = calls
         call("b2u_dropblock_plan", calls, n_calls * self.n_sites, None)     # flat dilate grid: first block of every call
@@ -199,6 +199,11 @@ class MaskPlan:
         self.center_words = center_words + 4
         self.center_bits = torch.zeros(center_words + 4, dtype=torch.int32, device=device)
         self.mask_bits = torch.empty(mask_words, dtype=torch.int32, device=device)
+        # v2 dilation (block size 7): sparse scatter of the centres into an NHWC word bitmap + word-parallel 7x7 OR
+        import os
+        self.mask_words = mask_words
+        self.dilate_v2 = block_size == 7 and os.environ.get("B2U_DILATE", "v2") != "v1"
+        self.scatter_bits = torch.empty(mask_words, dtype=torch.int32, device=device) if self.dilate_v2 else None
         self.keep_counts = torch.zeros(self.n_sites * n_calls, dtype=torch.int64, device=device)
         self.offset_base = torch.zeros(1, dtype=torch.int64, device=device)
 
@@ -231,8 +236,12 @@ class MaskPlan:
         else:
             call("b2u_dropblock_centers", ptr(self.table), n, C.c_uint64(seed & (2 ** 64 - 1)), ptr(self.offset_base),
                  ptr(self.center_bits), stream_ptr())
-        call("b2u_dropblock_dilate", ptr(self.table), n, self.host_table, ptr(self.center_bits), ptr(self.mask_bits),
-             ptr(self.keep_counts), stream_ptr())
+        if self.dilate_v2:
+            call("b2u_dropblock_dilate_v2", ptr(self.table), n, self.host_table, ptr(self.center_bits), ptr(self.scatter_bits),
+                 self.mask_words, ptr(self.mask_bits), ptr(self.keep_counts), stream_ptr())
+        else:
+            call("b2u_dropblock_dilate", ptr(self.table), n, self.host_table, ptr(self.center_bits), ptr(self.mask_bits),
+                 ptr(self.keep_counts), stream_ptr())
 
     def advance(self, n_calls: Optional[int] = None):
         call("b2u_advance_counter", ptr(self.offset_base), (n_calls or self.n_calls) * self.offset_per_call, stream_ptr())

@@ -20,6 +20,19 @@ from . import _lib
 from ._lib import DropblockCall, call, ptr, stream_ptr
 
 
+def _dilate(table, d, centers, bits, keep):
+    """Centre bitmap -> NHWC keep mask + keep count for a one-entry call table: the v2 kernels (sparse NHWC scatter +
+    word-parallel 7x7 OR) for the reference's block size 7, the generic bit-transpose kernel otherwise (B2U_DILATE=v1
+    forces it)."""
+    import os
+    if d.block_size == 7 and os.environ.get("B2U_DILATE", "v2") != "v1":
+        scatter = torch.empty_like(bits)
+        call("b2u_dropblock_dilate_v2", ptr(table), 1, C.byref(d), ptr(centers), ptr(scatter), bits.numel(), ptr(bits), ptr(keep),
+             stream_ptr())
+    else:
+        call("b2u_dropblock_dilate", ptr(table), 1, C.byref(d), ptr(centers), ptr(bits), ptr(keep), stream_ptr())
+
+
 class DropBlock2D(nn.Module):
     def __init__(self, drop_prob, block_size):
         super().__init__()
@@ -55,7 +68,7 @@ class DropBlock2D(nn.Module):
         bits = torch.empty(n * h * w * (c // 32), dtype=torch.int32, device=x.device)
         keep = torch.zeros(1, dtype=torch.int64, device=x.device)
         call("b2u_dropblock_centers", ptr(table), 1, C.c_uint64(seed & (2 ** 64 - 1)), None, ptr(centers), stream_ptr())
-        call("b2u_dropblock_dilate", ptr(table), 1, C.byref(d), ptr(centers), ptr(bits), ptr(keep), stream_ptr())
+        _dilate(table, d, centers, bits, keep)
         gen.set_offset(offset + rand_offset_increment(numel, sms, mt))
         shifts = torch.arange(32, device=x.device, dtype=torch.int32)
         m = ((bits.view(n, h, w, c // 32, 1) >> shifts) & 1).reshape(n, h, w, c).permute(0, 3, 1, 2)
@@ -153,7 +166,7 @@ class _SingleSitePlan:
         self.keep.zero_()
         call("b2u_dropblock_centers_ichan", ptr(table), 1, C.byref(self.d), C.c_uint64(seed & (2 ** 64 - 1)), None,
              ptr(self.centers), self.words, stream_ptr())
-        call("b2u_dropblock_dilate", ptr(table), 1, C.byref(self.d), ptr(self.centers), ptr(self.bits), ptr(self.keep), stream_ptr())
+        _dilate(table, self.d, self.centers, self.bits, self.keep)
 
     def mask_nchw(self, dtype):
         shifts = torch.arange(32, device=self.device, dtype=torch.int32)
