@@ -348,7 +348,7 @@ def run_gpu(args):
     eb = elementwise_bytes_per_step(NB, fused=runner.eng.fused_prologue if hasattr(runner.eng, "fused_prologue") else False)
     hbm = {}
     for name, nbytes in eb.items():
-        key = name if name in other else name.replace("b2u_gn_finalize", "b2u_gn_finalize_ex")
+        key = next((k for k in (name, name + "_ex", name + "_v2") if k in other), name)
         if key in other and other[key] > 0 and nbytes > 0:
             gbs = nbytes / (other[key] / 1000.0) / 1e9
             hbm[name] = {"algorithmic_mb_per_step": nbytes / 1e6, "ms_per_step": other[key], "achieved_gbs": gbs,

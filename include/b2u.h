@@ -203,6 +203,11 @@ int b2u_dropblock_plan(b2u_dropblock_call* host_table, int n_calls, long long* t
  * philox_offset (lets a captured CUDA graph advance the stream between replays); may be NULL. */
 int b2u_dropblock_centers(const b2u_dropblock_call* table, int n_calls, uint64_t seed,
                           const unsigned long long* offset_base, uint32_t* center_bits, void* stream);
+/* Same stream of draws; the host copy of the table lets the launcher split every thread's trips over short blocks
+ * (grid.z): the Monte-Carlo loop overlaps this kernel with the forward on a low-priority stream, and a forward kernel can
+ * only start on an SM once resident mask blocks have drained. */
+int b2u_dropblock_centers_ex(const b2u_dropblock_call* table, int n_calls, const b2u_dropblock_call* host_table,
+                             uint64_t seed, const unsigned long long* offset_base, uint32_t* center_bits, void* stream);
 /* Dropblock2d_ichan (utils_modules.py:86-139): centres = torch.bernoulli(p = gamma) over the full [N,C,H,W] tensor
  * (ATen bernoulli_tensor_cuda_kernel: thread idx draws one curand_uniform4 for elements 4*idx..4*idx+3, `u <= p`),
  * border of bs/2 zeroed; written into the same compact centre bitmap, so b2u_dropblock_dilate follows unchanged.

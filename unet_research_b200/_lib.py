@@ -99,6 +99,7 @@ SIGNATURES = {
     "b2u_mc_accumulate": (_I, [_P, _P, _P, _P, _P, _I, _LL, _I, _P]),
     "b2u_advance_counter": (_I, [_P, _LL, _P]),
     "b2u_dropblock_centers": (_I, [_P, _I, C.c_uint64, _P, _P, _P]),
+    "b2u_dropblock_centers_ex": (_I, [_P, _I, C.POINTER(DropblockCall), C.c_uint64, _P, _P, _P]),
     "b2u_dropblock_centers_ichan": (_I, [_P, _I, C.POINTER(DropblockCall), C.c_uint64, _P, _P, _LL, _P]),
     "b2u_dropblock_plan": (_I, [C.POINTER(DropblockCall), _I, C.POINTER(_LL)]),
     "b2u_dropblock_dilate": (_I, [_P, _I, C.POINTER(DropblockCall), _P, _P, _P, _P]),
@@ -121,7 +122,7 @@ _lib: Optional[C.CDLL] = None
 launch_count = 0          # kernels launched through this binding (bench.py reports it as gpu_launches)
 _LAUNCHERS = {"b2u_conv3x3_fwd": 1, "b2u_conv3x3_pro_fwd": 1, "b2u_convT2x2_fwd": 1, "b2u_conv_first_fwd": 1, "b2u_gn_finalize": 1, "b2u_gn_finalize_ex": 1,
               "b2u_gn_apply": 1, "b2u_gn_apply_pool": 1, "b2u_head_fwd": 1, "b2u_mc_finalize": 1,
-              "b2u_mc_accumulate": 1, "b2u_advance_counter": 1, "b2u_dropblock_centers": 1,
+              "b2u_mc_accumulate": 1, "b2u_advance_counter": 1, "b2u_dropblock_centers": 1, "b2u_dropblock_centers_ex": 1,
               "b2u_dropblock_dilate": 1, "b2u_dropblock_dilate_v2": 2, "b2u_dropblock_centers_ichan": 1, "b2u_dropblock_centers_from_uniform": 1, "b2u_rotate_bilinear": 1, "b2u_masked_bce_fwd": 2, "b2u_masked_bce_bwd": 1, "b2u_rotate_in_table": 1, "b2u_rotate_back_accumulate": 1,
               "b2u_pack_conv3x3_weight": 1, "b2u_pack_conv3x3_weight_pair": 1, "b2u_pack_convT2x2_weight": 1, "b2u_unit_bwd_stats": 1, "b2u_unit_bwd_finalize": 2,
               "b2u_unit_bwd_apply": 1, "b2u_wgrad": 2, "b2u_wgrad_first": 2, "b2u_gemm1x1_fwd": 1,

@@ -13,6 +13,8 @@
 //            and a popcount for block_mask.sum().
 #include "b2u_common.cuh"
 
+#include <stdlib.h>
+
 namespace b2u {
 
 // 32x32 -> 64 multiply as ONE IMAD.WIDE.U32 (the C++ uint64 product makes ptxas add a zero high-word
@@ -58,15 +60,24 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 // Blocks are SHORT on purpose: next to the high-priority forward pass the block scheduler hands freed SM slots to the
 // forward's CTAs first, so the mask build only fills what the forward leaves idle (a persistent grid keeps its warps
 // resident and was measured to destroy that overlap: 11.4 instead of 8.8 ms per Monte-Carlo step).
+constexpr uint32_t kMaxFastTrips = 64;
+
 __global__ void __launch_bounds__(256) dropblock_centers_kernel(const b2u_dropblock_call* __restrict__ table, uint64_t seed,
                                          const unsigned long long* __restrict__ offset_base,
-                                         uint32_t* __restrict__ center_bits) {
+                                         uint32_t* __restrict__ center_bits, uint32_t trips_per_block) {
   pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
   pdl_trigger();    // the successor may be scheduled once every CTA got here
   const b2u_dropblock_call c = table[blockIdx.y];
   if (blockIdx.x >= c.grid) return;
   const uint32_t tn = c.grid * 256u;
   const uint32_t trips = (c.numel - 1u) / (tn * 4u) + 1u;     // numel <= 2^32-1, tn*4 <= 2^21 * ... fits
+  // blockIdx.z splits a thread's trips into runs of trips_per_block (0 = all): a block lives ~1 us instead of up to ~10 us (36
+  // trips at the largest site).  The forward's kernels (high-priority stream) can only start on an SM once resident
+  // low-priority blocks have drained -- there is no preemption -- so the mask blocks' LIFETIME is a start-up delay for
+  // every one of the ~63 forward launches of a step.
+  const uint32_t trip_begin = trips_per_block ? blockIdx.z * trips_per_block : 0u;
+  if (trip_begin >= trips) return;
+  const uint32_t trip_end = trips_per_block ? min(trips, trip_begin + trips_per_block) : trips;
   const uint64_t off = c.philox_offset + (offset_base ? *offset_base : 0ull);
   const uint64_t ctr_base = off >> 2;                         // curand skipahead: offset counts 32-bit words
   const uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
@@ -80,22 +91,21 @@ __global__ void __launch_bounds__(256) dropblock_centers_kernel(const b2u_dropbl
   uint32_t my_trips = 0u;
   const uint64_t first = static_cast<uint64_t>(lane) * tn + idx0;
   if (lane < 4u && first < c.numel) my_trips = static_cast<uint32_t>((c.numel - first - 1ull) / (4ull * tn)) + 1u;
-  uint32_t* wp = center_bits + c.center_word_off + (first >> 5);
   const uint32_t wstep = tn >> 3;                              // words per trip (4 tn bits)
+  uint32_t* wp = center_bits + c.center_word_off + (first >> 5) + static_cast<size_t>(trip_begin) * wstep;
   const bool is1 = lane == 1u, is2 = lane == 2u, is3 = lane == 3u;
   // The counter is (offset/4 + trip, idx): its first word is the same for EVERY thread of the call and its second word is
   // fixed per thread, so the first two rounds split into a part that depends only on the trip (computed once per block
   // into shared memory: 3 words per trip) and a part that depends only on the thread (hoisted out of the trip loop).
   // Per trip that leaves 16 of the 20 wide multiplies -- the pipe the kernel is bound by.  Needs the low counter word
-  // not to wrap inside the call (otherwise, and for more than kMaxFastTrips trips, the plain loop below runs).
-  constexpr int kMaxFastTrips = 64;
+  // not to wrap inside the call (otherwise the plain loop below runs).
   __shared__ uint4 trip_u[kMaxFastTrips];
   const uint32_t ctr_lo = static_cast<uint32_t>(ctr_base), ctr_hi = static_cast<uint32_t>(ctr_base >> 32);
-  const bool fast = trips <= static_cast<uint32_t>(kMaxFastTrips) && ctr_lo + (trips - 1u) >= ctr_lo;   // uniform per block
+  const bool fast = trip_end - trip_begin <= kMaxFastTrips && ctr_lo + (trips - 1u) >= ctr_lo;   // uniform per block
   if (fast) {
-    if (threadIdx.x < trips) {
+    if (threadIdx.x < trip_end - trip_begin) {
       uint32_t h0, l0, h1, l1;
-      mulhilo(0xD2511F53u, ctr_lo + threadIdx.x, h0, l0);                 // round 1, counter word 0
+      mulhilo(0xD2511F53u, ctr_lo + trip_begin + threadIdx.x, h0, l0);    // round 1, counter word 0
       const uint32_t c2p = h0 ^ k1;                                       // (c3 = 0)
       mulhilo(0xCD9E8D57u, c2p, h1, l1);                                  // round 2, the trip-only product
       trip_u[threadIdx.x] = make_uint4(h1 ^ (k0 + 0x9E3779B9u), l1, l0 ^ (k1 + 0xBB67AE85u), 0u);
@@ -105,8 +115,8 @@ __global__ void __launch_bounds__(256) dropblock_centers_kernel(const b2u_dropbl
     mulhilo(0xCD9E8D57u, idx, hi_i, lo_i);                               // round 1, counter word 2 = idx
     mulhilo(0xD2511F53u, hi_i ^ ctr_hi ^ k0, h0p, l0p);                  // round 2, the thread-only product
 #pragma unroll 1
-    for (uint32_t trip = 0; trip < trips; ++trip) {
-      const uint4 u = trip_u[trip];
+    for (uint32_t trip = trip_begin; trip < trip_end; ++trip) {
+      const uint4 u = trip_u[trip - trip_begin];
       uint32_t r[4];
       philox_rounds<2>(u.x ^ lo_i, u.y, h0p ^ u.z, l0p, k0, k1, r);      // state after round 2, rounds 3..10 follow
       uint32_t words[4];
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(256) dropblock_centers_kernel(const b2u_dropbl
     return;
   }
 #pragma unroll 1
-  for (uint32_t trip = 0; trip < trips; ++trip) {
+  for (uint32_t trip = trip_begin; trip < trip_end; ++trip) {
     const uint64_t ctr = ctr_base + trip;
     uint32_t r[4];
     philox4x32_10(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), idx, 0u, k0, k1, r);
@@ -375,9 +385,18 @@ __global__ void __launch_bounds__(256) dropblock_scatter_kernel(const b2u_dropbl
   // times per warp trip of 4096 bits instead of ~6 times with one word per lane.  The decode locates the chunk's first
   // bit with ONE fp64 reciprocal division (exact after a one-step correction) and walks from there; row / channel
   // splits use 32-bit multiply-high reciprocals (dividends < 2^20 and < 2^16: floor(2^32 / d) + 1 is exact there).
-  const double inv_plane = 1.0 / static_cast<double>(plane);
-  const uint32_t mw = wc > 1 ? static_cast<uint32_t>((1ull << 32) / wc) + 1u : 0u;
-  const uint32_t mc = c.c > 1 ? static_cast<uint32_t>((1ull << 32) / static_cast<uint32_t>(c.c)) + 1u : 0u;
+  // (the three reciprocals are computed by ONE thread per block: as per-thread prologue they were 80 % of the kernel's
+  // instructions -- 570 k warps x ~300 instructions of software division)
+  __shared__ double sh_inv;
+  __shared__ uint32_t sh_mw, sh_mc;
+  if (threadIdx.x == 0) {
+    sh_inv = 1.0 / static_cast<double>(plane);
+    sh_mw = wc > 1 ? 0xFFFFFFFFu / wc + 1u : 0u;               // floor(2^32 / d) + 1 for d >= 2
+    sh_mc = c.c > 1 ? 0xFFFFFFFFu / static_cast<uint32_t>(c.c) + 1u : 0u;
+  }
+  __syncthreads();
+  const double inv_plane = sh_inv;
+  const uint32_t mw = sh_mw, mc = sh_mc;
   const uint4* cb = reinterpret_cast<const uint4*>(center_bits + c.center_word_off);
   uint32_t* pb = pbits + c.mask_word_off;
   const uint32_t cgs = c.c >> 5;
@@ -386,23 +405,27 @@ __global__ void __launch_bounds__(256) dropblock_scatter_kernel(const b2u_dropbl
     const uint4 q = __ldg(cb + i);
     uint32_t wds[4] = {q.x, q.y, q.z, q.w};
     if ((q.x | q.y | q.z | q.w) == 0u) continue;
+    // position of the chunk's first bit: plane (= img * C + ch), row, column -- one fp64 reciprocal division (exact after
+    // a one-step correction) and two multiply-high divisions per NON-EMPTY chunk; the set bits then walk from there
+    // with compare-and-wrap only (a chunk spans 128 positions: a handful of row wraps, at most a few plane wraps)
     const uint32_t e0 = i << 7;
     uint32_t pl0 = __double2uint_rz(static_cast<double>(e0) * inv_plane);
     uint32_t rem0 = e0 - pl0 * plane;
     if (static_cast<int32_t>(rem0) < 0) { --pl0; rem0 += plane; }
     else if (rem0 >= plane) { ++pl0; rem0 -= plane; }
+    const uint32_t y0 = mw ? __umulhi(rem0, mw) : rem0, x0 = rem0 - y0 * wc;
+    const uint32_t img0 = mc ? __umulhi(pl0, mc) : pl0, ch0 = pl0 - img0 * c.c;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       uint32_t wd = wds[k];
       while (wd) {
         const uint32_t b = __ffs(wd) - 1;
         wd &= wd - 1u;
-        const uint32_t e = e0 + 32u * k + b;
-        if (e >= nbits) break;                                             // padding bits of the last chunk
-        uint32_t pl = pl0, rem = rem0 + 32u * k + b;
-        while (rem >= plane) { rem -= plane; ++pl; }
-        const uint32_t y = mw ? __umulhi(rem, mw) : rem, x = rem - y * wc;
-        const uint32_t img = mc ? __umulhi(pl, mc) : pl, ch = pl - img * c.c;
+        const uint32_t d = 32u * k + b;
+        if (e0 + d >= nbits) break;                                        // padding bits of the last chunk
+        uint32_t x = x0 + d, y = y0, ch = ch0, img = img0;
+        while (x >= wc) { x -= wc; ++y; }
+        while (y >= hc) { y -= hc; if (++ch == static_cast<uint32_t>(c.c)) { ch = 0; ++img; } }
         atomicOr(pb + (img * pimg + (y + ex) * prow + (x + ex) * cgs + (ch >> 5)), 1u << (ch & 31u));
       }
     }
@@ -437,43 +460,49 @@ __device__ __forceinline__ void dilate_nhwc_block(const b2u_dropblock_call& c, i
   bool nb_ok[BS];
 #pragma unroll
   for (int t = 0; t < BS; ++t) nb_ok[t] = col_ok && px + t - EX >= 0 && px + t - EX < c.w;
-  auto hsmear = [&](int r) -> uint32_t {
+  // running pointers instead of r * roww products: the input pointer walks rows h_begin - EX .. h_end + EX - 1 (rows
+  // outside the image contribute zeros), the output pointer rows h_begin .. h_end - 1
+  const uint32_t* in_row = pcol + (static_cast<long>(h_begin) - EX) * roww;
+  uint32_t* out_row = mcol + static_cast<size_t>(h_begin) * roww;
+  int rin = h_begin - EX;
+  auto hsmear_next = [&]() -> uint32_t {
     uint32_t v = 0u;
-    if (r >= 0 && r < c.h) {                                  // uniform per block
-      const uint32_t* rowp = pcol + static_cast<size_t>(r) * roww;
+    if (rin >= 0 && rin < c.h) {                              // uniform per block
       if (interior) {
         uint32_t q[BS];
 #pragma unroll
-        for (int t = 0; t < BS; ++t) q[t] = __ldg(rowp + (t - EX) * cgs);
+        for (int t = 0; t < BS; ++t) q[t] = __ldg(in_row + (t - EX) * cgs);
 #pragma unroll
         for (int t = 0; t < BS; ++t) v |= q[t];
       } else {
 #pragma unroll
         for (int t = 0; t < BS; ++t)
-          if (nb_ok[t]) v |= __ldg(rowp + (t - EX) * cgs);
+          if (nb_ok[t]) v |= __ldg(in_row + (t - EX) * cgs);
       }
     }
+    in_row += roww;
+    ++rin;
     return v;
   };
   uint32_t ring[BS];
 #pragma unroll
-  for (int t = 0; t < BS - 1; ++t) ring[t] = hsmear(h_begin - EX + t);      // rows h_begin - EX .. h_begin + EX - 1
+  for (int t = 0; t < BS - 1; ++t) ring[t] = hsmear_next();                   // rows h_begin - EX .. h_begin + EX - 1
   unsigned int keep = 0;
   // output row r needs rows r - EX .. r + EX; the loop is unrolled by BS so that the ring slot is a compile-time index
   for (int r0 = h_begin; r0 < h_end; r0 += BS) {
 #pragma unroll
     for (int u = 0; u < BS; ++u) {
-      const int r = r0 + u;
-      if (r < h_end) {
-        ring[(u + BS - 1) % BS] = hsmear(r + EX);
+      if (r0 + u < h_end) {
+        ring[(u + BS - 1) % BS] = hsmear_next();
         uint32_t drop = 0u;
 #pragma unroll
         for (int t = 0; t < BS; ++t) drop |= ring[t];
         if (col_ok) {
           const uint32_t kw = ~drop;
           keep += __popc(kw);
-          mcol[static_cast<size_t>(r) * roww] = kw;
+          *out_row = kw;
         }
+        out_row += roww;
       }
     }
   }
@@ -518,17 +547,46 @@ __global__ void __launch_bounds__(kD2Threads) dropblock_dilate_nhwc_kernel(const
 
 using namespace b2u;
 
-extern "C" int b2u_dropblock_centers(const b2u_dropblock_call* table, int n_calls, uint64_t seed,
-                                     const unsigned long long* offset_base, uint32_t* center_bits, void* stream) {
+static int centers_launch(const b2u_dropblock_call* table, int n_calls, uint64_t seed, const unsigned long long* offset_base,
+                          uint32_t* center_bits, int max_trips, void* stream) {
   B2U_REQUIRE(table && center_bits && n_calls > 0, "bad arguments");
   int sms = 0, mt = 0;
   int rc = b2u_device_info(&sms, &mt);
   if (rc) return rc;
-  // torch's grid.x never exceeds SMs * (maxThreadsPerSM / 256); calls with a smaller grid exit early
-  dim3 grid(sms * (mt / 256), n_calls);
-  B2U_PDL_LAUNCH((dropblock_centers_kernel), grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), table, seed, offset_base, center_bits);
+  // torch's grid.x never exceeds SMs * (maxThreadsPerSM / 256); calls with a smaller grid exit early.  With max_trips > 0
+  // (the largest trip count of the table, from the host copy) grid.z splits the trips into runs of 4: short blocks.
+  static int env_tpb = -1;
+  if (env_tpb < 0) {
+    const char* e = getenv("B2U_CENTERS_TPB");
+    env_tpb = e ? atoi(e) : 12;
+    if (env_tpb < 1 || env_tpb > 64) env_tpb = 12;
+  }
+  // (4 trips per block DOUBLED the kernel's instructions: the per-thread prologue -- call table, thread-only Philox
+  // products, store role -- is ~150 instructions against 60 per trip)
+  const unsigned tpb = max_trips > 0 ? static_cast<unsigned>(env_tpb) : 0u;
+  dim3 grid(sms * (mt / 256), n_calls, tpb ? (static_cast<unsigned>(max_trips) + tpb - 1u) / tpb : 1u);
+  B2U_PDL_LAUNCH((dropblock_centers_kernel), grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), table, seed, offset_base, center_bits, tpb);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
+}
+
+extern "C" int b2u_dropblock_centers(const b2u_dropblock_call* table, int n_calls, uint64_t seed,
+                                     const unsigned long long* offset_base, uint32_t* center_bits, void* stream) {
+  return centers_launch(table, n_calls, seed, offset_base, center_bits, 0, stream);
+}
+
+extern "C" int b2u_dropblock_centers_ex(const b2u_dropblock_call* table, int n_calls, const b2u_dropblock_call* host_table,
+                                        uint64_t seed, const unsigned long long* offset_base, uint32_t* center_bits, void* stream) {
+  B2U_REQUIRE(host_table, "bad arguments");
+  int max_trips = 1;
+  for (int i = 0; i < n_calls; ++i) {
+    const b2u_dropblock_call& c = host_table[i];
+    B2U_REQUIRE(c.grid > 0 && c.numel > 0, "call %d: empty grid", i);
+    const unsigned long long per_trip = static_cast<unsigned long long>(c.grid) * 1024ull;
+    const int t = static_cast<int>((c.numel - 1ull) / per_trip) + 1;
+    if (t > max_trips) max_trips = t;
+  }
+  return centers_launch(table, n_calls, seed, offset_base, center_bits, max_trips, stream);
 }
 
 extern "C" int b2u_dropblock_centers_ichan(const b2u_dropblock_call* table, int n_calls, const b2u_dropblock_call* host_table,
@@ -634,7 +692,7 @@ extern "C" int b2u_dropblock_dilate_v2(const b2u_dropblock_call* table, int n_ca
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   B2U_CHECK_CUDA(cudaMemsetAsync(scatter_bits, 0, static_cast<size_t>(mask_words_total) * 4, st));
   const unsigned max_chunks = (max_words + 3u) / 4u;
-  unsigned bx = (max_chunks + 256u * 4u - 1u) / (256u * 4u);            // ~4 chunks of 128 bits per thread (grid-stride)
+  unsigned bx = (max_chunks + 256u * 16u - 1u) / (256u * 16u);          // ~16 chunks of 128 bits per thread (grid-stride)
   if (bx < 1u) bx = 1u;
   dim3 sgrid(bx, n_calls);
   dropblock_scatter_kernel<<<sgrid, 256, 0, st>>>(table, center_bits, scatter_bits);

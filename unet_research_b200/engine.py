@@ -202,6 +202,7 @@ class MaskPlan:
         # v2 dilation (block size 7): sparse scatter of the centres into an NHWC word bitmap + word-parallel 7x7 OR
         import os
         self.mask_words = mask_words
+        self.short_blocks = os.environ.get("B2U_CENTERS_SHORT", "0") != "0"     # measured: no gain
         self.dilate_v2 = block_size == 7 and os.environ.get("B2U_DILATE", "v2") != "v1"
         self.scatter_bits = torch.empty(mask_words, dtype=torch.int32, device=device) if self.dilate_v2 else None
         self.keep_counts = torch.zeros(self.n_sites * n_calls, dtype=torch.int64, device=device)
@@ -234,8 +235,12 @@ class MaskPlan:
             call("b2u_dropblock_centers_ichan", ptr(self.table), n, self.host_table, C.c_uint64(seed & (2 ** 64 - 1)),
                  ptr(self.offset_base), ptr(self.center_bits), self.center_words, stream_ptr())
         else:
-            call("b2u_dropblock_centers", ptr(self.table), n, C.c_uint64(seed & (2 ** 64 - 1)), ptr(self.offset_base),
-                 ptr(self.center_bits), stream_ptr())
+            if self.short_blocks:
+                call("b2u_dropblock_centers_ex", ptr(self.table), n, self.host_table, C.c_uint64(seed & (2 ** 64 - 1)),
+                     ptr(self.offset_base), ptr(self.center_bits), stream_ptr())
+            else:
+                call("b2u_dropblock_centers", ptr(self.table), n, C.c_uint64(seed & (2 ** 64 - 1)), ptr(self.offset_base),
+                     ptr(self.center_bits), stream_ptr())
         if self.dilate_v2:
             call("b2u_dropblock_dilate_v2", ptr(self.table), n, self.host_table, ptr(self.center_bits), ptr(self.scatter_bits),
                  self.mask_words, ptr(self.mask_bits), ptr(self.keep_counts), stream_ptr())
