@@ -248,6 +248,17 @@ class MaskPlan:
             call("b2u_dropblock_dilate", ptr(self.table), n, self.host_table, ptr(self.center_bits), ptr(self.mask_bits),
                  ptr(self.keep_counts), stream_ptr())
 
+    def generate_partial(self, seed: int, skip: str):
+        """Timing diagnostic (tests/exp notes in DESIGN.md): rebuild only part of the masks; the rest stays stale."""
+        n = self.n_calls * self.n_sites
+        if skip == "dilate":
+            call("b2u_dropblock_centers", ptr(self.table), n, C.c_uint64(seed & (2 ** 64 - 1)), ptr(self.offset_base),
+                 ptr(self.center_bits), stream_ptr())
+        elif skip == "centers":
+            self.keep_counts.zero_()
+            call("b2u_dropblock_dilate_v2", ptr(self.table), n, self.host_table, ptr(self.center_bits), ptr(self.scatter_bits),
+                 self.mask_words, ptr(self.mask_bits), ptr(self.keep_counts), stream_ptr())
+
     def advance(self, n_calls: Optional[int] = None):
         call("b2u_advance_counter", ptr(self.offset_base), (n_calls or self.n_calls) * self.offset_per_call, stream_ptr())
 

@@ -123,7 +123,11 @@ class MCRunner:
 
     def _generate(self, k: int, stride_blocks: int):
         m = self.masks[k]
-        m.generate(self.seed)
+        skip = os.environ.get("B2U_EXP_SKIP_MASKS", "")          # TIMING DIAGNOSTIC ONLY (stale masks): "all" / "centers" / "dilate"
+        if skip and self.graph is None and self.launches_per_step:
+            m.generate_partial(self.seed, skip)
+        else:
+            m.generate(self.seed)
         m.advance(stride_blocks * self.nb)
 
     def _pair(self):
