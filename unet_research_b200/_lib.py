@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libb2u.so")
+LIB_PATH = os.environ.get("B2U_LIB") or os.path.join(_HERE, "csrc", "libb2u.so")     # B2U_LIB: A/B runs of two builds
 
 BF16, F32, F16 = 0, 1, 2
 

@@ -57,7 +57,7 @@ constexpr int kPatchRows = 180;                      // (16 + 2) * (8 + 2)
 constexpr int kPatchBytes = kPatchRows * 128;        // 23040
 constexpr int kPatchStride = 23552;                  // rounded up to the 1024 B swizzle-atom alignment
 constexpr int kV2Threads = 224;
-constexpr int kProWarps = 4;                         // transform warps of the fused-prologue kernels (warps 7 .. 10)
+constexpr int kProWarps = 8;                         // transform warps of the fused-prologue kernels (warps 7 .. 14), two groups
 constexpr int kV2ThreadsPro = kV2Threads + 32 * kProWarps;
 
 // ---- fused prologue: one 16-byte vector (8 channels of one patch pixel) through GroupNorm affine, DropBlock, ReLU.
@@ -103,10 +103,10 @@ __device__ __forceinline__ void v2_epilogue_stats(const float (&x)[32], bool val
 }
 
 template <int BLOCK_N, int MT, int kFmt, bool kPro>
-// kPro kernels launch 352 threads but are compiled for a 512-thread bound = 128 registers per thread (a few bytes of
-// spills): 352 x 168 registers would own 59 k of the SM's 64 k registers and evict the co-resident DropBlock mask-build
-// blocks (8 k registers each) that the Monte-Carlo step overlaps with the forward -- measured: +0.5 ms per step.
-__global__ void __launch_bounds__(kPro ? 512 : kV2Threads, 1)
+// kPro kernels launch 480 threads but are compiled for a 680-thread bound = 96 registers per thread: 46 k registers per
+// CTA.  A CTA that owns 59 k of the SM's 64 k registers (352 x 168) evicts the co-resident DropBlock mask-build blocks
+// (8 k registers each) that the Monte-Carlo step overlaps with the forward -- measured: +0.5 ms per step.
+__global__ void __launch_bounds__(kPro ? 680 : kV2Threads, 1)
 conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvV2Params p) {
   constexpr bool kTf32 = kFmt == 1;
   static_assert(!(kPro && kTf32), "the fused prologue is built for the 16-bit storage formats");
@@ -145,7 +145,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
     if (kPro)
-      for (int s = 0; s < SA; ++s) mbar_init(&a_ready[s], kProWarps);
+      for (int s = 0; s < SA; ++s) mbar_init(&a_ready[s], 4 * MT);     // one arrive per warp that transformed a patch of the stage
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -266,28 +266,23 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // padding applies to the ACTIVATED tensor (reference utils_unet.py:166-182: Conv -> GroupNorm -> DropBlock -> ReLU,
     // the next Conv2d pads its input), so the affine must not touch them.
     if constexpr (kPro) {
-      const int tt = threadIdx.x - kV2Threads;
+      // Two groups of four warps take turns: with MT = 2 group g owns patch t = g of EVERY stage, with MT = 1 the
+      // stages of parity g.  A single warp per scheduler ran this role latency-bound (IPC 0.25, ~3000 cycles per patch
+      // against 1152-2304 of MMA per patch on the two shallow levels); the second warp per scheduler hides it.
+      const int grp = (threadIdx.x - kV2Threads) >> 7;           // 0 / 1
+      const int tt = (threadIdx.x - kV2Threads) & 127;
       const int j = tt & 7;
       const int r0 = tt >> 3;                                    // 0 .. 15
       const int cvs = p.cin >> 3;                                // 16-byte vectors (= mask bytes) per pixel
       const float lo_clamp = p.pro_relu ? 0.f : -3.0e38f;        // storage conversion saturates fp16 on its own
-      // Per-thread constants: the 12 rows this thread owns, as (py, px) inside the 18 x 10 patch and as mask-byte offsets
-      // relative to the patch origin pixel.  Row r0 + 176 exists only for r0 < 4 (180 rows).
-      int rel[12];
-#pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        const int row = r0 + 16 * k;
-        const int py = (row * 205) >> 11, px = row - py * 10;        // row / 10, row % 10 for row < 192
-        rel[k] = (py * p.w + px) * cvs;
-      }
-      const uint32_t rows_mask = r0 < 4 ? 0xFFFu : 0x7FFu;
-      // Patch metadata (8 coefficient pairs, 12 mask bytes, in-image flags) comes straight from global memory (L2 hits)
-      // and is fetched ONE PATCH AHEAD, so its latency overlaps the transform of the current patch.
+      const uint32_t rows_mask = r0 < 4 ? 0xFFFu : 0x7FFu;       // row r0 + 176 exists only for r0 < 4 (180 rows)
+      // Mask bytes and in-image flags of a patch come straight from global memory and are fetched ONE PATCH (of this
+      // group) AHEAD -- they stream from HBM; the 8 coefficient pairs (L2 hits) are fetched when the patch starts.
       struct Meta {
-        float ca[8], cb[8];
-        uint32_t mb[12];                                         // mask bytes, consumed one patch later: never packed or
-        uint32_t inb;                                            // touched before, so the HBM latency stays hidden
-      };                                                         // inb bit k: patch row r0 + 16 k is a real pixel
+        uint32_t mb[12];                                         // consumed one patch later, never touched before
+        uint32_t inb;                                            // bit k: patch row r0 + 16 k is a real pixel
+        int img;
+      };
       auto fetch = [&](int item, int kc, int t, Meta& m) {
         const int mg = item - fd_div(item, p.fd_mgroups) * p.num_mgroups;
         const int tile = mg * MT + t;
@@ -296,19 +291,14 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int r = tile_ok ? tile - img * tiles_per_image : 0;
         const int ty = fd_div(r, p.fd_tw);
         const int h0 = ty * 16 - 1, w0 = (r - ty * p.tiles_w) * 8 - 1;
-        const float4* cf = reinterpret_cast<const float4*>(p.pro_coef + static_cast<size_t>(img) * p.cin + kc * 64 + j * 8);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 c4 = __ldg(cf + i);
-          m.ca[2 * i] = c4.x; m.cb[2 * i] = c4.y; m.ca[2 * i + 1] = c4.z; m.cb[2 * i + 1] = c4.w;
-        }
+        m.img = img;
         // interior patches (92 % at 592x576): every row is a real pixel, no per-row tests
         uint32_t inb = rows_mask;
         if (!(h0 >= 0 && h0 + 17 < p.h && w0 >= 0 && w0 + 9 < p.w)) {       // warp-uniform
 #pragma unroll
           for (int k = 0; k < 12; ++k) {
             const int row = r0 + 16 * k;
-            const int py = (row * 205) >> 11, px = row - py * 10;
+            const int py = (row * 205) >> 11, px = row - py * 10;          // row / 10, row % 10 for row < 192
             const int hh = h0 + py, ww = w0 + px;
             if (!(hh >= 0 && hh < p.h && ww >= 0 && ww < p.w)) inb &= ~(1u << k);
           }
@@ -319,61 +309,69 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint8_t* mbase = p.pro_mask + (static_cast<size_t>(img) * p.h * p.w + static_cast<long>(h0) * p.w + w0) * cvs + kc * 8 + j;
 #pragma unroll
           for (int k = 0; k < 12; ++k) {
+            const int row = r0 + 16 * k;
+            const int py = (row * 205) >> 11, px = row - py * 10;
             m.mb[k] = 0xFFu;
-            if ((inb >> k) & 1u) m.mb[k] = __ldg(mbase + rel[k]);
+            if ((inb >> k) & 1u) m.mb[k] = __ldg(mbase + (py * p.w + px) * cvs);
           }
         } else {
 #pragma unroll
           for (int k = 0; k < 12; ++k) m.mb[k] = 0xFFu;
         }
       };
-      int s = 0;
-      uint32_t ph = 0;
       const uint32_t smA_u32 = smem_u32(smA);
-      Meta cur, nxt;
-      int n_item = blockIdx.x, n_kc = 0, n_t = 0;                // the patch `nxt` describes
-      auto advance = [&]() {
-        if (++n_t == MT) {
-          n_t = 0;
-          if (++n_kc == p.kc_chunks) { n_kc = 0; n_item += gridDim.x; }
+      // this group's patch sequence: (stage counter sc, item, kc, t)
+      const int t_mine = MT == 2 ? grp : 0;
+      const int stage_step = MT == 2 ? 1 : 2;
+      int c_item = blockIdx.x, c_kc = 0, c_sc = 0;               // cursor of the patch `nxt` describes
+      auto advance_stages = [&](int n) {
+        for (int i = 0; i < n; ++i) {
+          ++c_sc;
+          if (++c_kc == p.kc_chunks) { c_kc = 0; c_item += gridDim.x; }
         }
       };
-      fetch(n_item, n_kc, n_t, nxt);
-      advance();
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        for (int kc = 0; kc < p.kc_chunks; ++kc) {
-#pragma unroll 1
-          for (int t = 0; t < MT; ++t) {
-            cur = nxt;
-            fetch(n_item, n_kc, n_t, nxt);                       // next patch's metadata in flight during this transform
-            advance();
-            if (t == 0) mbar_wait(&a_full[s], ph);               // TMA bytes of all MT patches of this stage have landed
-            // row r0 + 16 k: (row & 7) = (r0 & 7) for every k, so the swizzled chunk offset is a per-thread constant
-            const uint32_t patch = smA_u32 + static_cast<uint32_t>((s * MT + t) * kPatchStride + r0 * 128 + ((j ^ (r0 & 7)) << 4));
-            // two halves of six rows: loads first (unconditional: rows outside the image hold TMA's zeros; only row
-            // 176 + r0 may not exist), then the arithmetic, then predicated stores -- no branches, six independent
-            // vectors for the scheduler, 24 live data registers
+      if (MT == 1 && grp == 1) advance_stages(1);
+      Meta cur, nxt;
+      fetch(c_item, c_kc, t_mine, nxt);
+      while (c_item < p.num_items) {
+        cur = nxt;
+        const int kc = c_kc, sc = c_sc;
+        advance_stages(stage_step);
+        fetch(c_item, c_kc, t_mine, nxt);                         // next patch's mask bytes in flight during this transform
+        float ca[8], cb[8];
+        {
+          const float4* cf = reinterpret_cast<const float4*>(p.pro_coef + static_cast<size_t>(cur.img) * p.cin + kc * 64 + j * 8);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              uint4 v[6];
-#pragma unroll
-              for (int i = 0; i < 6; ++i) {
-                const int k = half * 6 + i;
-                v[i] = (k < 11 || r0 < 4) ? lds128(patch + k * 2048) : make_uint4(0u, 0u, 0u, 0u);
-              }
-#pragma unroll
-              for (int i = 0; i < 6; ++i) v[i] = pro_transform<kFmt>(v[i], cur.ca, cur.cb, cur.mb[half * 6 + i], lo_clamp);
-#pragma unroll
-              for (int i = 0; i < 6; ++i)
-                if ((cur.inb >> (half * 6 + i)) & 1u) sts128(patch + (half * 6 + i) * 2048, v[i]);
-            }
+          for (int i = 0; i < 4; ++i) {
+            const float4 c4 = __ldg(cf + i);
+            ca[2 * i] = c4.x; cb[2 * i] = c4.y; ca[2 * i + 1] = c4.z; cb[2 * i + 1] = c4.w;
           }
-          // generic-proxy writes -> visible to the tensor core's async-proxy reads, then one arrive per warp
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_ready[s]);
-          if (++s == SA) { s = 0; ph ^= 1; }
         }
+        const int s = sc % p.sa;
+        const uint32_t ph = static_cast<uint32_t>(sc / p.sa) & 1u;
+        mbar_wait(&a_full[s], ph);                               // TMA bytes of all MT patches of this stage have landed
+        // row r0 + 16 k: (row & 7) = (r0 & 7) for every k, so the swizzled chunk offset is a per-thread constant
+        const uint32_t patch = smA_u32 + static_cast<uint32_t>((s * MT + t_mine) * kPatchStride + r0 * 128 + ((j ^ (r0 & 7)) << 4));
+        // two halves of six rows: loads first (unconditional: rows outside the image hold TMA's zeros; only row
+        // 176 + r0 may not exist), then the arithmetic, then predicated stores
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint4 v[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const int k = half * 6 + i;
+            v[i] = (k < 11 || r0 < 4) ? lds128(patch + k * 2048) : make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+          for (int i = 0; i < 6; ++i) v[i] = pro_transform<kFmt>(v[i], ca, cb, cur.mb[half * 6 + i], lo_clamp);
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+            if ((cur.inb >> (half * 6 + i)) & 1u) sts128(patch + (half * 6 + i) * 2048, v[i]);
+        }
+        // generic-proxy writes -> visible to the tensor core's async-proxy reads, then one arrive per warp
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[s]);
       }
     }
   } else {
