@@ -20,6 +20,8 @@
 #include "b2u_common.cuh"
 #include "conv_host.cuh"
 
+#include <stdlib.h>
+
 namespace b2u {
 
 // Division by a launch-invariant divisor as one IMAD.HI: q = (n * mul) >> 32 with mul = floor(2^32 / d) + 1, exact for
@@ -51,6 +53,7 @@ struct ConvV2Params {
   int x_shared;               // 1: every image reads the activation tensor of image 0 (Monte-Carlo: shared first conv)
   int cin;
   uint32_t fd_mgroups, fd_tpi, fd_tw;   // fd_make(num_mgroups), fd_make(tiles per image), fd_make(tiles_w)
+  int combine_stats;          // MT = 2 and an even number of tiles per image: one statistics reduction per item
 };
 
 constexpr int kPatchRows = 180;                      // (16 + 2) * (8 + 2)
@@ -102,11 +105,64 @@ __device__ __forceinline__ void v2_epilogue_stats(const float (&x)[32], bool val
   if (lane % LPV == 0) scratch[lane / LPV] = v[0];
 }
 
+// MT = 2 items whose two tiles lie in the same image: the per-thread sub-group sums of BOTH tiles are added before the
+// 31-shuffle transposed reduction, which then runs once per item and chunk instead of once per tile and chunk (it is the
+// critical path of the Cout = 64 / 128 layers: ~6200 cycles of epilogue per item next to 2304 of MMA).  The combined
+// sum goes to the statistics row of the first tile, the second tile's row is written as zero: gn_finalize adds all
+// rows of an image, so the row granularity is free.
+template <int NV>
+__device__ __forceinline__ void v2_partial_sums(const float (&x)[32], bool valid, float (&v)[NV], bool accumulate) {
+  constexpr int NSG = NV / 2;
+  constexpr int SGS = 32 / NSG;
+#pragma unroll
+  for (int j = 0; j < NSG; ++j) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < SGS; ++i) {
+      const float t = x[j * SGS + i];
+      s += t;
+      q += t * t;
+    }
+    s = valid ? s : 0.f;
+    q = valid ? q : 0.f;
+    v[2 * j] = accumulate ? v[2 * j] + s : s;
+    v[2 * j + 1] = accumulate ? v[2 * j + 1] + q : q;
+  }
+}
+template <int NV, typename OutT>
+__device__ __forceinline__ void v2_chunk_pair(uint32_t taddr0, uint32_t taddr1, bool valid0, bool valid1, OutT* y0, OutT* y1, int lane,
+                                              float* scratch) {
+  float v[NV];
+  {
+    uint32_t rr[32];
+    tmem_ld_32x32(taddr0, rr);
+    tmem_ld_wait();
+    float x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(rr[i]);
+    v2_partial_sums<NV>(x, valid0, v, false);
+    if (valid0) store_chunk32<OutT>(y0, x);
+  }
+  {
+    uint32_t rr[32];
+    tmem_ld_32x32(taddr1, rr);
+    tmem_ld_wait();
+    float x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(rr[i]);
+    v2_partial_sums<NV>(x, valid1, v, true);
+    if (valid1) store_chunk32<OutT>(y1, x);
+  }
+  warp_transpose_reduce<NV>(v, lane);
+  constexpr int LPV = 32 / NV;
+  if (lane % LPV == 0) scratch[lane / LPV] = v[0];
+}
+
 template <int BLOCK_N, int MT, int kFmt, bool kPro>
 // kPro kernels launch 480 threads but are compiled for a 680-thread bound = 96 registers per thread: 46 k registers per
 // CTA.  A CTA that owns 59 k of the SM's 64 k registers (352 x 168) evicts the co-resident DropBlock mask-build blocks
 // (8 k registers each) that the Monte-Carlo step overlaps with the forward -- measured: +0.5 ms per step.
-__global__ void __launch_bounds__(kPro ? 680 : kV2Threads, 1)
+__global__ void __launch_bounds__(kPro ? 680 : 416, 1)   // register caps: 80 (pro) / 152 (plain), see above
 conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvV2Params p) {
   constexpr bool kTf32 = kFmt == 1;
   static_assert(!(kPro && kTf32), "the fused prologue is built for the 16-bit storage formats");
@@ -388,6 +444,40 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int mg = item % p.num_mgroups;
       mbar_wait(&t_full[buf], pf);
       tc_fence_after();
+      if (MT == 2 && p.combine_stats && p.sgs_log2 >= 0) {
+        // both tiles exist and belong to one image (tiles per image is even: checked by the host)
+        const int tile0 = mg * 2;
+        const int img = tile0 / tiles_per_image;
+        const int ra = tile0 - img * tiles_per_image, rb = ra + 1;
+        const int tya = ra / p.tiles_w, txa = ra - tya * p.tiles_w;
+        const int tyb = rb / p.tiles_w, txb = rb - tyb * p.tiles_w;
+        const int ha = tya * 16 + dh, wa = txa * 8 + dw, hb = tyb * 16 + dh, wb = txb * 8 + dw;
+        const bool va = ha < p.h && wa < p.w, vb = hb < p.h && wb < p.w;
+        OutT* ya = reinterpret_cast<OutT*>(p.y) + ((static_cast<size_t>(img) * p.h + ha) * p.w + wa) * p.cout + n0;
+        OutT* yb = reinterpret_cast<OutT*>(p.y) + ((static_cast<size_t>(img) * p.h + hb) * p.w + wb) * p.cout + n0;
+        const uint32_t tb0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccCols;
+#pragma unroll 1
+        for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+          const uint32_t t0 = tb0 + chunk * 32, t1 = tb0 + BLOCK_N + chunk * 32;
+          switch (p.sgs_log2) {
+            case 1: v2_chunk_pair<32, OutT>(t0, t1, va, vb, ya + chunk * 32, yb + chunk * 32, lane, my_scratch + chunk * 32); break;
+            case 2: v2_chunk_pair<16, OutT>(t0, t1, va, vb, ya + chunk * 32, yb + chunk * 32, lane, my_scratch + chunk * 16); break;
+            case 3: v2_chunk_pair<8, OutT>(t0, t1, va, vb, ya + chunk * 32, yb + chunk * 32, lane, my_scratch + chunk * 8); break;
+            case 4: v2_chunk_pair<4, OutT>(t0, t1, va, vb, ya + chunk * 32, yb + chunk * 32, lane, my_scratch + chunk * 4); break;
+            default: v2_chunk_pair<2, OutT>(t0, t1, va, vb, ya + chunk * 32, yb + chunk * 32, lane, my_scratch + chunk * 2); break;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");           // all four quarter-tile partials are in smem
+        const int nslots = (BLOCK_N * 2) >> p.sgs_log2;
+        if (et < nslots) {
+          const float sum = stat_scratch[et] + stat_scratch[128 + et] + stat_scratch[256 + et] + stat_scratch[384 + et];
+          const int slots_per_row = (p.cout * 2) >> p.sgs_log2;
+          float* prow = p.partials + (static_cast<size_t>(img) * tiles_per_image + ra) * slots_per_row + ((n0 * 2) >> p.sgs_log2) + et;
+          prow[0] = sum;
+          prow[slots_per_row] = 0.f;                              // the second tile's row
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");           // scratch may be overwritten by the next item
+      } else
 #pragma unroll 1
       for (int t = 0; t < MT; ++t) {
         const int tile = mg * MT + t;
@@ -566,6 +656,16 @@ int conv3x3_v2_run(const void* x, const void* wpacked, void* y, float* partials,
   gp.fd_mgroups = fd_make(gp.num_mgroups);
   gp.fd_tpi = fd_make(pl.tiles_w * pl.tiles_h);
   gp.fd_tw = fd_make(pl.tiles_w);
+  {
+    static int env_combine = -1;
+    if (env_combine < 0) {
+      const char* e = getenv("B2U_COMBINE_STATS");
+      env_combine = (e && e[0] == '0') ? 0 : 1;
+    }
+    // even tile count per image: an item's two tiles never straddle images and the pairing is the same for every
+    // image whatever the batch (per-image results stay independent of the batch composition, bit for bit)
+    gp.combine_stats = (env_combine && pl.mt == 2 && (pl.tiles_w * pl.tiles_h) % 2 == 0) ? 1 : 0;
+  }
   if (pro) {
     B2U_REQUIRE(static_cast<double>(gp.num_items) * gp.num_mgroups < 4.0e9 && static_cast<double>(gp.total_tiles + 2) * pl.tiles_w * pl.tiles_h < 4.0e9,
                 "fused prologue: tile count out of range for the fast division");
