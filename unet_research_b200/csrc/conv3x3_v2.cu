@@ -550,6 +550,9 @@ static int v2_make_plan(const b2u_conv_desc* d, V2Plan* pl, bool pro = false) {
   // measured on B200 (tests/gpu_diag.py convbench): BLOCK_N 256 wants the double-buffered accumulator (MT 1),
   // narrower tiles want the shared weight stage (MT 2)
   int mt = bn == 256 ? 1 : 2;
+  // one 64-channel chunk of K and a 128-wide tile (the 64 -> 128 layer): the second pixel tile only lengthens the item
+  // (217 -> 162 us fused, 76 -> 66 us plain at 296x288; tests/exp_conv_plan.py)
+  if (bn == 128 && d->cin * (d->dtype == B2U_F32 ? 2 : 1) <= 64) mt = 1;
   if (d->reserved[3] == 1 || d->reserved[3] == 2) mt = d->reserved[3];
   pl->block_n = bn;
   pl->mt = mt;
