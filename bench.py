@@ -448,7 +448,7 @@ def run_gpu(args):
         if not args.no_rotation:
             # BASELINE configs[3]: rotation ensemble, angles 1..359 sharded over the ranks, same pinned host in/out
             m_eval, _ = build_canonical(dev, dropblock=False, compute=compute)
-            rv = U.RotationEval(m_eval, num_iterations=359, return_num=25, angle_batch=5)
+            rv = U.RotationEval(m_eval, num_iterations=359, return_num=25)
             sec_r = e2e_time(rv, 2)
             e2e["rotation_ensemble"] = {"metric": "rotation-ensemble fwd passes/s at 584x565 (angles 1..359, rotate-in -> eval forward -> rotate-back, per-pixel mean/std)",
                                         "value": 359 / sec_r, "unit": UNIT, "seconds_per_call": sec_r, "angles": 359,
