@@ -80,6 +80,18 @@ def test_convT2x2_bf16(case):
     assert r["nan"] == 0 and r["rel"] < 3e-3 and r["stats_rel"] < 1e-4
 
 
+@pytest.mark.parametrize("dtype", [_lib.BF16, _lib.F16])
+@pytest.mark.parametrize("case", [(1, 16, 16, 128, 64), (2, 37, 36, 1024, 512), (1, 20, 24, 256, 128), (3, 19, 13, 128, 64), (2, 74, 72, 512, 256)])
+def test_convT2x2_tma_store_equals_thread_store(case, dtype):
+    """The TMA-store epilogue (staged 128-byte rows, 5-D pixel-shuffle box clipped at the tensor bounds) writes exactly what
+    the per-thread store path writes -- ragged tiles, several images, every (tap, 64-channel) column group -- and leaves
+    nothing unwritten (the output starts as NaN)."""
+    a = D._conv_case(*case, dtype, conv_t=True, stages=1)      # reserved[1] == 1: per-thread stores
+    b = D._conv_case(*case, dtype, conv_t=True, stages=2)      # reserved[1] == 2: TMA stores
+    assert a["nan"] == 0 and b["nan"] == 0 and b["rel"] < 3e-3 and b["stats_rel"] < 1e-4
+    assert torch.equal(a["y"], b["y"]) and torch.equal(a["parts"], b["parts"])
+
+
 def test_conv_tf32():
     for case, ct in (((1, 16, 16, 64, 64), False), ((2, 24, 40, 128, 256), False), ((1, 16, 16, 128, 64), True)):
         r = D._conv_case(*case, _lib.F32, conv_t=ct)

@@ -165,6 +165,25 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, uint64_
       : "memory");
 }
 
+// ---- TMA stores (shared -> global, bulk async-group completion).  The box is clipped at the tensor bounds, so ragged
+// border tiles need no per-row predicate; the source rows must be visible to the async proxy (fence_proxy_async)
+// before the store is issued, and the staging buffer may be rewritten once `bulk_wait_read<N>` has returned.
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const void* tmap, uint32_t src_smem, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
 // be scheduled while its predecessor in the stream is still running; `pdl_wait()` (griddepcontrol.wait) blocks until the
 // predecessor grid has completed and its memory is visible, so everything a kernel does BEFORE the wait (barrier
@@ -385,6 +404,30 @@ template <> __device__ __forceinline__ void store_chunk32<__half>(__half* dst, c
     d4[i] = v;
   }
 }
+
+// 8 consecutive accumulator columns -> one 16-byte vector of the 16-bit storage type (same rounding as store_chunk32)
+template <typename T> __device__ __forceinline__ uint4 pack8(const float* x);
+template <> __device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const float* x) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(x[0], x[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(x[2], x[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(x[4], x[5]);
+  __nv_bfloat162 d = __floats2bfloat162_rn(x[6], x[7]);
+  uint4 v;
+  v.x = *reinterpret_cast<uint32_t*>(&a);
+  v.y = *reinterpret_cast<uint32_t*>(&b);
+  v.z = *reinterpret_cast<uint32_t*>(&c);
+  v.w = *reinterpret_cast<uint32_t*>(&d);
+  return v;
+}
+template <> __device__ __forceinline__ uint4 pack8<__half>(const float* x) {
+  uint4 v;
+  v.x = pack_half2_sat(x[0], x[1]);
+  v.y = pack_half2_sat(x[2], x[3]);
+  v.z = pack_half2_sat(x[4], x[5]);
+  v.w = pack_half2_sat(x[6], x[7]);
+  return v;
+}
+template <> __device__ __forceinline__ uint4 pack8<float>(const float* x) { return make_uint4(0u, 0u, 0u, 0u); }   // never staged
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -54,8 +54,16 @@ struct ConvV2Params {
   int cin;
   uint32_t fd_mgroups, fd_tpi, fd_tw;   // fd_make(num_mgroups), fd_make(tiles per image), fd_make(tiles_w)
   int combine_stats;          // MT = 2 and an even number of tiles per image: one statistics reduction per item
+  int stage_off;              // byte offset of the four 2 KB staging slots inside the aligned shared memory
 };
 
+// TMA-store epilogue (16-bit formats): tiles up to this BLOCK_N stage their output rows in shared memory and write them
+// with TMA stores; wider tiles (the tensor-bound deep layers) keep the per-thread stores and their deeper weight ring.
+// Compile-time (0 = never, 256 = every 16-bit kernel) so that the unused path costs no registers: A/B runs build two
+// libraries (-DB2U_V2_TMA_MAX_BN=0) and select one with B2U_LIB.
+#ifndef B2U_V2_TMA_MAX_BN
+#define B2U_V2_TMA_MAX_BN 128
+#endif
 constexpr int kPatchRows = 180;                      // (16 + 2) * (8 + 2)
 constexpr int kPatchBytes = kPatchRows * 128;        // 23040
 constexpr int kPatchStride = 23552;                  // rounded up to the 1024 B swizzle-atom alignment
@@ -129,8 +137,31 @@ __device__ __forceinline__ void v2_partial_sums(const float (&x)[32], bool valid
     v[2 * j + 1] = accumulate ? v[2 * j + 1] + q : q;
   }
 }
-template <int NV, typename OutT>
-__device__ __forceinline__ void v2_chunk_pair(uint32_t taddr0, uint32_t taddr1, bool valid0, bool valid1, OutT* y0, OutT* y1, int lane,
+// One 32-column accumulator chunk of this warp's 32 pixels (4 rows x 8 pixels of the tile) -> global memory.
+// Per-thread path: a thread writes its own 64-byte run; a warp-wide STG.128 then touches 32 different 128-byte lines.
+// TMA path (16-bit formats): the warp stages its 32 x 64-byte runs in its 2 KB slot (64-byte swizzle: physical 16-byte
+// chunk = i ^ ((row >> 1) & 3), conflict-free for STS.128) and lane 0 stores the box {32 ch, 8 w, 4 h, 1 n}; the tensor
+// bounds clip ragged tiles and tiles past the end.  Single-buffered: the wait for the previous store's shared-memory
+// read sits behind the TMEM load and the statistics arithmetic of this chunk.
+template <typename OutT>
+__device__ __forceinline__ void v2_store_chunk(const CUtensorMap* tmY, uint32_t slot, int lane, const float (&x)[32], int c0, int w0, int h0,
+                                               int img) {
+  if (lane == 0) bulk_wait_read<0>();
+  __syncwarp();
+  const uint32_t row = slot + static_cast<uint32_t>(lane * 64);
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sts128(row + static_cast<uint32_t>((i ^ sw) << 4), pack8<OutT>(x + 8 * i));
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_4d(tmY, slot, c0, w0, h0, img);
+    bulk_commit();
+  }
+}
+
+template <int NV, typename St0, typename St1>
+__device__ __forceinline__ void v2_chunk_pair(uint32_t taddr0, uint32_t taddr1, bool valid0, bool valid1, St0&& store0, St1&& store1, int lane,
                                               float* scratch) {
   float v[NV];
   {
@@ -141,7 +172,7 @@ __device__ __forceinline__ void v2_chunk_pair(uint32_t taddr0, uint32_t taddr1, 
 #pragma unroll
     for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(rr[i]);
     v2_partial_sums<NV>(x, valid0, v, false);
-    if (valid0) store_chunk32<OutT>(y0, x);
+    store0(x);
   }
   {
     uint32_t rr[32];
@@ -151,7 +182,7 @@ __device__ __forceinline__ void v2_chunk_pair(uint32_t taddr0, uint32_t taddr1, 
 #pragma unroll
     for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(rr[i]);
     v2_partial_sums<NV>(x, valid1, v, true);
-    if (valid1) store_chunk32<OutT>(y1, x);
+    store1(x);
   }
   warp_transpose_reduce<NV>(v, lane);
   constexpr int LPV = 32 / NV;
@@ -163,8 +194,10 @@ template <int BLOCK_N, int MT, int kFmt, bool kPro>
 // CTA.  A CTA that owns 59 k of the SM's 64 k registers (352 x 168) evicts the co-resident DropBlock mask-build blocks
 // (8 k registers each) that the Monte-Carlo step overlaps with the forward -- measured: +0.5 ms per step.
 __global__ void __launch_bounds__(kPro ? 680 : 416, 1)   // register caps: 80 (pro) / 152 (plain), see above
-conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvV2Params p) {
+conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
+                  const ConvV2Params p) {
   constexpr bool kTf32 = kFmt == 1;
+  constexpr bool kTmaSt = !kTf32 && BLOCK_N <= B2U_V2_TMA_MAX_BN;
   static_assert(!(kPro && kTf32), "the fused prologue is built for the 16-bit storage formats");
   using OutT = typename FmtTraits<kFmt>::T;
   constexpr int kBBytes = BLOCK_N * 128;
@@ -197,6 +230,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (kTmaSt) tma_prefetch_desc(&tmY);
     for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
@@ -437,6 +471,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int dh = row >> 3, dw = row & 7;
     float* my_scratch = stat_scratch + q * 128;
     const int et = threadIdx.x - 64;                             // 0..127
+    const uint32_t my_slot = smem_u32(smem + p.stage_off) + static_cast<uint32_t>(q * 2048);
     int buf = 0;
     uint32_t pf = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -459,12 +494,20 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll 1
         for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
           const uint32_t t0 = tb0 + chunk * 32, t1 = tb0 + BLOCK_N + chunk * 32;
+          auto st_a = [&](const float (&x)[32]) {
+            if constexpr (kTmaSt) v2_store_chunk<OutT>(&tmY, my_slot, lane, x, n0 + chunk * 32, txa * 8, tya * 16 + q * 4, img);
+            else if (va) store_chunk32<OutT>(ya + chunk * 32, x);
+          };
+          auto st_b = [&](const float (&x)[32]) {
+            if constexpr (kTmaSt) v2_store_chunk<OutT>(&tmY, my_slot, lane, x, n0 + chunk * 32, txb * 8, tyb * 16 + q * 4, img);
+            else if (vb) store_chunk32<OutT>(yb + chunk * 32, x);
+          };
           switch (p.sgs_log2) {
-            case 1: v2_chunk_pair<32, OutT>(t0, t1, va, vb, ya + chunk * 32, yb + chunk * 32, lane, my_scratch + chunk * 32); break;
-            case 2: v2_chunk_pair<16, OutT>(t0, t1, va, vb, ya + chunk * 32, yb + chunk * 32, lane, my_scratch + chunk * 16); break;
-            case 3: v2_chunk_pair<8, OutT>(t0, t1, va, vb, ya + chunk * 32, yb + chunk * 32, lane, my_scratch + chunk * 8); break;
-            case 4: v2_chunk_pair<4, OutT>(t0, t1, va, vb, ya + chunk * 32, yb + chunk * 32, lane, my_scratch + chunk * 4); break;
-            default: v2_chunk_pair<2, OutT>(t0, t1, va, vb, ya + chunk * 32, yb + chunk * 32, lane, my_scratch + chunk * 2); break;
+            case 1: v2_chunk_pair<32>(t0, t1, va, vb, st_a, st_b, lane, my_scratch + chunk * 32); break;
+            case 2: v2_chunk_pair<16>(t0, t1, va, vb, st_a, st_b, lane, my_scratch + chunk * 16); break;
+            case 3: v2_chunk_pair<8>(t0, t1, va, vb, st_a, st_b, lane, my_scratch + chunk * 8); break;
+            case 4: v2_chunk_pair<4>(t0, t1, va, vb, st_a, st_b, lane, my_scratch + chunk * 4); break;
+            default: v2_chunk_pair<2>(t0, t1, va, vb, st_a, st_b, lane, my_scratch + chunk * 2); break;
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");           // all four quarter-tile partials are in smem
@@ -505,7 +548,9 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               default: v2_epilogue_stats<2>(x, valid, lane, my_scratch + chunk * 2); break;
             }
           }
-          if (valid) {
+          if constexpr (kTmaSt) {
+            v2_store_chunk<OutT>(&tmY, my_slot, lane, x, n0 + chunk * 32, tx * 8, ty * 16 + q * 4, img);   // a tile past the end has img == n: clipped
+          } else if (valid) {
             store_chunk32<OutT>(yrow + chunk * 32, x);
           }
         }
@@ -526,6 +571,7 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (++buf == kNumBuf) { buf = 0; pf ^= 1; }
     }
   }
+  if (kTmaSt && warp >= 2 && warp <= 5 && lane == 0) bulk_wait<0>();   // staging slots read, stores complete, before the CTA exits
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -535,9 +581,11 @@ conv3x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // ----------------------------------------------------------------------------- host side
 struct V2Plan {
-  int block_n, mt, sa, sb, tiles_w, tiles_h, sgs, resident_b;
+  int block_n, mt, sa, sb, tiles_w, tiles_h, sgs, resident_b, tma_store, stage_off;
   size_t smem;
 };
+
+constexpr int kV2StoreSlots = 4 * 2048;             // one 2 KB staging slot per epilogue warp
 
 static int v2_make_plan(const b2u_conv_desc* d, V2Plan* pl, bool pro = false) {
   pl->tiles_w = (d->w + 7) / 8;
@@ -556,8 +604,9 @@ static int v2_make_plan(const b2u_conv_desc* d, V2Plan* pl, bool pro = false) {
   if (d->reserved[3] == 1 || d->reserved[3] == 2) mt = d->reserved[3];
   pl->block_n = bn;
   pl->mt = mt;
+  pl->tma_store = (d->dtype != B2U_F32 && bn <= B2U_V2_TMA_MAX_BN) ? 1 : 0;      // the kernels' kTmaSt
   // pipeline depths: fill ~200 KB; the weight ring gets at least 3 stages, the patch ring at least 2
-  const size_t budget = 222 * 1024 - 4096;
+  const size_t budget = 222 * 1024 - 4096 - (pl->tma_store ? kV2StoreSlots : 0);
   int sa = 2, sb = 3;
   auto bytes = [&](int a, int b) { return static_cast<size_t>(a) * mt * kPatchStride + static_cast<size_t>(b) * bn * 128; };
   if (pro) {
@@ -587,14 +636,20 @@ static int v2_make_plan(const b2u_conv_desc* d, V2Plan* pl, bool pro = false) {
   pl->sa = sa;
   pl->sb = sb;
   pl->smem = bytes(sa, sb) + 1024 + (2 * sa + 2 * sb + 4) * 8 + 16 + 4 * 128 * 4 + sa * 8;
+  pl->stage_off = 0;
+  if (pl->tma_store) {
+    pl->stage_off = static_cast<int>((pl->smem - 1024 + 1023) & ~static_cast<size_t>(1023));   // offset from the ALIGNED base
+    pl->smem = static_cast<size_t>(pl->stage_off) + kV2StoreSlots + 1024;
+  }
   pl->sgs = conv_stat_subgroup(d->cout, d->num_groups);
   return B2U_OK;
 }
 
 template <int BN, int MT, int TF, bool PRO>
-static int v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvV2Params& gp, int grid, size_t smem, cudaStream_t st) {
+static int v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const ConvV2Params& gp, int grid, size_t smem,
+                     cudaStream_t st) {
   B2U_SET_MAX_SMEM_ONCE((conv3x3_v2_kernel<BN, MT, TF, PRO>), 227 * 1024);
-  B2U_PDL_LAUNCH((conv3x3_v2_kernel<BN, MT, TF, PRO>), grid, PRO ? kV2ThreadsPro : kV2Threads, smem, st, ta, tb, gp);
+  B2U_PDL_LAUNCH((conv3x3_v2_kernel<BN, MT, TF, PRO>), grid, PRO ? kV2ThreadsPro : kV2Threads, smem, st, ta, tb, ty, gp);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -638,6 +693,17 @@ int conv3x3_v2_run(const void* x, const void* wpacked, void* y, float* partials,
     rc = conv_encode_map(&tb, d->dtype, 3, wpacked, dims, strides, box);
     if (rc) return rc;
   }
+  CUtensorMap ty = ta;
+  if (pl.tma_store) {
+    // output [n][h][w][cout]: an epilogue warp stores 32 channels of 4 rows x 8 pixels (64-byte runs, 64-byte swizzle)
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->cout), static_cast<cuuint64_t>(d->w), static_cast<cuuint64_t>(d->h),
+                          static_cast<cuuint64_t>(d->n)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(d->cout) * es, static_cast<cuuint64_t>(d->w) * d->cout * es,
+                             static_cast<cuuint64_t>(d->h) * d->w * d->cout * es};
+    cuuint32_t box[4] = {32, 8, 4, 1};
+    rc = conv_encode_map(&ty, d->dtype, 4, y, dims, strides, box, 64);
+    if (rc) return rc;
+  }
   ConvV2Params gp;
   gp.n = d->n; gp.h = d->h; gp.w = d->w;
   gp.tiles_w = pl.tiles_w; gp.tiles_h = pl.tiles_h;
@@ -651,6 +717,7 @@ int conv3x3_v2_run(const void* x, const void* wpacked, void* y, float* partials,
   gp.resident_b = pl.resident_b;
   gp.y = y;
   gp.partials = partials;
+  gp.stage_off = pl.stage_off;
   gp.pro_coef = pro ? reinterpret_cast<const float2*>(pro->coef) : nullptr;
   gp.pro_mask = pro ? reinterpret_cast<const uint8_t*>(pro->mask) : nullptr;
   gp.pro_relu = pro ? pro->relu : 0;
@@ -683,12 +750,12 @@ int conv3x3_v2_run(const void* x, const void* wpacked, void* y, float* partials,
 #define B2U_V2_CASE(BN, MTV)                                                                        \
   if (pl.block_n == BN && pl.mt == MTV) {                                                            \
     if (pro) {                                                                                       \
-      if (d->dtype == B2U_F16) return v2_launch<BN, MTV, 2, true>(ta, tb, gp, grid, pl.smem, st);    \
-      return v2_launch<BN, MTV, 0, true>(ta, tb, gp, grid, pl.smem, st);                             \
+      if (d->dtype == B2U_F16) return v2_launch<BN, MTV, 2, true>(ta, tb, ty, gp, grid, pl.smem, st);    \
+      return v2_launch<BN, MTV, 0, true>(ta, tb, ty, gp, grid, pl.smem, st);                             \
     }                                                                                                \
-    if (d->dtype == B2U_F32) return v2_launch<BN, MTV, 1, false>(ta, tb, gp, grid, pl.smem, st);     \
-    if (d->dtype == B2U_F16) return v2_launch<BN, MTV, 2, false>(ta, tb, gp, grid, pl.smem, st);     \
-    return v2_launch<BN, MTV, 0, false>(ta, tb, gp, grid, pl.smem, st);                              \
+    if (d->dtype == B2U_F32) return v2_launch<BN, MTV, 1, false>(ta, tb, ty, gp, grid, pl.smem, st);     \
+    if (d->dtype == B2U_F16) return v2_launch<BN, MTV, 2, false>(ta, tb, ty, gp, grid, pl.smem, st);     \
+    return v2_launch<BN, MTV, 0, false>(ta, tb, ty, gp, grid, pl.smem, st);                              \
   }
   B2U_V2_CASE(64, 1) B2U_V2_CASE(64, 2) B2U_V2_CASE(128, 1) B2U_V2_CASE(128, 2) B2U_V2_CASE(256, 1) B2U_V2_CASE(256, 2)
 #undef B2U_V2_CASE

@@ -15,8 +15,18 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue: two
 // warps per TMEM lane quarter, each draining four of the eight 32-column chunks of an accumulator.
+//
+// TMA-STORE EPILOGUE (kTmaStore, 16-bit formats).  A thread owns one input pixel, i.e. one 128-byte run of the
+// pixel-shuffled output per (tap, 64 channels), and neighbouring threads own runs 256 bytes apart: a warp-wide
+// STG.128 touched 32 different lines with 16 bytes each (the two shallow levels ran at 0.39-0.43 of their HBM-write
+// floor, profiles/r01e_step_metrics.md).  Now every epilogue warp stages its 32 pixels x 64 channels (4 KB, 128-byte
+// swizzle: conflict-free STS.128) in its own double-buffered slot and one lane issues a 5-D TMA store whose box
+// {64 ch, 8 w, 1 dy, 4 h, 1 n} over the output viewed as [n][h][dy][w][dx * cout + c] is the pixel shuffle; the
+// tensor bounds clip ragged tiles.  Only __syncwarp() is needed: no warp ever touches another warp's slot.
 #include "b2u_common.cuh"
 #include "conv_host.cuh"
+
+#include <stdlib.h>
 
 namespace b2u {
 
@@ -30,6 +40,7 @@ struct ConvTParams {
   int stages;
   int sgs_log2;               // statistics sub-group size (log2), -1 = none
   void* y;                    // [n, 2h, 2w, cout]
+  int stage_off;              // byte offset of the TMA-store staging slots inside the aligned shared memory (kTmaStore)
   float* partials;            // [n][tiles_per_image * 4][cout / sgs][2]
 };
 
@@ -60,10 +71,12 @@ __device__ __forceinline__ void convT_epilogue_stats(const float (&x)[32], bool 
   if (lane % LPV == 0) scratch[lane / LPV] = v[0];
 }
 
-template <int kFmt>
+template <int kFmt, bool kTmaStore>
 __global__ void __launch_bounds__(kTThreads, 1)
-convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvTParams p) {
+convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
+                const ConvTParams p) {
   constexpr bool kTf32 = kFmt == 1;
+  static_assert(!(kTmaStore && kTf32), "the TMA-store epilogue stages 16-bit rows");
   using OutT = typename FmtTraits<kFmt>::T;
   constexpr int kKElems = kTf32 ? 32 : 64;
   constexpr int kUmmaK = kTf32 ? 8 : 16;
@@ -88,6 +101,7 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (kTmaStore) tma_prefetch_desc(&tmY);
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
     fence_barrier_init();
@@ -170,6 +184,8 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int et = threadIdx.x - 64 - grp * 128;                 // 0..127 within the group
     const int out_w = 2 * p.w;
     const int buf = grp;
+    // this warp's two 4 KB staging slots (1024-byte aligned: the 128-byte swizzle is a function of the address)
+    const uint32_t my_stage = smem_u32(smem + p.stage_off) + static_cast<uint32_t>((warp - 2) * 8192 + lane * 128);
     uint32_t pf = 0;
     int li = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++li) {
@@ -197,7 +213,30 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             default: convT_epilogue_stats<2>(x, valid, lane, my_scratch + chunk * 2); break;
           }
         }
-        if (valid) {
+        if constexpr (kTmaStore) {
+          // chunks (2k, 2k+1) are the two 64-byte halves of one 128-byte row (64 channels of one tap): slot k & 1
+          const int pair = chunk >> 1, half = chunk & 1;
+          const uint32_t slot = my_stage + static_cast<uint32_t>((pair & 1) * 4096);
+          if (half == 0) {
+            // the store issued two pairs ago read this slot: at most the previous pair's store may still be in flight
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            sts128(slot + static_cast<uint32_t>((((half << 2) | i) ^ (lane & 7)) << 4), pack8<OutT>(x + 8 * i));
+          if (half == 1) {
+            fence_proxy_async();                                   // generic-proxy writes -> visible to the TMA engine
+            __syncwarp();
+            if (lane == 0) {
+              const int gcol = nt * kTBlockN + pair * 64;          // column of the [pixels] x [4*Cout] product
+              const int tap = gcol / p.cout;
+              const int co0 = gcol - tap * p.cout;
+              tma_store_5d(&tmY, slot, (tap & 1) * p.cout + co0, tx * 8, tap >> 1, ty * 16 + q * 4, img);
+              bulk_commit();
+            }
+          }
+        } else if (valid) {
           const int gcol = nt * kTBlockN + chunk * 32;             // column of the [pixels] x [4*Cout] product
           const int tap = gcol / p.cout;
           const int co0 = gcol - tap * p.cout;
@@ -240,6 +279,7 @@ convT_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   }
+  if (kTmaStore && warp >= 2 && lane == 0) bulk_wait<0>();       // staging slots are read (and the stores complete) before the CTA exits
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -263,12 +303,27 @@ int convT_v2_stat_layout(const b2u_conv_desc* d, int* rows_per_image, int* subgr
   return B2U_OK;
 }
 
-template <int TF>
-static int convT_v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvTParams& gp, int grid, size_t smem, cudaStream_t st) {
-  B2U_SET_MAX_SMEM_ONCE((convT_v2_kernel<TF>), 227 * 1024);
-  B2U_PDL_LAUNCH((convT_v2_kernel<TF>), grid, kTThreads, smem, st, ta, tb, gp);
+template <int TF, bool TS>
+static int convT_v2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty, const ConvTParams& gp, int grid, size_t smem,
+                           cudaStream_t st) {
+  B2U_SET_MAX_SMEM_ONCE((convT_v2_kernel<TF, TS>), 227 * 1024);
+  B2U_PDL_LAUNCH((convT_v2_kernel<TF, TS>), grid, kTThreads, smem, st, ta, tb, ty, gp);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
+}
+
+// TMA-store epilogue: 16-bit outputs (a 64-channel run is one 128-byte swizzle row).  B2U_CONVT_TMA_STORE=0 / reserved[1] == 1
+// select the per-thread store path (A/B runs); the fp32-storage (tf32) kernels always use it.
+static bool convT_use_tma_store(const b2u_conv_desc* d) {
+  if (d->dtype == B2U_F32 || d->cout % 64 != 0) return false;
+  if (d->reserved[1] == 1) return false;
+  if (d->reserved[1] == 2) return true;
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("B2U_CONVT_TMA_STORE");
+    env = (e && e[0] == '0') ? 0 : 1;
+  }
+  return env != 0;
 }
 
 int convT_v2_run(const void* x, const void* wpacked, void* y, float* partials, const b2u_conv_desc* d, void* stream) {
@@ -296,6 +351,19 @@ int convT_v2_run(const void* x, const void* wpacked, void* y, float* partials, c
     rc = conv_encode_map(&tb, d->dtype, 2, wpacked, dims, strides, box);
     if (rc) return rc;
   }
+  const bool tma_store = convT_use_tma_store(d);
+  CUtensorMap ty = ta;
+  if (tma_store) {
+    // output [n][2h][2w][cout] viewed as [n][h][dy][w][dx * cout + c]: the box {64, 8, 1, 4, 1} at (dx * cout + co0, w0, dy, h0, n)
+    // is the pixel-shuffled destination of 4 x 8 input pixels for one tap; w and h are clipped at the tensor bounds
+    cuuint64_t dims[5] = {static_cast<cuuint64_t>(2) * d->cout, static_cast<cuuint64_t>(d->w), 2, static_cast<cuuint64_t>(d->h),
+                          static_cast<cuuint64_t>(d->n)};
+    const cuuint64_t row = static_cast<cuuint64_t>(2) * d->w * d->cout * es;          // one output row
+    cuuint64_t strides[4] = {static_cast<cuuint64_t>(2) * d->cout * es, row, 2 * row, 2 * row * d->h};
+    cuuint32_t box[5] = {64, 8, 1, 4, 1};
+    rc = conv_encode_map(&ty, d->dtype, 5, y, dims, strides, box);
+    if (rc) return rc;
+  }
   ConvTParams gp;
   gp.n = d->n; gp.h = d->h; gp.w = d->w;
   gp.tiles_w = (d->w + 7) / 8; gp.tiles_h = (d->h + 15) / 16;
@@ -303,18 +371,24 @@ int convT_v2_run(const void* x, const void* wpacked, void* y, float* partials, c
   gp.num_items = gp.total_tiles * (4 * d->cout / kTBlockN);
   gp.kc_chunks = d->cin / ke;
   gp.cout = d->cout;
-  gp.stages = 4;
+  // the staging slots (8 warps x 2 x 4 KB) take the place of the fourth pipeline stage
+  gp.stages = tma_store ? 3 : 4;
   const int sgs = conv_stat_subgroup(d->cout, d->num_groups);
   gp.sgs_log2 = sgs > 0 ? conv_ilog2(sgs) : -1;
   gp.y = y;
   gp.partials = partials;
-  const size_t smem = static_cast<size_t>(gp.stages) * (kTABytes + kTBBytes) + 1024 + (2 * gp.stages + 4) * 8 + 16 + 2 * 4 * 256 * 4;
+  size_t smem = static_cast<size_t>(gp.stages) * (kTABytes + kTBBytes) + 1024 + (2 * gp.stages + 4) * 8 + 16 + 2 * 4 * 256 * 4;
+  gp.stage_off = 0;
+  if (tma_store) {
+    gp.stage_off = static_cast<int>((smem - 1024 + 1023) & ~static_cast<size_t>(1023));   // offset from the ALIGNED base
+    smem = static_cast<size_t>(gp.stage_off) + 8 * 8192 + 1024;
+  }
   int grid = b2u_num_sms();
   if (grid > gp.num_items) grid = gp.num_items;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (d->dtype == B2U_F32) return convT_v2_launch<1>(ta, tb, gp, grid, smem, st);
-  if (d->dtype == B2U_F16) return convT_v2_launch<2>(ta, tb, gp, grid, smem, st);
-  return convT_v2_launch<0>(ta, tb, gp, grid, smem, st);
+  if (d->dtype == B2U_F32) return convT_v2_launch<1, false>(ta, tb, ty, gp, grid, smem, st);
+  if (d->dtype == B2U_F16) return tma_store ? convT_v2_launch<2, true>(ta, tb, ty, gp, grid, smem, st) : convT_v2_launch<2, false>(ta, tb, ty, gp, grid, smem, st);
+  return tma_store ? convT_v2_launch<0, true>(ta, tb, ty, gp, grid, smem, st) : convT_v2_launch<0, false>(ta, tb, ty, gp, grid, smem, st);
 }
 
 }  // namespace b2u

@@ -253,7 +253,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int conv_encode_map(CUtensorMap* map, int dtype, int rank, const void* base, const cuuint64_t* dims,
-                    const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+                    const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     b2u_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -262,7 +262,8 @@ int conv_encode_map(CUtensorMap* map, int dtype, int rank, const void* base, con
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, dtype == B2U_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (dtype == B2U_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), rank,
                   const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     b2u_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", static_cast<int>(r), rank);
     return B2U_ERR_CUDA;

@@ -5,7 +5,7 @@
 namespace b2u {
 
 int conv_encode_map(CUtensorMap* map, int dtype, int rank, const void* base, const cuuint64_t* dims,
-                    const cuuint64_t* strides_bytes, const cuuint32_t* box);
+                    const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle_bytes = 128);
 int conv_validate_desc(const b2u_conv_desc* d);
 int conv_stat_subgroup(int cout, int num_groups);
 int conv_ilog2(int v);

@@ -233,6 +233,7 @@ class DropBlockEval(_MCBase):
         self.use_cuda_graph = use_cuda_graph
         self.overlap_masks = overlap_masks
         self._runners = {}
+        self._prologue_stream = None
 
     def set_mode(self, mode):
         self.mode = mode
@@ -276,20 +277,38 @@ class DropBlockEval(_MCBase):
         acc = None
         samples = None
         per_iter = 0
+        # A rank's share is a run of full batches plus, possibly, remainder batches (125 = 12 x 10 + 5 at 8 GPUs), each with
+        # its own runner.  Every runner's prologue (input copy, accumulator reset, mask build of ITS first step) is
+        # enqueued before the first runner's steps: the first one on the caller's stream, the later ones on a low-priority
+        # side stream, so that their mask builds overlap the first runner's forwards instead of standing alone between
+        # two runners (1.4 ms per call at 8 GPUs).
+        segments = []
         done = t0
         while done < t1:
             nb = min(self.iter_batch, t1 - done)
             steps = (t1 - done) // nb
-            r = self._runner(nb, h0, w0, dev, active, p, bs)
+            segments.append((self._runner(nb, h0, w0, dev, active, p, bs), steps, done))
+            done += steps * nb
+        cur = torch.cuda.current_stream(dev)
+        for i, (r, steps, start) in enumerate(segments):
+            if i == 0:
+                r.begin(im, mask, start, seed, stream_start)
+            else:
+                if self._prologue_stream is None or self._prologue_stream.device != dev:
+                    self._prologue_stream = torch.cuda.Stream(device=dev, priority=0)
+                self._prologue_stream.wait_stream(cur)
+                with torch.cuda.stream(self._prologue_stream):
+                    r.begin(im, mask, start, seed, stream_start)
+        for i, (r, steps, start) in enumerate(segments):
             per_iter = r.per_iter
-            r.begin(im, mask, done, seed, stream_start)
+            if i > 0:
+                cur.wait_stream(self._prologue_stream)
             r.run_steps(steps)
             if acc is None:
                 acc, samples = r.acc, r.samples
             else:                                      # remainder batch: fold into the first runner's buffers
                 acc += r.acc
                 samples += r.samples
-            done += steps * nb
         if acc is None:                                # this rank owns no iterations
             acc = torch.zeros(2, h0, w0, dtype=torch.float64, device=dev)
             samples = torch.zeros(max(R, 1), h0, w0, dtype=torch.float32, device=dev)
