@@ -1026,8 +1026,13 @@ def sec_gradprec(h=584, w=565, dropblock=True):
     pac = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     torch.manual_seed(4321)
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        lac = O.train_step_loss(pac, x, gt, fov, cfg)
-    lac.float().backward()
+        seg = O.unet_forward(pac, x, 4, 32, cfg)
+    # F.binary_cross_entropy refuses to run under autocast: the loss tail of train_step_loss in fp32, as autocast would
+    # run it (utils_training.py:28-33)
+    seg = seg.float() * fov
+    lac = torch.nn.functional.binary_cross_entropy(seg, gt * fov)
+    lac = lac * (seg.numel() / fov.count_nonzero())
+    lac.backward()
     gac = {k: v.grad.double() for k, v in pac.items()}
     rows = []
     for k in ours:

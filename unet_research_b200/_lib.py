@@ -25,6 +25,11 @@ class ConvDesc(C.Structure):
                 ("reserved", C.c_int32 * 4)]
 
 
+class PackEntry(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("out0", C.c_void_p), ("out1", C.c_void_p), ("kind", C.c_int32), ("cout", C.c_int32),
+                ("cin", C.c_int32), ("first_block", C.c_int32)]
+
+
 class ApplyDesc(C.Structure):
     _fields_ = [("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("dtype", C.c_int32),
                 ("relu", C.c_int32), ("out_cstride", C.c_int32), ("out_coffset", C.c_int32),
@@ -71,6 +76,8 @@ SIGNATURES = {
     "b2u_device_info": (_I, [C.POINTER(_I), C.POINTER(_I)]),
     "b2u_pack_conv3x3_weight": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b2u_pack_conv3x3_weight_pair": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "b2u_pack_batched_plan": (_I, [_P, _I, _P]),
+    "b2u_pack_batched": (_I, [_P, _I, _I, _I, _P]),
     "b2u_pack_convT2x2_weight": (_I, [_P, _P, _I, _I, _I, _P]),
     "b2u_conv3x3_stat_layout": (_I, [C.POINTER(ConvDesc), C.POINTER(_I), C.POINTER(_I)]),
     "b2u_convT2x2_stat_layout": (_I, [C.POINTER(ConvDesc), C.POINTER(_I), C.POINTER(_I)]),
@@ -124,7 +131,7 @@ _LAUNCHERS = {"b2u_conv3x3_fwd": 1, "b2u_conv3x3_pro_fwd": 1, "b2u_convT2x2_fwd"
               "b2u_gn_apply": 1, "b2u_gn_apply_pool": 1, "b2u_head_fwd": 1, "b2u_mc_finalize": 1,
               "b2u_mc_accumulate": 1, "b2u_advance_counter": 1, "b2u_dropblock_centers": 1, "b2u_dropblock_centers_ex": 1,
               "b2u_dropblock_dilate": 1, "b2u_dropblock_dilate_v2": 2, "b2u_dropblock_centers_ichan": 1, "b2u_dropblock_centers_from_uniform": 1, "b2u_rotate_bilinear": 1, "b2u_masked_bce_fwd": 2, "b2u_masked_bce_bwd": 1, "b2u_rotate_in_table": 1, "b2u_rotate_back_accumulate": 1,
-              "b2u_pack_conv3x3_weight": 1, "b2u_pack_conv3x3_weight_pair": 1, "b2u_pack_convT2x2_weight": 1, "b2u_unit_bwd_stats": 1, "b2u_unit_bwd_finalize": 2,
+              "b2u_pack_conv3x3_weight": 1, "b2u_pack_conv3x3_weight_pair": 1, "b2u_pack_batched": 1, "b2u_pack_convT2x2_weight": 1, "b2u_unit_bwd_stats": 1, "b2u_unit_bwd_finalize": 2,
               "b2u_unit_bwd_apply": 1, "b2u_wgrad": 2, "b2u_wgrad_first": 2, "b2u_gemm1x1_fwd": 1,
               "b2u_pack_convT2x2_dgrad_weight": 1, "b2u_sgd_step": 2, "b2u_confusion_counts": 1, "b2u_square_pad_resize": 1}
 
@@ -147,10 +154,17 @@ def load() -> C.CDLL:
     return lib
 
 
+# TIMING DIAGNOSTIC ONLY (upper-bound experiments on captured steps, tests/exp_train_skip.py): entry points named in
+# B2U_EXP_SKIP_CALLS are not launched -- their outputs are stale, results are garbage, only the step time means anything.
+_SKIP = frozenset(t for t in os.environ.get("B2U_EXP_SKIP_CALLS", "").split(",") if t)
+
+
 def call(name: str, *args) -> None:
     """Invoke an int-returning entry point; raise B2uError with the library's message on failure."""
     global launch_count
     lib = load()
+    if _SKIP and name in _SKIP:
+        return
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise B2uError(f"{name} failed (code {rc}): {lib.b2u_last_error().decode(errors='replace')}")

@@ -58,11 +58,12 @@ struct ConvV2Params {
 };
 
 // TMA-store epilogue (16-bit formats): tiles up to this BLOCK_N stage their output rows in shared memory and write them
-// with TMA stores; wider tiles (the tensor-bound deep layers) keep the per-thread stores and their deeper weight ring.
-// Compile-time (0 = never, 256 = every 16-bit kernel) so that the unused path costs no registers: A/B runs build two
-// libraries (-DB2U_V2_TMA_MAX_BN=0) and select one with B2U_LIB.
+// with TMA stores (256 = every 16-bit kernel, 0 = never).  Compile-time so that the unused path costs no registers: A/B
+// runs build two libraries (python tests/build_variant.py stg -DB2U_V2_TMA_MAX_BN=0) and select one with B2U_LIB.
+// Measured stand-alone at batch 10, fp16 (profiles/r02d_exp_tma_store.log): 64->64 281 -> 241 us, 128->128 200 -> 175,
+// 128->256 111 -> 96, 256->256 184 -> 170, 512->512 176 -> 169, 1024->1024 243 -> 220.
 #ifndef B2U_V2_TMA_MAX_BN
-#define B2U_V2_TMA_MAX_BN 128
+#define B2U_V2_TMA_MAX_BN 256
 #endif
 constexpr int kPatchRows = 180;                      // (16 + 2) * (8 + 2)
 constexpr int kPatchBytes = kPatchRows * 128;        // 23040

@@ -469,6 +469,58 @@ __global__ void pack_convT_kernel(const float* __restrict__ w, T* __restrict__ o
   }
 }
 
+// Batched repack (b2u_pack_batched): block -> (tensor, 32 x 32 tile) through the table's first_block prefix; the tile
+// bodies are the per-tensor kernels' (same rounding, same outputs).
+template <typename T>
+__global__ void __launch_bounds__(256) pack_batched_kernel(const b2u_pack_entry* __restrict__ table, int n) {
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
+  __shared__ T tile[9][32][33];
+  __shared__ int s_entry;
+  if (threadIdx.x == 0) {
+    int e = 0;
+    while (e + 1 < n && static_cast<int>(blockIdx.x) >= table[e + 1].first_block) ++e;
+    s_entry = e;
+  }
+  __syncthreads();
+  const b2u_pack_entry en = table[s_entry];
+  const int b = blockIdx.x - en.first_block;
+  const int cin = en.cin, cout = en.cout;
+  const int tiles_ci = cin >> 5;
+  const int ci0 = (b % tiles_ci) * 32, co0 = (b / tiles_ci) * 32;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const float* __restrict__ w = en.w;
+  if (en.kind == 0) {
+    T* __restrict__ fwd = static_cast<T*>(en.out0);
+    T* __restrict__ dgrad = static_cast<T*>(en.out1);
+    for (int f = threadIdx.x; f < 32 * 288; f += 256) {
+      const int co_l = f / 288, rem = f - co_l * 288;
+      const int ci_l = rem / 9, tap = rem - ci_l * 9;
+      tile[tap][co_l][ci_l] = to_operand<T>(w[(static_cast<long>(co0 + co_l) * cin + ci0) * 9 + rem]);
+    }
+    __syncthreads();
+    for (int r = wrp; r < 9 * 32; r += 8) {
+      const int tap = r >> 5, row = r & 31;
+      fwd[(static_cast<long>(tap) * cout + co0 + row) * cin + ci0 + lane] = tile[tap][row][lane];
+      if (dgrad) dgrad[(static_cast<long>(8 - tap) * cin + ci0 + row) * cout + co0 + lane] = tile[tap][lane][row];
+    }
+  } else {
+    // w[ci][co][tap]: a ci row of the tile is 128 contiguous floats
+    T* __restrict__ fwd = static_cast<T*>(en.out0);            // [tap][co][ci]
+    T* __restrict__ dgrad = static_cast<T*>(en.out1);          // [ci][tap * cout + co]
+    for (int f = threadIdx.x; f < 32 * 128; f += 256) {
+      const int ci_l = f >> 7, rem = f & 127;
+      tile[rem & 3][ci_l][rem >> 2] = to_operand<T>(w[(static_cast<long>(ci0 + ci_l) * cout + co0) * 4 + rem]);
+    }
+    __syncthreads();
+    for (int r = wrp; r < 4 * 32; r += 8) {
+      const int tap = r >> 5, row = r & 31;
+      fwd[(static_cast<long>(tap) * cout + co0 + row) * cin + ci0 + lane] = tile[tap][lane][row];
+      if (dgrad) dgrad[static_cast<long>(ci0 + row) * (4 * cout) + tap * cout + co0 + lane] = tile[tap][row][lane];
+    }
+  }
+}
+
 }  // namespace b2u
 
 using namespace b2u;
@@ -542,6 +594,30 @@ extern "C" int b2u_pack_conv3x3_weight_pair(const float* w, void* packed_fwd, vo
     B2U_PDL_LAUNCH((pack_conv3x3_pair_kernel<__half>), grid, 256, 0, st, w, static_cast<__half*>(packed_fwd), static_cast<__half*>(packed_dgrad), cout, cin);
   else
     B2U_PDL_LAUNCH((pack_conv3x3_pair_kernel<__nv_bfloat16>), grid, 256, 0, st, w, static_cast<__nv_bfloat16*>(packed_fwd), static_cast<__nv_bfloat16*>(packed_dgrad), cout, cin);
+  B2U_LAUNCH_CHECK();
+  return B2U_OK;
+}
+extern "C" int b2u_pack_batched_plan(b2u_pack_entry* entries, int n, int* total_blocks) {
+  B2U_REQUIRE(entries && total_blocks && n > 0, "bad arguments");
+  int blocks = 0;
+  for (int i = 0; i < n; ++i) {
+    b2u_pack_entry& e = entries[i];
+    B2U_REQUIRE(e.kind == 0 || e.kind == 1, "entry %d: kind must be 0 (Conv2d 3x3) or 1 (ConvTranspose2d 2x2)", i);
+    B2U_REQUIRE(e.w && e.out0, "entry %d: null pointer", i);
+    B2U_REQUIRE(e.cout > 0 && e.cin > 0 && e.cout % 32 == 0 && e.cin % 32 == 0, "entry %d: cout and cin must be multiples of 32 (got %d, %d)", i,
+                e.cout, e.cin);
+    e.first_block = blocks;
+    blocks += (e.cin / 32) * (e.cout / 32);
+  }
+  *total_blocks = blocks;
+  return B2U_OK;
+}
+extern "C" int b2u_pack_batched(const b2u_pack_entry* entries_dev, int n, int total_blocks, int dtype, void* stream) {
+  B2U_REQUIRE(entries_dev && n > 0 && total_blocks > 0, "bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == B2U_F32) B2U_PDL_LAUNCH((pack_batched_kernel<float>), total_blocks, 256, 0, st, entries_dev, n);
+  else if (dtype == B2U_F16) B2U_PDL_LAUNCH((pack_batched_kernel<__half>), total_blocks, 256, 0, st, entries_dev, n);
+  else B2U_PDL_LAUNCH((pack_batched_kernel<__nv_bfloat16>), total_blocks, 256, 0, st, entries_dev, n);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }

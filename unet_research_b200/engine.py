@@ -17,6 +17,7 @@ bit-packed NHWC (uint32 [N,H,W,C/32]).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -200,7 +201,6 @@ class MaskPlan:
         self.center_bits = torch.zeros(center_words + 4, dtype=torch.int32, device=device)
         self.mask_bits = torch.empty(mask_words, dtype=torch.int32, device=device)
         # v2 dilation (block size 7): sparse scatter of the centres into an NHWC word bitmap + word-parallel 7x7 OR
-        import os
         self.mask_words = mask_words
         self.short_blocks = os.environ.get("B2U_CENTERS_SHORT", "0") != "0"     # measured: no gain
         self.dilate_v2 = block_size == 7 and os.environ.get("B2U_DILATE", "v2") != "v1"
@@ -370,14 +370,20 @@ class UNetEngine:
         self._aliased = set()
         self._workspaces: Dict[Tuple[int, int, int], Workspace] = {}
         self.training_weights = False          # set by enable_training(): also keep the dgrad-packed weights
+        self.batched_pack = os.environ.get("B2U_BATCHED_PACK", "1") != "0"
+        self._pack_table = None                # (pointer signature, device table, blocks) of the batched weight pack
         # Fused conv prologue (16-bit inference schedules): the GroupNorm affine + DropBlock mask + ReLU of a unit is applied
         # by the CONSUMING 3x3 conv on the TMA-landed patch in shared memory (b2u_conv3x3_pro_fwd) instead of a stand-alone
         # gn_apply pass that writes and re-reads the activated tensor.  Training keeps the unfused schedule: the weight
         # gradients read the activated tensors.  `fuse_levels`: encoder/decoder resolutions (0 = full size) that fuse.
-        import os
+        # Default: every level but the full-resolution one.  With the TMA-store epilogue the plain 64 -> 64 conv at
+        # 592x576 runs in 241 us (+ 139 us of gn_apply) against 545 us fused -- the eight transform warps and the MMA
+        # compete for the same shared-memory bandwidth when Cout = 64 -- and the Monte-Carlo step is 7.20 ms with levels
+        # 1..4 fused against 7.54 with all five (profiles/r02d_exp_fuse_levels.log); levels 1..4 fuse at equal time and
+        # 2.6 GB less DRAM traffic per step.
         self.fused_prologue = dtype != _lib.F32 and os.environ.get("B2U_FUSED", "1") != "0"
         lv = os.environ.get("B2U_FUSE_LEVELS")
-        self.fuse_levels = set(int(t) for t in lv.split(",") if t != "") if lv is not None else set(range(depth + 1))
+        self.fuse_levels = set(int(t) for t in lv.split(",") if t != "") if lv is not None else set(range(1, depth + 1))
         self._sd_ref = state_dict
         self.load_weights(state_dict)
 
@@ -407,8 +413,14 @@ class UNetEngine:
                 slot(key, shape, torch.float32).copy_(v32.view(shape))
 
         self._sd_ref = sd
+        # Tensor-core weights whose fp32 source already lives on the device (the training case: the parameters themselves)
+        # are packed by ONE batched launch through a device-resident table of stable pointers; anything else (CPU state
+        # dicts, other dtypes: a temporary fp32 copy per call) goes through the per-tensor entry points.
+        batch = []                                  # (w ptr, out0, out1, kind, cout, cin)
+        keep = []
         for k, v in sd.items():
             v32 = v.detach().to(device=dev, dtype=torch.float32).contiguous()
+            aliased = v32.data_ptr() == v.data_ptr()
             if v32.dim() == 4 and k == "down_blocks.0.0.0.weight":
                 plain(k, v, v32, tuple(v32.shape))                         # direct first-layer kernel reads fp32
             elif v32.dim() == 4 and k.startswith("output_conv"):
@@ -419,14 +431,38 @@ class UNetEngine:
                 cout, cin = v32.shape[0], v32.shape[1]
                 # forward operand [9][Cout][Cin] and (training) the data-gradient operand [9][Cin][Cout], taps rotated 180
                 dg = slot(k + "#dgrad", (9, cin, cout), dt) if self.training_weights else None
-                call("b2u_pack_conv3x3_weight_pair", ptr(v32), ptr(slot(k, (9, cout, cin), dt)), ptr(dg), cout, cin, self.dtype, st)
+                fw = slot(k, (9, cout, cin), dt)
+                if aliased and self.batched_pack:
+                    batch.append((v32.data_ptr(), fw.data_ptr(), dg.data_ptr() if dg is not None else 0, 0, cout, cin))
+                else:
+                    call("b2u_pack_conv3x3_weight_pair", ptr(v32), ptr(fw), ptr(dg), cout, cin, self.dtype, st)
             elif v32.dim() == 4 and v32.shape[2] == 2:
                 cin, cout = v32.shape[0], v32.shape[1]
-                call("b2u_pack_convT2x2_weight", ptr(v32), ptr(slot(k, (4, cout, cin), dt)), cin, cout, self.dtype, st)
-                if self.training_weights:
-                    call("b2u_pack_convT2x2_dgrad_weight", ptr(v32), ptr(slot(k + "#dgrad", (1, cin, 4 * cout), dt)), cin, cout, self.dtype, st)
+                fw = slot(k, (4, cout, cin), dt)
+                dg = slot(k + "#dgrad", (1, cin, 4 * cout), dt) if self.training_weights else None
+                if aliased and self.batched_pack:
+                    batch.append((v32.data_ptr(), fw.data_ptr(), dg.data_ptr() if dg is not None else 0, 1, cout, cin))
+                else:
+                    call("b2u_pack_convT2x2_weight", ptr(v32), ptr(fw), cin, cout, self.dtype, st)
+                    if dg is not None:
+                        call("b2u_pack_convT2x2_dgrad_weight", ptr(v32), ptr(dg), cin, cout, self.dtype, st)
             else:
                 plain(k, v, v32, tuple(v32.shape))
+            keep.append(v32)
+        if batch:
+            sig = tuple(batch)
+            if self._pack_table is None or self._pack_table[0] != sig:
+                if torch.cuda.is_current_stream_capturing():
+                    raise _lib.B2uError("weight pointers changed inside a CUDA-graph capture: the batched pack table cannot be rebuilt here")
+                ents = (_lib.PackEntry * len(batch))()
+                for e, (wp, o0, o1, kind, cout, cin) in zip(ents, batch):
+                    e.w, e.out0, e.out1, e.kind, e.cout, e.cin, e.first_block = wp, o0, o1 or None, kind, cout, cin, 0
+                blocks = C.c_int(0)
+                call("b2u_pack_batched_plan", C.byref(ents), len(batch), C.byref(blocks))
+                host = torch.frombuffer(bytearray(bytes(ents)), dtype=torch.uint8)
+                self._pack_table = (sig, host.to(dev), blocks.value)
+            _, table, blocks = self._pack_table
+            call("b2u_pack_batched", ptr(table), len(batch), blocks, self.dtype, st)
         if sync:
             torch.cuda.current_stream().synchronize()  # v32 temporaries die here
 
