@@ -347,7 +347,7 @@ def run_gpu(args):
     # ---- roofline of the dominant kernel family: per-launch CUDA-event timing, eager mode
     conv_ms, other = time_conv_kernels(runner, dev, reps=max(3, min(K, 10)))
     conv_tflops = CONV_FLOP_PER_FORWARD * NB / (conv_ms / 1000.0) / 1e12
-    eb = elementwise_bytes_per_step(NB, fused=runner.eng.fused_prologue if hasattr(runner.eng, "fused_prologue") else False)
+    eb = elementwise_bytes_per_step(NB, fused=(sorted(runner.eng.fuse_levels) if getattr(runner.eng, "fused_prologue", False) else False))
     hbm = {}
     for name, nbytes in eb.items():
         key = next((k for k in (name, name + "_ex", name + "_v2") if k in other), name)
@@ -477,7 +477,9 @@ def run_gpu(args):
     if rank == 0:
         cfg = workload_config(world, NB)
         cfg.update({"iter_batch": NB, "cuda_graph": True, "mask_build": "side stream, overlapped with the forward of the previous step",
-                    "fused_prologue": bool(getattr(runner.eng, "fused_prologue", False))})
+                    "fused_prologue": bool(getattr(runner.eng, "fused_prologue", False)),
+                    "fused_levels": sorted(getattr(runner.eng, "fuse_levels", [])) if getattr(runner.eng, "fused_prologue", False) else [],
+                    "epilogue": "TMA stores (conv3x3: 32-channel runs per warp; convT: 5-D pixel-shuffle box)"})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype_name,
@@ -603,22 +605,28 @@ def conv_bytes_per_step(nb, filters=64, depth=4, h=592, w=576):
 
 
 def elementwise_bytes_per_step(nb, filters=64, depth=4, h=592, w=576, h0=H0, w0=W0, fused=False):
+    fuse_levels = set(range(depth + 1)) if fused is True else (set() if not fused else set(fused))
+    return _elementwise_bytes(nb, filters, depth, h, w, h0, w0, fuse_levels)
+
+
+def _elementwise_bytes(nb, filters, depth, h, w, h0, w0, fuse_levels):
     """ALGORITHMIC HBM bytes of one Monte-Carlo step (nb batched iterations, 16-bit activations) per fused kernel
     family, from the tensor shapes alone: every activation read once / written once, bit masks
-    1 bit per element, statistics and coefficients ignored.  fused=True: the schedule in which the conv3x3 prologue
-    applies GroupNorm + DropBlock + ReLU (the stand-alone applies in front of 3x3 convs are gone)."""
+    1 bit per element, statistics and coefficients ignored.  fuse_levels: the resolutions (0 = full size) whose conv3x3
+    prologue applies GroupNorm + DropBlock + ReLU (the stand-alone applies in front of those 3x3 convs are gone)."""
     out = {"b2u_gn_apply": 0.0, "b2u_gn_apply_pool": 0.0, "b2u_head_fwd": 0.0, "b2u_conv_first_fwd": 0.0,
            "b2u_dropblock_dilate": 0.0}
     c = filters
     bits = 0.0
     for lvl in range(depth + 1):
         e = float(h >> lvl) * (w >> lvl) * c                     # elements of one conv output at this level
+        fused = lvl in fuse_levels
         if lvl < depth:
             # encoder: unit 1 apply (first level reads the SHARED raw tensor once), unit 2 apply+pool, pooled-GN apply
             if not fused:
                 out["b2u_gn_apply"] += (2.0 * e * (1 if lvl == 0 else nb) + 2.0 * e * nb + e * nb / 8.0)
             out["b2u_gn_apply_pool"] += nb * (2.0 * e + 2.0 * e + 0.5 * e + e / 8.0 + e / 8.0)
-            if not fused:
+            if (lvl + 1) not in fuse_levels:                     # the pooled tensor's apply belongs to the NEXT level's first conv
                 out["b2u_gn_apply"] += nb * (2.0 * e / 4 + 2.0 * e / 4)
             # decoder at the same resolution: up-conv apply (with concat mask), unit 1 apply, unit 2 apply (not the last level)
             out["b2u_gn_apply"] += nb * (4.0 * e + e / 8.0)

@@ -603,6 +603,28 @@ static int v2_make_plan(const b2u_conv_desc* d, V2Plan* pl, bool pro = false) {
   // (217 -> 162 us fused, 76 -> 66 us plain at 296x288; tests/exp_conv_plan.py)
   if (bn == 128 && d->cin * (d->dtype == B2U_F32 ? 2 : 1) <= 64) mt = 1;
   if (d->reserved[3] == 1 || d->reserved[3] == 2) mt = d->reserved[3];
+  // UNDER-FILLED GRIDS (batch-1 training / single-image inference at the deep levels: 15 pixel tiles at 37x36 make 30-60
+  // items for 148 SMs, and every CTA walks its whole K loop alone: 50 us for a layer whose tensor time is 18 us).  When
+  // the default tile leaves SMs idle, pick the narrower BLOCK_N with the lowest waves x columns-per-item x inefficiency
+  // (narrow tiles re-read the activation patch per N tile: 1.1 / 1.5 for 128 / 64 against 256 at MT 1, 1.35 for 64 against
+  // 128 at MT 2).  MT is NOT changed: the statistics epilogue pairs the two tiles of an MT = 2 item before its fp32
+  // reduction, so a batch-dependent MT would make an image's result depend on the batch it is computed in (outputs and
+  // per-chunk statistics do not depend on BLOCK_N: same K order per output element, 32-column reduction chunks).
+  if (d->reserved[0] == 0 && d->reserved[3] == 0) {
+    const int sms = b2u_num_sms();
+    const long tiles = static_cast<long>(d->n) * pl->tiles_w * pl->tiles_h;
+    auto items = [&](int b) { return ((tiles + mt - 1) / mt) * (d->cout / b); };
+    if (items(bn) < sms) {
+      auto ineff = [&](int b) { return mt == 1 ? (b == 256 ? 1.0 : (b == 128 ? 1.1 : 1.5)) : (b == 64 ? 1.35 : 1.0); };
+      auto cost = [&](int b) { return static_cast<double>((items(b) + sms - 1) / sms) * b * ineff(b); };
+      double best = cost(bn);
+      for (int b = bn / 2; b >= 64; b /= 2) {
+        if (d->cout % b != 0) continue;
+        const double c = cost(b);
+        if (c < 0.85 * best) { best = c; bn = b; }
+      }
+    }
+  }
   pl->block_n = bn;
   pl->mt = mt;
   pl->tma_store = (d->dtype != B2U_F32 && bn <= B2U_V2_TMA_MAX_BN) ? 1 : 0;      // the kernels' kTmaSt

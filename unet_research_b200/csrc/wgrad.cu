@@ -9,6 +9,13 @@
 // A CTA owns a 128 x 64 (cg x cx) block for up to 8 taps (8 x 64 = 512 TMEM columns; the accumulators live for the
 // whole CTA, there is no per-tile epilogue) and a slice of the pixel tiles (split-K); partial sums are written as
 // fp32 and reduced in a fixed order by wgrad_reduce_kernel, which also permutes into the PyTorch weight layout.
+//
+// TAP PAIRS.  The B operand of an MN-major descriptor is a sequence of 64-element MN blocks LBO bytes apart.  Two taps
+// of the same patch are two shifted views of it, a constant number of patch rows apart -- so ONE N = 128 MMA whose
+// second MN block starts `distance` bytes after the first computes two taps at once: pairs (0,1), (3,4), (6,7)
+// (one patch row = 128 B apart) and (2,5) (one patch line = 10 rows = 1280 B apart).  Half the MMAs, and the A operand
+// (the gradient tile, 4 KB per K step) is read from shared memory once per pair instead of once per tap: an N = 64 MMA
+// needs 192 B of operands per tensor cycle against the 128 B/cycle the SM delivers.
 #include "b2u_common.cuh"
 #include "conv_host.cuh"
 
@@ -42,11 +49,17 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   return d;
 }
 
+#ifndef B2U_WGRAD_PAIR_TAPS
+#define B2U_WGRAD_PAIR_TAPS 1
+#endif
+constexpr bool kPairTaps = B2U_WGRAD_PAIR_TAPS != 0;
+
 template <int TAPS>   // 9: 3x3 (tap groups of 8 + 1 over blockIdx.z), 1: plain
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
   // bf16 A/B both MN-major (bits 15, 16), fp32 accumulate, M = 128, N = 64
   constexpr uint32_t kIdesc = umma_idesc(128, 64, 1) | (1u << 15) | (1u << 16);
+  constexpr uint32_t kIdescPair = umma_idesc(128, 128, 1) | (1u << 15) | (1u << 16);
   constexpr int kXBytes = TAPS == 9 ? 180 * 128 : 128 * 128;
   constexpr int kXStride = TAPS == 9 ? kXPatchStride : 128 * 128;
   constexpr int kStageBytes = kGBytes + kXStride;
@@ -121,6 +134,21 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
         tc_fence_after();
         const uint32_t g_addr = smem_u32(smem + s * kStageBytes);
         const uint32_t x_addr = g_addr + kGBytes;
+        if (TAPS == 9 && blockIdx.z == 0 && kPairTaps) {
+#pragma unroll
+          for (int pr = 0; pr < 4; ++pr) {
+            // pair pr = taps (a, b): TMEM columns [pr * 128, +64) = tap a, [pr * 128 + 64, +64) = tap b
+            const int ta = pr < 3 ? 3 * pr : 2;
+            const int dist = pr < 3 ? 128 : 1280;                  // bytes between the two views
+            const int row_off = (ta / 3) * 10 + (ta % 3);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t adesc = umma_desc_mn_sw128(g_addr + ks * 2048, 128 * 128, 1024);
+              const uint64_t bdesc = umma_desc_mn_sw128(x_addr + (row_off + ks * 20) * 128, dist, 1280);
+              umma_ss_conv<false>(tmem_u + pr * 128, adesc, bdesc, kIdescPair, (first && ks == 0) ? 0u : 1u, leader);
+            }
+          }
+        } else
         for (int t = 0; t < tap_count; ++t) {
           const int tap = tap_begin + t;
           const int row_off = TAPS == 9 ? (tap / 3) * 10 + (tap % 3) : 0;
@@ -147,7 +175,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
     tc_fence_after();
     const bool valid = (m0 + row) < p.cg && t_begin < t_end;
     for (int t = 0; t < tap_count; ++t) {
-      const int tap = tap_begin + t;
+      // paired layout: TMEM column block t holds tap [0, 1, 3, 4, 6, 7, 2, 5][t]
+      const int tap = (TAPS == 9 && blockIdx.z == 0 && kPairTaps) ? (t < 6 ? 3 * (t >> 1) + (t & 1) : (t == 6 ? 2 : 5)) : tap_begin + t;
       float* dst = p.ws + ((static_cast<size_t>(slice) * p.taps + tap) * p.cg + (m0 + row)) * p.cx + c0;
 #pragma unroll 1
       for (int chunk = 0; chunk < 2; ++chunk) {
@@ -461,6 +490,7 @@ extern "C" int b2u_pack_convT2x2_dgrad_weight(const float* w, void* packed, int 
   const long total = 4L * cout * cin;
   const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   if (dtype == B2U_F32) B2U_PDL_LAUNCH((pack_convT_dgrad_kernel<float>), blocks, 256, 0, st, w, static_cast<float*>(packed), cin, cout);
+  else if (dtype == B2U_F16) B2U_PDL_LAUNCH((pack_convT_dgrad_kernel<__half>), blocks, 256, 0, st, w, static_cast<__half*>(packed), cin, cout);
   else B2U_PDL_LAUNCH((pack_convT_dgrad_kernel<__nv_bfloat16>), blocks, 256, 0, st, w, static_cast<__nv_bfloat16*>(packed), cin, cout);
   B2U_LAUNCH_CHECK();
   return B2U_OK;
