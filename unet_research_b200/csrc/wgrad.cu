@@ -228,15 +228,18 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
 
 // layout 0 with 9 taps: one thread per (cg, cx) pair sums the slices of all nine taps (reads coalesced along cx)
 // and writes its nine taps as one 36-byte run, so a warp writes 1152 contiguous bytes of the PyTorch layout.
-__global__ void __launch_bounds__(256) wgrad_reduce9_kernel(const float* __restrict__ ws, float* __restrict__ dw, int slices, int cg, int cx) {
+__global__ void __launch_bounds__(1024) wgrad_reduce9_kernel(const float* __restrict__ ws, float* __restrict__ dw, int slices, int cg, int cx) {
   pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
   pdl_trigger();    // the successor may be scheduled once every CTA got here
-  // blockDim = (32 pairs, SG slice groups): slice group y sums slices y, y + SG, ...; the groups are then added in a
-  // fixed order through shared memory (deterministic), and thread (x, 0) writes the nine taps.
-  __shared__ float part[8][32][9];
+  // blockDim = (PX pairs, SG slice groups), PX * SG = 256 .. 1024 threads: slice group y sums slices y, y + SG, ...; the
+  // groups are then added in a fixed order through (dynamic) shared memory (deterministic), and thread (x, 0) writes the
+  // nine taps.  Many slices / few pairs (full-resolution layers: 148 slices of 4096 pairs) -> up to 32 groups; few slices
+  // / many pairs (deep layers) -> 128 .. 256 pairs per block instead of one-warp blocks.
+  extern __shared__ float part_raw[];       // [nsg][PX][9]
+  const int px = blockDim.x;
   const long pairs = static_cast<long>(cg) * cx;
   const long total = 9 * pairs;
-  const long i = blockIdx.x * 32L + threadIdx.x;
+  const long i = static_cast<long>(blockIdx.x) * px + threadIdx.x;
   const int sg = threadIdx.y, nsg = blockDim.y;
   float acc[9];
 #pragma unroll
@@ -249,13 +252,16 @@ __global__ void __launch_bounds__(256) wgrad_reduce9_kernel(const float* __restr
     }
   }
   if (nsg > 1) {
+    float* mine = part_raw + (static_cast<size_t>(sg) * px + threadIdx.x) * 9;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) part[sg][threadIdx.x][t] = acc[t];
+    for (int t = 0; t < 9; ++t) mine[t] = acc[t];
     __syncthreads();
     if (sg == 0) {
-      for (int y = 1; y < nsg; ++y)
+      for (int y = 1; y < nsg; ++y) {
+        const float* other = part_raw + (static_cast<size_t>(y) * px + threadIdx.x) * 9;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) acc[t] += part[y][threadIdx.x][t];
+        for (int t = 0; t < 9; ++t) acc[t] += other[t];
+      }
     }
   }
   if (sg == 0 && i < pairs) {
@@ -449,8 +455,14 @@ extern "C" int b2u_wgrad(const void* g, const void* x, float* workspace, float* 
   }
   if (d->taps == 9 && d->layout == 0) {
     const long pairs = static_cast<long>(d->cg) * d->cx;
-    const int nsg = pl.slices >= 8 ? 8 : (pl.slices >= 4 ? 4 : (pl.slices >= 2 ? 2 : 1));
-    B2U_PDL_LAUNCH((wgrad_reduce9_kernel), static_cast<unsigned>((pairs + 31) / 32), dim3(32, nsg), 0, st, workspace, dw, pl.slices, d->cg, d->cx);
+    // slice groups per block: enough threads in flight for the layers with many slices and few (cg, cx) pairs (64 x 64
+    // at 148 slices: 128 blocks; with 8 groups every thread walked 19 slices x 9 taps serially, 26 us for 22 MB)
+    int nsg = 1;
+    while (nsg < 32 && nsg * 2 <= pl.slices && (nsg < 8 || pairs * nsg < 148L * 1024 * 2)) nsg *= 2;
+    int px = 32;
+    while (px * nsg < 256 && px < 256) px *= 2;               // at least 8 warps per block
+    const size_t smem = nsg > 1 ? static_cast<size_t>(nsg) * px * 9 * sizeof(float) : 0;
+    B2U_PDL_LAUNCH((wgrad_reduce9_kernel), static_cast<unsigned>((pairs + px - 1) / px), dim3(px, nsg), smem, st, workspace, dw, pl.slices, d->cg, d->cx);
   } else {
     int blocks = static_cast<int>((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
     B2U_PDL_LAUNCH((wgrad_reduce_kernel), blocks, 256, 0, st, workspace, dw, pl.slices, d->taps, d->cg, d->cx, d->layout, pl.slices);
