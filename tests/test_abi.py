@@ -201,3 +201,20 @@ def test_io_formats_roundtrip(tmp_path):
     m2.create_model()
     bio.load_checkpoint_into(m2, p)
     assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+
+
+def test_pack_batched_plan_without_gpu():
+    """b2u_pack_batched_plan is host-only: flat grid prefix (one 32 x 32 tile per block) and argument validation."""
+    ents = (_lib.PackEntry * 3)()
+    for e, (kind, cout, cin) in zip(ents, [(0, 128, 64), (1, 64, 128), (0, 1024, 512)]):
+        e.w, e.out0, e.out1, e.kind, e.cout, e.cin = 0x1000, 0x2000, None, kind, cout, cin
+    blocks = C.c_int(0)
+    _lib.call("b2u_pack_batched_plan", C.byref(ents), 3, C.byref(blocks))
+    assert [e.first_block for e in ents] == [0, 8, 16] and blocks.value == 16 + 32 * 16
+    assert C.sizeof(_lib.PackEntry) == 3 * 8 + 4 * 4
+    ents[1].cin = 100
+    with pytest.raises(_lib.B2uError, match="multiples of 32"):
+        _lib.call("b2u_pack_batched_plan", C.byref(ents), 3, C.byref(blocks))
+    ents[1].cin, ents[1].kind = 128, 7
+    with pytest.raises(_lib.B2uError, match="kind"):
+        _lib.call("b2u_pack_batched_plan", C.byref(ents), 3, C.byref(blocks))
