@@ -201,6 +201,129 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
   }
 }
 
+// Cg = 64 (the three weight gradients of the full-resolution level, the most expensive ones at batch 1): with the
+// gradient tile as the M = 128 operand half of every MMA multiplies zero rows, and the ninth tap needs its own CTA group.
+// Here the roles are SWAPPED: A = two taps of the activation patch stacked along M (two 64-channel MN blocks LBO = the
+// distance between the two shifted views apart), B = the 64 gradient channels (N = 64).  Five MMAs per K step cover the
+// nine taps -- pairs (0,1), (3,4), (6,7), (2,5) and (7,8), the last one recomputing tap 7 in rows it then ignores --
+// in 5 x 64 = 320 TMEM columns: one CTA owns all nine taps, M is full, the gradient tile is a single 16 KB box.
+// D[row = (tap of the pair, cx), column = cg]; the epilogue writes ws[slice][tap][cg][cx] with lanes along cx (coalesced).
+constexpr int kSwapStageBytes = 128 * 128 + kXPatchStride;       // one gradient box + one halo patch
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_swap64_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+  constexpr uint32_t kIdesc = umma_idesc(128, 64, 1) | (1u << 15) | (1u << 16);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stages = p.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * kSwapStageBytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* done_bar = empty_bar + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x;
+  const int c0 = blockIdx.y * 64;
+  const int t_begin = slice * p.tiles_per_slice;
+  const int t_end = min(t_begin + p.tiles_per_slice, p.total_tiles);
+  const int tiles_per_image = p.tiles_w * p.tiles_h;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmG);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        const int img = tile / tiles_per_image;
+        const int r = tile - img * tiles_per_image;
+        const int ty = r / p.tiles_w, tx = r - ty * p.tiles_w;
+        mbar_wait(&empty_bar[s], ph);
+        mbar_arrive_expect_tx(&full_bar[s], 128 * 128 + 180 * 128);
+        uint8_t* st = smem + s * kSwapStageBytes;
+        tma_load_4d(st, &tmG, &full_bar[s], 0, tx * 8, ty * 16, img);
+        tma_load_4d(st + 128 * 128, &tmX, &full_bar[s], c0, tx * 8 - 1, ty * 16 - 1, img);
+        if (++s == stages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t tmem_u = warp_uniform(tmem_base);
+    int s = 0;
+    uint32_t ph = 0;
+    bool first = true;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t g_addr = smem_u32(smem + s * kSwapStageBytes);
+      const uint32_t x_addr = g_addr + 128 * 128;
+#pragma unroll
+      for (int pr = 0; pr < 5; ++pr) {
+        const int ta = pr < 3 ? 3 * pr : (pr == 3 ? 2 : 7);       // first tap of the pair
+        const int dist = pr == 3 ? 1280 : 128;                     // bytes between the two views (second tap: ta + 1, or ta + 3)
+        const int row_off = (ta / 3) * 10 + (ta % 3);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t adesc = umma_desc_mn_sw128(x_addr + (row_off + ks * 20) * 128, dist, 1280);
+          const uint64_t bdesc = umma_desc_mn_sw128(g_addr + ks * 2048, 128 * 128, 1024);
+          umma_ss_conv<false>(tmem_u + pr * 64, adesc, bdesc, kIdesc, (first && ks == 0) ? 0u : 1u, leader);
+        }
+      }
+      first = false;
+      umma_commit_conv(&empty_bar[s], leader);
+      if (++s == stages) { s = 0; ph ^= 1; }
+    }
+    umma_commit_conv(done_bar, leader);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int half = row >> 6, cxl = row & 63;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    if (t_begin < t_end) {
+#pragma unroll 1
+      for (int pr = 0; pr < 5; ++pr) {
+        const int ta = pr < 3 ? 3 * pr : (pr == 3 ? 2 : 7);
+        const int tap = half ? (pr == 3 ? 5 : ta + 1) : ta;
+        const bool write = !(pr == 4 && half == 0);               // tap 7 was already written by pair 2
+        float* dst = p.ws + ((static_cast<size_t>(slice) * 9 + tap) * 64) * p.cx + c0 + cxl;
+#pragma unroll 1
+        for (int chunk = 0; chunk < 2; ++chunk) {
+          uint32_t rr[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + pr * 64 + chunk * 32, rr);
+          tmem_ld_wait();
+          if (write) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dst[static_cast<size_t>(chunk * 32 + i) * p.cx] = __uint_as_float(rr[i]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // dw = sum over slices of ws, permuted to the PyTorch layout.
 // layout 0: Conv2d [cg][cx][3][3] (taps 9) ; layout 1: ConvTranspose2d [cx][cout][2][2] with cg = 4*cout, tap-major (taps 1)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int slices, int taps, int cg, int cx,
@@ -362,9 +485,20 @@ __global__ void pack_convT_dgrad_kernel(const float* __restrict__ w, T* __restri
 }
 
 struct WgPlan {
-  int tiles_w, tiles_h, total_tiles, slices, tiles_per_slice, mblks, xchunks, groups, stages;
+  int tiles_w, tiles_h, total_tiles, slices, tiles_per_slice, mblks, xchunks, groups, stages, swap64;
   size_t smem;
 };
+
+// Cg = 64, 3x3: the operand-swapped kernel (B2U_WGRAD_SWAP64=0 selects the generic one for A/B runs)
+static bool wg_use_swap64(const b2u_wgrad_desc* d) {
+  if (d->taps != 9 || d->cg != 64 || d->layout != 0) return false;
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("B2U_WGRAD_SWAP64");
+    env = (e && e[0] == '0') ? 0 : 1;
+  }
+  return env != 0;
+}
 
 static int wg_plan(const b2u_wgrad_desc* d, WgPlan* pl) {
   B2U_REQUIRE(d, "null descriptor");
@@ -390,7 +524,13 @@ static int wg_plan(const b2u_wgrad_desc* d, WgPlan* pl) {
   pl->tiles_per_slice = (pl->total_tiles + slices - 1) / slices;
   pl->slices = (pl->total_tiles + pl->tiles_per_slice - 1) / pl->tiles_per_slice;
   pl->stages = 3;
-  const int stage_bytes = kGBytes + (d->taps == 9 ? kXPatchStride : 128 * 128);
+  int stage_bytes = kGBytes + (d->taps == 9 ? kXPatchStride : 128 * 128);
+  pl->swap64 = wg_use_swap64(d) ? 1 : 0;
+  if (pl->swap64) {
+    pl->groups = 1;
+    pl->stages = 4;
+    stage_bytes = kSwapStageBytes;
+  }
   pl->smem = static_cast<size_t>(pl->stages) * stage_bytes + 1024 + (2 * pl->stages + 1) * 8 + 16;
   return B2U_OK;
 }
@@ -439,7 +579,10 @@ extern "C" int b2u_wgrad(const void* g, const void* x, float* workspace, float* 
   p.ws = workspace;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(pl.slices, pl.mblks * pl.xchunks, pl.groups);
-  if (d->taps == 9) {
+  if (pl.swap64) {
+    B2U_SET_MAX_SMEM_ONCE((wgrad_swap64_kernel), 227 * 1024);
+    B2U_PDL_LAUNCH((wgrad_swap64_kernel), grid, kWgThreads, pl.smem, st, tg, tx, p);
+  } else if (d->taps == 9) {
     B2U_SET_MAX_SMEM_ONCE((wgrad_kernel<9>), 227 * 1024);
     B2U_PDL_LAUNCH((wgrad_kernel<9>), grid, kWgThreads, pl.smem, st, tg, tx, p);
   } else {
