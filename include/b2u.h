@@ -348,6 +348,10 @@ int b2u_rotate_back_accumulate(const float* seg, const float* fov, double* acc, 
  * reference's split (top = d/2, left = d - d/2).  ATen's anti-aliased triangle filter, fp32. */
 int b2u_square_pad_resize(const float* x, float* out, int planes, int h, int w, int square_pad, int oh, int ow,
                           void* stream);
+/* Its backward (the multi-fidelity training steps resize the segmentation back up before the loss,
+ * MF-training-UNI.py:66-69): grad_in[planes][h][w] = adjoint of the same filter applied to grad_out[planes][oh][ow]. */
+int b2u_square_pad_resize_bwd(const float* grad_out, float* grad_in, int planes, int h, int w, int square_pad, int oh, int ow,
+                              void* stream);
 
 /* ------------------------------------------------------------------ evaluation metrics (utils_metrics.py:157-173)
  * TP, FP, FN, TN of round(seg) against (long)gt over the pixels with (long)mask != 0 (the FOV), in one pass on the

@@ -530,6 +530,54 @@ def test_square_pad_resize_matches_torchvision():
     assert D.rel(tens, rtens)[0] < 1e-2 and D.rel(mean, rmean)[0] < 5e-3
 
 
+def test_square_pad_resize_backward_matches_torch_autograd():
+    """VERDICT r1 missing 7: the multi-fidelity training steps (MF-training-UNI.py:54-73) resize the segmentation back up
+    before the loss, so the gradient flows through TF.resize.  The adjoint kernel against torch's autograd through the
+    oracle restatement (F.interpolate antialias=True on the zero-padded square): down-scaling with padding, up-scaling
+    without (the resize-back-up of the step), non-square targets, mixed up / down, and the whole MF-style step around
+    this package's UNet (resize down -> model -> resize up -> masked BCE) against the same step built from torch ops."""
+    import unet_research_b200 as U
+    from oracle import unet_oracle as O
+    from unet_research_b200 import synthetic
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(3)
+    for (h, w, size, pad) in [(584, 565, 128, True), (128, 128, (584, 584), False), (120, 116, (64, 80), False), (37, 53, 29, True),
+                              (64, 200, (128, 50), False), (100, 80, 100, True)]:
+        x = torch.randn(2, 1, h, w, generator=g).to(dev)
+        oh, ow = (size, size) if isinstance(size, int) else size
+        wgt = torch.randn(2, 1, oh, ow, generator=g).to(dev)
+        xa = x.clone().requires_grad_(True)
+        (U.square_pad_resize(xa, size, square_pad=pad) * wgt).sum().backward()
+        xb = x.clone().requires_grad_(True)
+        src = O.square_pad(xb) if pad else xb
+        (torch.nn.functional.interpolate(src, size=(oh, ow), mode="bilinear", align_corners=False, antialias=True) * wgt).sum().backward()
+        err = float((xa.grad - xb.grad).abs().max())
+        assert err < 2e-5 * max(1.0, float(xb.grad.abs().max())), (h, w, size, pad, err)
+    # the multi-fidelity training step around this package's UNet, fused resize kernels vs torch's own resize ops
+    h, w, new = 120, 116, 64
+    im = synthetic.make_image(h, w, seed=1234).to(dev)
+    gt = synthetic.make_gt(h, w).to(dev)
+    fov = synthetic.make_fov_mask(h, w).to(dev)
+    losses, grads = [], []
+    for fused in (True, False):
+        m, _ = D._build_model(dev)
+        m.train()
+        if fused:
+            x = U.square_pad_resize(im, new)
+            seg = U.square_pad_resize(m(x), (max(h, w), max(h, w)), square_pad=False)
+        else:
+            x = O.square_pad_resize(im, new)
+            seg = torch.nn.functional.interpolate(m(x), size=(max(h, w), max(h, w)), mode="bilinear", align_corners=False, antialias=True)
+        mk, g2 = O.square_pad(fov), O.square_pad(gt)
+        loss = torch.nn.functional.binary_cross_entropy(seg.clamp(0, 1) * mk, g2 * mk) * (seg.numel() / mk.count_nonzero())
+        loss.backward()
+        losses.append(float(loss.detach()))
+        grads.append(torch.cat([p.grad.flatten() for p in m.parameters()]))
+    # the two inputs differ by ~1e-6 (summation order of the filter taps); bf16 rounding inside the network amplifies that
+    assert abs(losses[0] - losses[1]) < 1e-4 * abs(losses[1])
+    assert D.rel(grads[0], grads[1])[0] < 2e-2
+
+
 def test_fused_sgd_matches_torch():
     """FusedSGD (clip + momentum SGD in two launches) against torch.nn.utils.clip_grad_norm_ + torch.optim.SGD
     (reference training.py:32 + Lightning gradient_clip_val) over several steps, ragged tensor sizes included."""

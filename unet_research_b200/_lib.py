@@ -120,6 +120,7 @@ SIGNATURES = {
     "b2u_rotate_in_table": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _P]),
     "b2u_rotate_back_accumulate": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
     "b2u_square_pad_resize": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "b2u_square_pad_resize_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "b2u_confusion_counts": (_I, [_P, _P, _P, _LL, _P, _P]),
     "b2u_sgd_step": (_I, [_P, _P, _I, _P, _F, _F, _F, _I, _P, _P]),
     "b2u_sgd_chunk_elems": (_LL, []),
@@ -133,7 +134,7 @@ _LAUNCHERS = {"b2u_conv3x3_fwd": 1, "b2u_conv3x3_pro_fwd": 1, "b2u_convT2x2_fwd"
               "b2u_dropblock_dilate": 1, "b2u_dropblock_dilate_v2": 2, "b2u_dropblock_centers_ichan": 1, "b2u_dropblock_centers_from_uniform": 1, "b2u_rotate_bilinear": 1, "b2u_masked_bce_fwd": 2, "b2u_masked_bce_bwd": 1, "b2u_rotate_in_table": 1, "b2u_rotate_back_accumulate": 1,
               "b2u_pack_conv3x3_weight": 1, "b2u_pack_conv3x3_weight_pair": 1, "b2u_pack_batched": 1, "b2u_pack_convT2x2_weight": 1, "b2u_unit_bwd_stats": 1, "b2u_unit_bwd_finalize": 2,
               "b2u_unit_bwd_apply": 1, "b2u_wgrad": 2, "b2u_wgrad_first": 2, "b2u_gemm1x1_fwd": 1,
-              "b2u_pack_convT2x2_dgrad_weight": 1, "b2u_sgd_step": 2, "b2u_confusion_counts": 1, "b2u_square_pad_resize": 1}
+              "b2u_pack_convT2x2_dgrad_weight": 1, "b2u_sgd_step": 2, "b2u_confusion_counts": 1, "b2u_square_pad_resize": 1, "b2u_square_pad_resize_bwd": 1}
 
 
 def load() -> C.CDLL:
