@@ -1095,11 +1095,13 @@ extern "C" int b2u_head_fwd(const void* x, const float* coef, const uint32_t* ma
   const int grid = grid_for((groups + kHeadPix - 1) / kHeadPix * (d->c / 8), 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (d->c == 64 && d->dtype != B2U_F32 && static_cast<long>(d->h) * d->w < (1l << 31)) {
-    // 8 pixels per 8-lane group and trip; grid = whole resident waves (2 blocks per SM) with an integral trip count
+    // 8 pixels per 8-lane group and trip; grid = exactly the resident slots (2 blocks per SM), every block walks
+    // ceil(trips) of them -- the last trip is partly empty.  (An integral trip count made 258 blocks of 5 trips at
+    // 584x565: 110 SMs with two blocks, 38 with one -- the busiest SM did 10 trips where 9 suffice.)
     const long gtrips = (groups + 7) / 8;
     const long slots = static_cast<long>(b2u_num_sms()) * 2 * 32;          // groups resident at once
-    const int trips = static_cast<int>((gtrips + slots - 1) / slots);
-    const int grid8 = static_cast<int>((gtrips + 32l * trips - 1) / (32l * trips));
+    const int grid8 = static_cast<int>(gtrips >= slots ? slots / 32 : (gtrips + 31) / 32);
+    const int trips = static_cast<int>((gtrips + 32l * grid8 - 1) / (32l * grid8));
 #define B2U_HEAD8_T(T)                                                                                              \
   B2U_PDL_LAUNCH((head8_kernel<T>), grid8, 256, 0, st, static_cast<const T*>(x), reinterpret_cast<const float2*>(coef),  \
                  reinterpret_cast<const uint8_t*>(mask1), w_head, out, logits, fov, acc, samples, iter_base, *d, trips)
