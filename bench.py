@@ -466,7 +466,7 @@ def run_gpu(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        val, k, w, cores, kind, others = oracle_mc_forward_timer(2, 0, budget_s=25.0, extras=True)
+        val, k, w, cores, kind, others = oracle_mc_forward_timer(6, 0, budget_s=25.0, extras=True)   # ~15 s of CPU work (+ ~4 s of other legs)
         cpu_baseline = {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
                         "sample": f"{k} MC-DropBlock forward passes of the same 584x565 image "
                                   f"({'unmodified reference modules' if kind == 'reference' else 'oracle port'}, torch fp32, all host threads) after 1 warm-up",
