@@ -113,7 +113,9 @@ class MCRunner:
         # Where in the forward the mask build of the next step is forked (engine.forward hook points).  The mask
         # kernels take issue slots from whatever runs next to them; the deep levels' conv kernels (long K loops, short
         # epilogues) have the most to spare, the 592x576 levels the least (tests/exp_overlap.py).
-        self.fork_point = os.environ.get("B2U_MC_FORK", "enc0")
+        # Measured again with the TMA-store epilogues and the two-pass full-resolution level (profiles/r02d_exp_fork_point.log):
+        # enc0 7.47-7.51 ms, enc1 7.37-7.45, enc2 7.38-7.44, enc3 7.45-7.52, bottleneck 7.63-7.67 per step.
+        self.fork_point = os.environ.get("B2U_MC_FORK", "enc1")
 
     # ---- building blocks (all launch-only)
     def _forward(self, k: int, hook=None):
