@@ -229,7 +229,11 @@ class MaskPlan:
 
     def generate(self, seed: int):
         """Launch both mask phases for the whole table (reads the stream position from `offset_base`)."""
-        self.keep_counts.zero_()
+        self.centers(seed)
+        self.dilate()
+
+    def centers(self, seed: int):
+        """Phase 1: the Philox draws of every call -> compact centre bitmap (ALU-bound; reads `offset_base`)."""
         n = self.n_calls * self.n_sites
         if self.mode == "ichan":
             call("b2u_dropblock_centers_ichan", ptr(self.table), n, self.host_table, C.c_uint64(seed & (2 ** 64 - 1)),
@@ -241,6 +245,11 @@ class MaskPlan:
             else:
                 call("b2u_dropblock_centers", ptr(self.table), n, C.c_uint64(seed & (2 ** 64 - 1)), ptr(self.offset_base),
                      ptr(self.center_bits), stream_ptr())
+
+    def dilate(self):
+        """Phase 2: centre bitmap -> NHWC keep masks + keep counts (memory-bound)."""
+        self.keep_counts.zero_()
+        n = self.n_calls * self.n_sites
         if self.dilate_v2:
             call("b2u_dropblock_dilate_v2", ptr(self.table), n, self.host_table, ptr(self.center_bits), ptr(self.scatter_bits),
                  self.mask_words, ptr(self.mask_bits), ptr(self.keep_counts), stream_ptr())
