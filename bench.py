@@ -462,6 +462,8 @@ def run_gpu(args):
         train = bench_train(dev, rank, world, args.train_steps, 4, peaks)
         if e2e is not None:
             e2e["train"] = {k: train[k] for k in ("metric", "value", "unit", "ms_per_step", "global_batch", "allreduce")}
+            if not args.no_sweep:
+                e2e["train"]["sweep"] = bench_train_sweep(dev, rank, world)
         roofline["train"] = train.get("roofline")
 
     cpu_baseline = None
@@ -646,7 +648,18 @@ def _elementwise_bytes(nb, filters, depth, h, w, h0, w0, fuse_levels):
     return out
 
 
-def bench_train(dev, rank, world, steps, warmup, peaks=None):
+def bench_train_sweep(dev, rank, world, steps=20):
+    """BASELINE configs[4], training part: the same step (fwd + bwd + clip + SGD, batch 1 per GPU, DropBlock on, bf16, CUDA
+    graphs, NCCL gradient averaging when N > 1) at the multi-fidelity training sizes (MF-training-UNI.py:33-44: 128, 256 and the
+    584 x 584 padded original)."""
+    out = []
+    for size in (128, 256, 584):
+        t = bench_train(dev, rank, world, steps, 4, None, hw=(size, size))
+        out.append({"size": f"{size}x{size}", "ms_per_step": t["ms_per_step"], "imgs_per_s": t["value"]})
+    return out
+
+
+def bench_train(dev, rank, world, steps, warmup, peaks=None, hw=None):
     """BASELINE configs[1] (+ configs[4] data-parallel part): fwd + bwd + clip + SGD, batch 1 per GPU, 584x565,
     DropBlock bs 7 p .15, bf16; with N > 1 every rank trains on its own image and the gradients are averaged over
     NCCL inside backward (decoder-side bucket overlapped with the encoder backward).  Returns the `train` object."""
@@ -656,6 +669,7 @@ def bench_train(dev, rank, world, steps, warmup, peaks=None):
     import unet_research_b200 as U
     from unet_research_b200 import synthetic
     from unet_research_b200.canonical import build_canonical
+    H0, W0 = hw if hw is not None else (globals()["H0"], globals()["W0"])
     model, _ = build_canonical(dev, dropblock=True, compute="bf16")
     model.train()
     model.data_parallel = world > 1
