@@ -60,3 +60,44 @@ def test_sharded_statistics_match_full_stack(world, tmp_path):
     torch.testing.assert_close(res["mean"].float(), stack.mean(0), rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(res["std"].float(), stack.std(0), rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(res["samples"], stack[:R], rtol=0, atol=0)
+
+
+def test_plan_segments_and_shards_cover_every_iteration_once():
+    """Host logic of the Monte-Carlo loop: block sharding over ranks + runs of equal batches per rank cover [0, T) exactly
+    once, rank 0 owns the first iterations (the saved samples need no exchange), at most one remainder run per rank."""
+    from unet_research_b200.uncertainty import plan_segments, shard_range
+    assert plan_segments(0, 125, 10) == [(10, 12, 0), (5, 1, 120)]
+    assert plan_segments(7, 7, 10) == []
+    assert plan_segments(3, 10, 10) == [(7, 1, 3)]
+    for total, world, ib in [(1000, 8, 10), (359, 8, 10), (13, 2, 5), (5, 8, 10), (1000, 3, 16), (1, 1, 10)]:
+        seen = []
+        for rank in range(world):
+            t0, t1 = shard_range(total, rank, world)
+            segs = plan_segments(t0, t1, ib)
+            assert len(segs) <= 2
+            for nb, steps, start in segs:
+                assert 1 <= nb <= ib and steps >= 1
+                seen += list(range(start, start + nb * steps))
+        assert seen == list(range(total))
+        assert shard_range(total, 0, world)[0] == 0
+
+
+def test_bench_elementwise_bytes_follow_the_fused_levels():
+    """bench.py's algorithmic bytes of the stand-alone apply kernels: fusing a level removes its applies, never adds bytes,
+    and the boolean forms equal the all / none level sets."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    none = bench.elementwise_bytes_per_step(10, fused=False)
+    allf = bench.elementwise_bytes_per_step(10, fused=True)
+    assert allf == bench.elementwise_bytes_per_step(10, fused=[0, 1, 2, 3, 4]) and none == bench.elementwise_bytes_per_step(10, fused=[])
+    prev = none["b2u_gn_apply"]
+    for lv in ([4], [3, 4], [2, 3, 4], [1, 2, 3, 4], [0, 1, 2, 3, 4]):
+        cur = bench.elementwise_bytes_per_step(10, fused=lv)["b2u_gn_apply"]
+        assert cur < prev
+        prev = cur
+    default = bench.elementwise_bytes_per_step(10, fused=[1, 2, 3, 4])
+    assert allf["b2u_gn_apply"] < default["b2u_gn_apply"] < none["b2u_gn_apply"]
+    assert default["b2u_gn_apply_pool"] == none["b2u_gn_apply_pool"] and default["b2u_head_fwd"] == none["b2u_head_fwd"]

@@ -41,6 +41,20 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def plan_segments(t0: int, t1: int, iter_batch: int):
+    """A rank's iterations [t0, t1) as runs of equal batches: [(batch, steps, first iteration), ...] -- full batches of
+    `iter_batch`, then ONE remainder batch (125 iterations at batch 10 = (10, 12, t0), (5, 1, t0 + 120)).  Every run has its
+    own runner (workspace + CUDA graphs are shaped by the batch)."""
+    out = []
+    done = t0
+    while done < t1:
+        nb = min(iter_batch, t1 - done)
+        steps = (t1 - done) // nb
+        out.append((nb, steps, done))
+        done += steps * nb
+    return out
+
+
 def _dist():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
@@ -284,13 +298,8 @@ class DropBlockEval(_MCBase):
         # enqueued before the first runner's steps: the first one on the caller's stream, the later ones on a low-priority
         # side stream, so that their mask builds overlap the first runner's forwards instead of standing alone between
         # two runners (1.4 ms per call at 8 GPUs).
-        segments = []
-        done = t0
-        while done < t1:
-            nb = min(self.iter_batch, t1 - done)
-            steps = (t1 - done) // nb
-            segments.append((self._runner(nb, h0, w0, dev, active, p, bs), steps, done))
-            done += steps * nb
+        segments = [(self._runner(nb, h0, w0, dev, active, p, bs), steps, start)
+                    for nb, steps, start in plan_segments(t0, t1, self.iter_batch)]
         cur = torch.cuda.current_stream(dev)
         for i, (r, steps, start) in enumerate(segments):
             if i == 0:
