@@ -77,33 +77,40 @@ struct UnitRaw {
   bool inside;
 };
 
-template <typename T>
-__device__ __forceinline__ void unit_load(const UnitBwdParams& p, const UnitBwdPtrs& q, int n, int hh, int ww, int cv, UnitRaw<T>& r) {
-  const long pix = (static_cast<long>(n) * p.h + hh) * p.w + ww;
-  r.y.load(reinterpret_cast<const T*>(q.y) + pix * p.c + cv * 8);
-  r.m1 = q.mask1 ? q.mask1[pix * (p.c >> 3) + cv] : 0xFFu;
+// HAS_P / HAS_H: the pool-backward / head source exists (compile time: the A-only units -- 16 of the 26 -- then carry no
+// pooled-index, argmax, crop or (row, column) arithmetic at all; the first version decided all of it per pixel at run
+// time and spent ~280 instructions per 8-channel vector, issue-bound at 1.2-2.0 TB/s).  `pix` is the pixel index inside
+// image n; every tensor is addressed as per-image base + 32-bit offset (the host checks h * w * channels < 2^31).
+template <typename T, bool HAS_P, bool HAS_H>
+__device__ __forceinline__ void unit_load(const UnitBwdParams& p, const UnitBwdPtrs& q, int n, int pix, int hh, int ww, int cv, UnitRaw<T>& r) {
+  const int npix = p.h * p.w;
+  r.y.load(reinterpret_cast<const T*>(q.y) + static_cast<size_t>(n) * npix * p.c + (pix * p.c + cv * 8));
+  r.m1 = q.mask1 ? q.mask1[static_cast<size_t>(n) * npix * (p.c >> 3) + (pix * (p.c >> 3) + cv)] : 0xFFu;
   r.m2 = 0xFFu;
-  if (q.ga) {
-    r.ga.load(reinterpret_cast<const T*>(q.ga) + pix * p.a_cstride + p.a_coffset + cv * 8);
-    if (q.mask2) r.m2 = q.mask2[pix * (p.mask2_cstride >> 3) + (p.mask2_coffset >> 3) + cv];
+  if (!HAS_H) {
+    r.ga.load(reinterpret_cast<const T*>(q.ga) + static_cast<size_t>(n) * npix * p.a_cstride + (pix * p.a_cstride + p.a_coffset + cv * 8));
+    if (q.mask2) r.m2 = q.mask2[static_cast<size_t>(n) * npix * (p.mask2_cstride >> 3) + (pix * (p.mask2_cstride >> 3) + (p.mask2_coffset >> 3) + cv)];
   }
-  if (q.gp) {
-    const long pp = (static_cast<long>(n) * (p.h >> 1) + (hh >> 1)) * (p.w >> 1) + (ww >> 1);
-    r.gp.load(reinterpret_cast<const T*>(q.gp) + pp * p.c + cv * 8);
-    r.am = *reinterpret_cast<const uint2*>(q.argmax + pp * p.c + cv * 8);
+  if (HAS_P) {
+    const int pp = (hh >> 1) * (p.w >> 1) + (ww >> 1);
+    const size_t pbase = static_cast<size_t>(n) * (npix >> 2) * p.c;
+    r.gp.load(reinterpret_cast<const T*>(q.gp) + pbase + (pp * p.c + cv * 8));
+    r.am = *reinterpret_cast<const uint2*>(q.argmax + pbase + (pp * p.c + cv * 8));
   }
   r.inside = false;
   r.o = r.go = 0.f;
-  if (q.grad_out && hh < p.h0 && ww < p.w0) {
-    const long op = (static_cast<long>(n) * p.h0 + hh) * p.w0 + ww;
-    r.o = q.out[op];
-    r.go = q.grad_out[op];
-    r.inside = true;
+  if (HAS_H) {
+    if (hh < p.h0 && ww < p.w0) {
+      const size_t op = static_cast<size_t>(n) * p.h0 * p.w0 + (hh * p.w0 + ww);
+      r.o = q.out[op];
+      r.go = q.grad_out[op];
+      r.inside = true;
+    }
   }
 }
 
 // upstream gradient g[8] -> dZ[8], raw y[8] (returned in xhat) and the activation for one (pixel, channel vector)
-template <typename T>
+template <typename T, bool HAS_P, bool HAS_H>
 __device__ __forceinline__ void unit_grad8(const UnitBwdParams& p, const UnitBwdPtrs& q, const UnitRaw<T>& r, int hh, int ww, int cv,
                                            const float (&a)[8], const float (&b)[8], float s1, float s2,
                                            float (&dz)[8], float (&xhat)[8], float (&act)[8], float& dlogit) {
@@ -112,7 +119,7 @@ __device__ __forceinline__ void unit_grad8(const UnitBwdParams& p, const UnitBwd
   float g[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) g[i] = 0.f;
-  if (q.ga) {
+  if (!HAS_H) {
     float t[8];
     r.ga.to_float(t);
     if (q.mask2) {
@@ -122,7 +129,7 @@ __device__ __forceinline__ void unit_grad8(const UnitBwdParams& p, const UnitBwd
 #pragma unroll
     for (int i = 0; i < 8; ++i) g[i] += t[i];
   }
-  if (q.gp) {
+  if (HAS_P) {
     float t[8];
     r.gp.to_float(t);
     const uint32_t code = ((hh & 1) << 1) | (ww & 1);
@@ -133,7 +140,7 @@ __device__ __forceinline__ void unit_grad8(const UnitBwdParams& p, const UnitBwd
     }
   }
   dlogit = 0.f;
-  if (q.grad_out) {
+  if (HAS_H) {
     if (r.inside) dlogit = r.go * r.o * (1.f - r.o);
     const float4 wa = __ldg(reinterpret_cast<const float4*>(q.w_head + cv * 8));
     const float4 wb = __ldg(reinterpret_cast<const float4*>(q.w_head + cv * 8 + 4));
@@ -156,7 +163,7 @@ constexpr int kBwdUnroll = 2;       // pixels per thread per trip (all loads of 
 // grid = (rows, n); thread owns channel vector t % cvs; deterministic block reduction to partials[n][row][c][3]
 // GPV = GroupNorm groups per 8-channel vector (1 when the group size is >= 8, else 8 / group size): the per-group
 // (mean, rstd[, c1, c2]) live in GPV registers each instead of 8.
-template <typename T, int GPV>
+template <typename T, int GPV, bool HAS_P, bool HAS_H>
 __global__ void __launch_bounds__(256, 2) unit_bwd_stats_kernel(UnitBwdParams p, UnitBwdPtrs q) {
   pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
   pdl_trigger();    // the successor may be scheduled once every CTA got here
@@ -198,21 +205,24 @@ __global__ void __launch_bounds__(256, 2) unit_bwd_stats_kernel(UnitBwdParams p,
 #pragma unroll
     for (int u = 0; u < kBwdUnroll; ++u) {
       const int pix = base + u * slots;
-      hh[u] = pix / p.w;
-      ww[u] = pix - hh[u] * p.w;
-      if (pix < npix) unit_load<T>(p, q, n, hh[u], ww[u], cv, raw[u]);
+      hh[u] = ww[u] = 0;
+      if (HAS_P || HAS_H) {                                   // (row, column) only where a source needs them
+        hh[u] = pix / p.w;
+        ww[u] = pix - hh[u] * p.w;
+      }
+      if (pix < npix) unit_load<T, HAS_P, HAS_H>(p, q, n, pix, hh[u], ww[u], cv, raw[u]);
     }
 #pragma unroll
     for (int u = 0; u < kBwdUnroll; ++u) {
       if (base + u * slots < npix) {
         float dz[8], xhat[8], act[8], dlogit;
-        unit_grad8<T>(p, q, raw[u], hh[u], ww[u], cv, a, b, s1, s2, dz, xhat, act, dlogit);
+        unit_grad8<T, HAS_P, HAS_H>(p, q, raw[u], hh[u], ww[u], cv, a, b, s1, s2, dz, xhat, act, dlogit);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float xh = (xhat[i] - mean8[i / CPG]) * rstd8[i / CPG];   // xhat[] holds the raw conv output
           acc1[i] += dz[i];
           acc2[i] += dz[i] * xh;
-          acc3[i] += dlogit * act[i];
+          if (HAS_H) acc3[i] += dlogit * act[i];
         }
       }
     }
@@ -328,7 +338,7 @@ __global__ void __launch_bounds__(kBwdFinWarps * 32) bwd_finalize_kernel(const f
   }
 }
 
-template <typename T, int GPV>
+template <typename T, int GPV, bool HAS_P, bool HAS_H>
 __global__ void __launch_bounds__(256, 2) unit_bwd_apply_kernel(UnitBwdParams p, UnitBwdPtrs q) {
   pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
   pdl_trigger();    // the successor may be scheduled once every CTA got here
@@ -370,31 +380,34 @@ __global__ void __launch_bounds__(256, 2) unit_bwd_apply_kernel(UnitBwdParams p,
 #pragma unroll
     for (int u = 0; u < kBwdUnroll; ++u) {
       const int pix = base + u * slots;
-      hh[u] = pix / p.w;
-      ww[u] = pix - hh[u] * p.w;
-      if (pix < npix) unit_load<T>(p, q, n, hh[u], ww[u], cv, raw[u]);
+      hh[u] = ww[u] = 0;
+      if (HAS_P || HAS_H || p.s2d) {                          // (row, column) only where a source or the output layout needs them
+        hh[u] = pix / p.w;
+        ww[u] = pix - hh[u] * p.w;
+      }
+      if (pix < npix) unit_load<T, HAS_P, HAS_H>(p, q, n, pix, hh[u], ww[u], cv, raw[u]);
     }
 #pragma unroll
     for (int u = 0; u < kBwdUnroll; ++u) {
       if (base + u * slots < npix) {
         float dz[8], xhat[8], act[8], dlogit;
-        unit_grad8<T>(p, q, raw[u], hh[u], ww[u], cv, a, b, s1, s2, dz, xhat, act, dlogit);
+        unit_grad8<T, HAS_P, HAS_H>(p, q, raw[u], hh[u], ww[u], cv, a, b, s1, s2, dz, xhat, act, dlogit);
         float o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float xh = (xhat[i] - mean8[i / CPG]) * rstd8[i / CPG];
           o[i] = rstd8[i / CPG] * (gm[i] * dz[i] - c1[i / CPG] - xh * c2[i / CPG]);
         }
-        long dst;
+        int dst;                                              // offset inside image n
         if (p.s2d) {
-          const long pp = (static_cast<long>(n) * (p.h >> 1) + (hh[u] >> 1)) * (p.w >> 1) + (ww[u] >> 1);
+          const int pp = (hh[u] >> 1) * (p.w >> 1) + (ww[u] >> 1);
           dst = (pp * 4 + (((hh[u] & 1) << 1) | (ww[u] & 1))) * p.c + cv * 8;
         } else {
-          dst = ((static_cast<long>(n) * p.h + hh[u]) * p.w + ww[u]) * p.c + cv * 8;
+          dst = (base + u * slots) * p.c + cv * 8;
         }
         Vec8<T> v;
         v.from_float(o);
-        v.store(dy + dst);
+        v.store(dy + static_cast<size_t>(n) * npix * p.c + dst);
       }
     }
   }
@@ -421,7 +434,14 @@ static int fill_unit(const b2u_unit_bwd_desc* d, UnitBwdParams* p, UnitBwdPtrs* 
   B2U_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->c % 8 == 0 && d->c / 8 <= 256, "bad tensor shape");
   B2U_REQUIRE(d->num_groups > 0 && d->c % d->num_groups == 0, "bad group count");
   B2U_REQUIRE(d->y && d->coef && d->mean_rstd && d->gamma, "null unit tensors");
-  B2U_REQUIRE(d->grad_a || d->grad_pool || d->grad_out, "no upstream gradient source");
+  B2U_REQUIRE(d->grad_a || d->grad_out, "no upstream gradient source");
+  // the kernels are specialised for the three source sets the backward schedule produces
+  B2U_REQUIRE(!d->grad_out || (!d->grad_a && !d->grad_pool), "the head source (grad_out) stands alone");
+  B2U_REQUIRE(!d->grad_pool || d->grad_a, "the pool source (grad_pool) comes with a dense source (grad_a)");
+  {
+    const long long widest = d->a_cstride > d->c ? d->a_cstride : d->c;
+    B2U_REQUIRE(static_cast<long long>(d->h) * d->w * widest < (1ll << 31), "image too large for 32-bit in-image offsets");
+  }
   B2U_REQUIRE(!d->grad_pool || (d->argmax && d->h % 2 == 0 && d->w % 2 == 0), "pool source needs argmax and even h,w");
   B2U_REQUIRE(!d->grad_out || (d->out && d->w_head), "head source needs out and w_head");
   B2U_REQUIRE(!d->mask2 || d->keep_counts2, "mask2 needs keep counts");
@@ -467,15 +487,22 @@ extern "C" int b2u_unit_bwd_stats(const b2u_unit_bwd_desc* d, float* partials, v
   const int gsize = d->c / d->num_groups;
   const int gpv = gsize >= 8 ? 1 : 8 / gsize;
   B2U_REQUIRE(gpv == 1 || gpv == 2 || gpv == 4, "group size %d must be 2, 4 or a multiple of 8", gsize);
+#define B2U_STATS_S(T, HP, HH)                                                                       \
+  do {                                                                                               \
+    if (gpv == 1) B2U_PDL_LAUNCH((unit_bwd_stats_kernel<T, 1, HP, HH>), grid, threads, smem, st, p, q);      \
+    else if (gpv == 2) B2U_PDL_LAUNCH((unit_bwd_stats_kernel<T, 2, HP, HH>), grid, threads, smem, st, p, q); \
+    else B2U_PDL_LAUNCH((unit_bwd_stats_kernel<T, 4, HP, HH>), grid, threads, smem, st, p, q);               \
+  } while (0)
 #define B2U_STATS(T)                                                                  \
   do {                                                                                \
-    if (gpv == 1) B2U_PDL_LAUNCH((unit_bwd_stats_kernel<T, 1>), grid, threads, smem, st, p, q);      \
-    else if (gpv == 2) B2U_PDL_LAUNCH((unit_bwd_stats_kernel<T, 2>), grid, threads, smem, st, p, q); \
-    else B2U_PDL_LAUNCH((unit_bwd_stats_kernel<T, 4>), grid, threads, smem, st, p, q);               \
+    if (d->grad_out) B2U_STATS_S(T, false, true);                                     \
+    else if (d->grad_pool) B2U_STATS_S(T, true, false);                               \
+    else B2U_STATS_S(T, false, false);                                                \
   } while (0)
   if (d->dtype == B2U_F32) B2U_STATS(float);
   else B2U_STATS(__nv_bfloat16);
 #undef B2U_STATS
+#undef B2U_STATS_S
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
@@ -509,15 +536,22 @@ extern "C" int b2u_unit_bwd_apply(const b2u_unit_bwd_desc* d, const float* group
   const int gsize = d->c / d->num_groups;
   const int gpv = gsize >= 8 ? 1 : 8 / gsize;
   B2U_REQUIRE(gpv == 1 || gpv == 2 || gpv == 4, "group size %d must be 2, 4 or a multiple of 8", gsize);
+#define B2U_APPLY_S(T, HP, HH)                                                                    \
+  do {                                                                                            \
+    if (gpv == 1) B2U_PDL_LAUNCH((unit_bwd_apply_kernel<T, 1, HP, HH>), grid, threads, 0, st, p, q);      \
+    else if (gpv == 2) B2U_PDL_LAUNCH((unit_bwd_apply_kernel<T, 2, HP, HH>), grid, threads, 0, st, p, q); \
+    else B2U_PDL_LAUNCH((unit_bwd_apply_kernel<T, 4, HP, HH>), grid, threads, 0, st, p, q);               \
+  } while (0)
 #define B2U_APPLY(T)                                                               \
   do {                                                                             \
-    if (gpv == 1) B2U_PDL_LAUNCH((unit_bwd_apply_kernel<T, 1>), grid, threads, 0, st, p, q);      \
-    else if (gpv == 2) B2U_PDL_LAUNCH((unit_bwd_apply_kernel<T, 2>), grid, threads, 0, st, p, q); \
-    else B2U_PDL_LAUNCH((unit_bwd_apply_kernel<T, 4>), grid, threads, 0, st, p, q);               \
+    if (d->grad_out) B2U_APPLY_S(T, false, true);                                  \
+    else if (d->grad_pool) B2U_APPLY_S(T, true, false);                            \
+    else B2U_APPLY_S(T, false, false);                                             \
   } while (0)
   if (d->dtype == B2U_F32) B2U_APPLY(float);
   else B2U_APPLY(__nv_bfloat16);
 #undef B2U_APPLY
+#undef B2U_APPLY_S
   B2U_LAUNCH_CHECK();
   return B2U_OK;
 }
