@@ -31,6 +31,7 @@ struct WgradParams {
   int taps;                  // 9 or 1
   int xchunks;               // cx / 64
   int stages;
+  int tma_store;             // 1: the epilogue stages 32 x 32 fp32 blocks in the (by then idle) pipeline stages and writes them with TMA stores
   float* ws;                 // [slices][taps][cg][cx]
 };
 
@@ -56,7 +57,8 @@ constexpr bool kPairTaps = B2U_WGRAD_PAIR_TAPS != 0;
 
 template <int TAPS>   // 9: 3x3 (tap groups of 8 + 1 over blockIdx.z), 1: plain
 __global__ void __launch_bounds__(kWgThreads, 1)
-wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+             const WgradParams p) {
   // bf16 A/B both MN-major (bits 15, 16), fp32 accumulate, M = 128, N = 64
   constexpr uint32_t kIdesc = umma_idesc(128, 64, 1) | (1u << 15) | (1u << 16);
   constexpr uint32_t kIdescPair = umma_idesc(128, 128, 1) | (1u << 15) | (1u << 16);
@@ -174,6 +176,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
     mbar_wait(done_bar, 0);
     tc_fence_after();
     const bool valid = (m0 + row) < p.cg && t_begin < t_end;
+    // TMA-store path: a thread owns one accumulator ROW (one gradient channel), i.e. a 128-byte run of fp32 per 32
+    // columns, and neighbouring threads own rows cx * 4 bytes apart -- a warp-wide STG.128 touched 32 lines with 16
+    // bytes each, 16 of them per tap and thread, and this epilogue is fully exposed (the accumulators live for the whole
+    // CTA).  Every warp now stages its 32 rows x 128 bytes in one of two 4 KB slots carved out of the pipeline stages (all
+    // MMAs have completed: done_bar) under the 128-byte swizzle and writes the block with one TMA store.
+    const bool tma_st = p.tma_store != 0 && t_begin < t_end;
+    const uint32_t slot0 = smem_u32(smem) + static_cast<uint32_t>(q * 8192);
+    int nstore = 0;
     for (int t = 0; t < tap_count; ++t) {
       // paired layout: TMEM column block t holds tap [0, 1, 3, 4, 6, 7, 2, 5][t]
       const int tap = (TAPS == 9 && blockIdx.z == 0 && kPairTaps) ? (t < 6 ? 3 * (t >> 1) + (t & 1) : (t == 6 ? 2 : 5)) : tap_begin + t;
@@ -183,7 +193,24 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
         uint32_t rr[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 64 + chunk * 32, rr);
         tmem_ld_wait();
-        if (valid) {
+        if (tma_st) {
+          const uint32_t slot = slot0 + static_cast<uint32_t>((nstore & 1) * 4096);
+          if (lane == 0) bulk_wait_read<1>();                 // the store issued two blocks ago has read this slot
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            sts128(slot + static_cast<uint32_t>(lane * 128 + ((i ^ (lane & 7)) << 4)), make_uint4(rr[4 * i], rr[4 * i + 1], rr[4 * i + 2], rr[4 * i + 3]));
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmW)), "r"(slot), "r"(c0 + chunk * 32),
+                           "r"((slice * p.taps + tap) * p.cg + m0 + q * 32)
+                         : "memory");
+            bulk_commit();
+          }
+          ++nstore;
+        } else if (valid) {
           float4* d4 = reinterpret_cast<float4*>(dst + chunk * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -192,6 +219,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CU
         }
       }
     }
+    if (tma_st && lane == 0) bulk_wait<0>();
     tc_fence_before();
   }
   __syncthreads();
@@ -571,7 +599,25 @@ extern "C" int b2u_wgrad(const void* g, const void* x, float* workspace, float* 
     rc = conv_encode_map(&tx, B2U_BF16, 4, x, dims, strides, d->taps == 9 ? box9 : box1);
     if (rc) return rc;
   }
+  CUtensorMap tw = tg;
+  // workspace [slices * taps * cg rows][cx] fp32: 32 x 32 blocks (128-byte rows).  Rows of a block must not run past the
+  // tensor's cg rows of one (slice, tap): the 128-row M block is full only when cg is a multiple of 128.
+  static int env_tma = -1;
+  if (env_tma < 0) {
+    const char* e = getenv("B2U_WGRAD_TMA_STORE");
+    env_tma = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool tma_store = env_tma && !pl.swap64 && d->cg % 128 == 0 &&
+                         static_cast<long long>(pl.slices) * d->taps * d->cg < (1ll << 31);
+  if (tma_store) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(d->cx), static_cast<cuuint64_t>(pl.slices) * d->taps * d->cg};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(d->cx) * 4};
+    cuuint32_t box[2] = {32, 32};
+    rc = conv_encode_map(&tw, B2U_F32, 2, workspace, dims, strides, box);
+    if (rc) return rc;
+  }
   WgradParams p;
+  p.tma_store = tma_store ? 1 : 0;
   p.n = d->n; p.h = d->h; p.w = d->w;
   p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.total_tiles = pl.total_tiles;
   p.tiles_per_slice = pl.tiles_per_slice; p.slices = pl.slices;
@@ -584,10 +630,10 @@ extern "C" int b2u_wgrad(const void* g, const void* x, float* workspace, float* 
     B2U_PDL_LAUNCH((wgrad_swap64_kernel), grid, kWgThreads, pl.smem, st, tg, tx, p);
   } else if (d->taps == 9) {
     B2U_SET_MAX_SMEM_ONCE((wgrad_kernel<9>), 227 * 1024);
-    B2U_PDL_LAUNCH((wgrad_kernel<9>), grid, kWgThreads, pl.smem, st, tg, tx, p);
+    B2U_PDL_LAUNCH((wgrad_kernel<9>), grid, kWgThreads, pl.smem, st, tg, tx, tw, p);
   } else {
     B2U_SET_MAX_SMEM_ONCE((wgrad_kernel<1>), 227 * 1024);
-    B2U_PDL_LAUNCH((wgrad_kernel<1>), grid, kWgThreads, pl.smem, st, tg, tx, p);
+    B2U_PDL_LAUNCH((wgrad_kernel<1>), grid, kWgThreads, pl.smem, st, tg, tx, tw, p);
   }
   B2U_LAUNCH_CHECK();
   const long total = static_cast<long>(d->taps) * d->cg * d->cx;
