@@ -557,8 +557,8 @@ __global__ void __launch_bounds__(256, 2) head8_kernel(const T* __restrict__ x, 
   pdl_trigger();    // the successor may be scheduled once every CTA got here
   const int l = threadIdx.x & 7;
   const int gbase = threadIdx.x & 24;                         // first lane of this group within the warp
-  const long group = (blockIdx.x * 256L + threadIdx.x) >> 3;
-  const long ngroups = gridDim.x * 32L;
+  const long group = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 3;
+  const long ngroups = gridDim.x * static_cast<long>(blockDim.x >> 3);
   const long npix0 = static_cast<long>(d.h0) * d.w0;
   const long img_stride = static_cast<long>(d.h) * d.w;
   float wh[8];
@@ -575,7 +575,13 @@ __global__ void __launch_bounds__(256, 2) head8_kernel(const T* __restrict__ x, 
     int pb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) pb[j] = __shfl_sync(0xffffffffu, mypb, gbase + j);
-    double s1 = 0.0, s2 = 0.0;
+    double s1 = 0.0, s2 = 0.0, a1 = 0.0, a2 = 0.0;
+    float fv0 = 1.f;
+    if (acc && active) {                                      // fetched a whole trip before their use
+      a1 = acc[op];
+      a2 = acc[npix0 + op];
+      if (fov && !d.fov_per_image) fv0 = fov[op];
+    }
     for (int n = 0; n < d.n; ++n) {
       Vec8<T> vec[8];
       uint32_t m1[8];
@@ -619,7 +625,7 @@ __global__ void __launch_bounds__(256, 2) head8_kernel(const T* __restrict__ x, 
         if (logits) logits[static_cast<long>(n) * npix0 + op] = dot;
         if (out) out[static_cast<long>(n) * npix0 + op] = yv;
         if (acc) {
-          const float fv = fov ? fov[(d.fov_per_image ? static_cast<long>(n) * npix0 : 0) + op] : 1.f;
+          const float fv = (fov && d.fov_per_image) ? fov[static_cast<long>(n) * npix0 + op] : fv0;
           const float v = yv * fv;
           s1 += static_cast<double>(v);
           s2 += static_cast<double>(v) * static_cast<double>(v);
@@ -629,10 +635,169 @@ __global__ void __launch_bounds__(256, 2) head8_kernel(const T* __restrict__ x, 
       }
     }
     if (acc && active) {
-      acc[op] += s1;
-      acc[npix0 + op] += s2;
+      acc[op] = a1 + s1;
+      acc[npix0 + op] = a2 + s2;
     }
   }
+}
+
+// head8 with the 16-byte activation vectors (and the 8 mask bytes of a pixel) moved by cp.async through a per-thread
+// shared-memory ring of S items (item = one image of one trip: 8 vectors per thread): the loads of the next S - 1 items
+// are in flight WHILE an item is reduced, at no register cost (head8_kernel holds its 8 vectors in registers and has
+// nothing in flight during the butterfly / sigmoid / fp64 tail -- 128 registers leave no room for a second set).  A
+// thread reads back only the vectors it copied itself (no barrier); the mask bytes are copied by the pixel's own lane
+// (8 bytes) and read by the eight lanes of its group after a __syncwarp.  Same arithmetic in the same order as head8_kernel.
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, int S>
+__global__ void __launch_bounds__(256, 2) head8_async_kernel(const T* __restrict__ x, const float2* __restrict__ coef, const uint8_t* __restrict__ mask1,
+                             const float* __restrict__ w_head, float* __restrict__ out, float* __restrict__ logits,
+                             const float* __restrict__ fov, double* __restrict__ acc, float* __restrict__ samples,
+                             const long long* __restrict__ iter_base, b2u_head_desc d, int trips) {
+  extern __shared__ __align__(16) uint8_t head_ring[];        // [S][8][nt] uint4, then [S][nt] 8-byte pixel masks
+  pdl_wait();       // predecessor grid complete + visible (no-op without the PDL launch attribute)
+  pdl_trigger();    // the successor may be scheduled once every CTA got here
+  const int nt = blockDim.x;
+  const int l = threadIdx.x & 7;
+  const int gbase = threadIdx.x & 24;                         // first lane of this group within the warp
+  const long group = (blockIdx.x * static_cast<long>(nt) + threadIdx.x) >> 3;
+  const long ngroups = gridDim.x * static_cast<long>(nt >> 3);
+  const long npix0 = static_cast<long>(d.h0) * d.w0;
+  const long img_stride = static_cast<long>(d.h) * d.w;
+  const uint32_t ring = smem_u32(head_ring) + threadIdx.x * 16u;
+  const uint32_t mring = smem_u32(head_ring) + static_cast<uint32_t>(S * 8 * nt) * 16u;
+  const uint32_t stage_bytes = static_cast<uint32_t>(8 * nt) * 16u;
+  const uint32_t mstage_bytes = static_cast<uint32_t>(nt) * 8u;
+  float wh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) wh[i] = __ldg(w_head + l * 8 + i);
+  const long long base_iter = iter_base ? *iter_base : 0;
+  const bool h4 = (l & 4) != 0, h2 = (l & 2) != 0, h1 = (l & 1) != 0;
+  const int items = trips * d.n;
+
+  // producer cursor: item (p_tr, p_n) goes to stage p_s; p_pb = this lane's own pixel of trip p_tr (clamped)
+  int p_tr = 0, p_n = 0, p_s = 0, p_pb = 0;
+  auto own_pixel = [&](int tr, long& op, bool& active) {
+    op = (tr * ngroups + group) * 8 + l;
+    active = op < npix0;
+    const long opc = active ? op : npix0 - 1;
+    const int oh = static_cast<int>(opc / d.w0), ow = static_cast<int>(opc - static_cast<long>(oh) * d.w0);
+    return oh * d.w + ow;
+  };
+  {
+    long op_; bool a_;
+    p_pb = own_pixel(0, op_, a_);
+  }
+  auto issue = [&]() {
+    if (p_tr < trips) {
+      const long img_off = static_cast<long>(p_n) * img_stride;
+      const uint32_t sdst = ring + static_cast<uint32_t>(p_s) * stage_bytes;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int pbj = __shfl_sync(0xffffffffu, p_pb, gbase + j);
+        cp_async16(sdst + static_cast<uint32_t>(j * nt) * 16u, x + (img_off + pbj) * 64 + l * 8);
+      }
+      if (mask1) cp_async8(mring + static_cast<uint32_t>(p_s) * mstage_bytes + threadIdx.x * 8u, mask1 + (img_off + p_pb) * 8);
+      if (++p_n == d.n) {
+        p_n = 0;
+        ++p_tr;
+        long op_; bool a_;
+        p_pb = own_pixel(p_tr < trips ? p_tr : 0, op_, a_);
+      }
+      if (++p_s == S) p_s = 0;
+    }
+    cp_async_commit();                                          // (an empty group past the end keeps the wait count uniform)
+  };
+#pragma unroll
+  for (int s = 0; s < S - 1; ++s) issue();
+
+  int c_n = 0, c_tr = 0, c_s = 0;
+  long op = 0;
+  bool active = false;
+  double s1 = 0.0, s2 = 0.0, a1 = 0.0, a2 = 0.0;
+  float fv0 = 1.f;
+  for (int k = 0; k < items; ++k) {
+    cp_async_wait<S - 2>();                                     // item k has landed (this thread's copies)
+    __syncwarp();                                               // ... and the other lanes' mask bytes; stage (k - 1) % S is free
+    issue();                                                    // item k + S - 1 into the stage consumed last iteration
+    if (c_n == 0) {
+      // a trip's own-pixel state; the fov value and the accumulator pair are fetched HERE, a whole trip before their use
+      // (they were two exposed DRAM round trips per trip: every warp of the SM reaches them at about the same time)
+      own_pixel(c_tr, op, active);
+      s1 = 0.0; s2 = 0.0;
+      if (acc && active) {
+        a1 = acc[op];
+        a2 = acc[npix0 + op];
+        if (fov && !d.fov_per_image) fv0 = fov[op];
+      }
+    }
+    const int n = c_n;
+    Coef8 cf;
+    cf.load(coef + static_cast<size_t>(n) * 64 + l * 8);
+    const uint32_t ssrc = ring + static_cast<uint32_t>(c_s) * stage_bytes;
+    const uint32_t msrc = mring + static_cast<uint32_t>(c_s) * mstage_bytes + static_cast<uint32_t>(threadIdx.x & ~7) * 8u + l;
+    float ds[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      Vec8<T> v;
+      v.raw = lds128(ssrc + static_cast<uint32_t>(j * nt) * 16u);
+      uint32_t m1 = 0xFFu;
+      if (mask1) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(m1) : "r"(msrc + j * 8u));
+      float f[8];
+      v.to_float(f);
+      apply8(f, cf, m1, true);
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dot = fmaf(f[i], wh[i], dot);
+      ds[j] = dot;
+    }
+    float e4[4], e2[2];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float send = h4 ? ds[kk] : ds[kk + 4], keep = h4 ? ds[kk + 4] : ds[kk];
+      e4[kk] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const float send = h2 ? e4[kk] : e4[kk + 2], keep = h2 ? e4[kk + 2] : e4[kk];
+      e2[kk] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const float send1 = h1 ? e2[0] : e2[1], keep1 = h1 ? e2[1] : e2[0];
+    const float dot = keep1 + __shfl_xor_sync(0xffffffffu, send1, 1);
+    if (active) {
+      float yv = 1.f / (1.f + expf(-dot));
+      yv = fminf(fmaxf(yv, 0.f), 1.f);
+      if (yv != yv) yv = 0.f;
+      if (logits) logits[static_cast<long>(n) * npix0 + op] = dot;
+      if (out) out[static_cast<long>(n) * npix0 + op] = yv;
+      if (acc) {
+        const float fv = (fov && d.fov_per_image) ? fov[static_cast<long>(n) * npix0 + op] : fv0;
+        const float v = yv * fv;
+        s1 += static_cast<double>(v);
+        s2 += static_cast<double>(v) * static_cast<double>(v);
+        const long long it = base_iter + n;
+        if (samples && it < d.return_num) samples[it * npix0 + op] = v;
+      }
+    }
+    if (++c_n == d.n) {
+      c_n = 0;
+      ++c_tr;
+      if (acc && active) {
+        acc[op] = a1 + s1;
+        acc[npix0 + op] = a2 + s2;
+      }
+    }
+    if (++c_s == S) c_s = 0;
+  }
+  cp_async_wait<0>();
 }
 
 __global__ void mc_finalize_kernel(const double* __restrict__ acc, float* __restrict__ mean, float* __restrict__ stdv,
@@ -1099,12 +1264,58 @@ extern "C" int b2u_head_fwd(const void* x, const float* coef, const uint32_t* ma
     // ceil(trips) of them -- the last trip is partly empty.  (An integral trip count made 258 blocks of 5 trips at
     // 584x565: 110 SMs with two blocks, 38 with one -- the busiest SM did 10 trips where 9 suffice.)
     const long gtrips = (groups + 7) / 8;
-    const long slots = static_cast<long>(b2u_num_sms()) * 2 * 32;          // groups resident at once
-    const int grid8 = static_cast<int>(gtrips >= slots ? slots / 32 : (gtrips + 31) / 32);
-    const int trips = static_cast<int>((gtrips + 32l * grid8 - 1) / (32l * grid8));
+    // Variant and shape of the launch.  Default: the cp.async ring kernel with 2 stages and 224 or 192 threads per block,
+    // whichever fills the last trip better (tests/exp_head.py, profiles/r02i_exp_head.log: at 10 x 584 x 565 the register
+    // kernel at 256 threads takes 104 us, the ring kernel 95 us with 2 stages x 224 threads, 101 us with 3 stages, 110 us
+    // with 4 -- the larger the ring the smaller L1 -- and 110-126 us at 256 threads, whose 9472 resident groups leave
+    // the fifth trip 35 % full).  Diagnostic overrides, read per call: B2U_HEAD_ASYNC=0 (register kernel, 256 threads),
+    // B2U_HEAD_THREADS, B2U_HEAD_STAGES.
+    int nt = 0, use_async = 1, stages = 2;
+    if (const char* e = getenv("B2U_HEAD_ASYNC")) use_async = atoi(e);
+    if (const char* e = getenv("B2U_HEAD_THREADS")) nt = atoi(e);
+    if (const char* e = getenv("B2U_HEAD_STAGES")) stages = atoi(e);
+    const long sms2 = static_cast<long>(b2u_num_sms()) * 2;                 // blocks resident at once
+    if (nt == 0 && !use_async) nt = 256;
+    if (nt == 0) {
+      double best = -1.0;
+      for (int cand = 224; cand >= 192; cand -= 32) {
+        const long g = cand / 8, resident = sms2 * g;
+        const long tr = gtrips >= resident ? (gtrips + resident - 1) / resident : 1;
+        const double fill = gtrips >= resident ? static_cast<double>(gtrips) / static_cast<double>(tr * resident) : 1.0;
+        if (fill > best + 1e-9) { best = fill; nt = cand; }
+      }
+    }
+    B2U_REQUIRE(nt >= 64 && nt <= 256 && nt % 32 == 0, "B2U_HEAD_THREADS must be 64..256, a multiple of 32");
+    B2U_REQUIRE(stages >= 2 && stages <= 4, "B2U_HEAD_STAGES must be 2, 3 or 4");
+    const long gpb = nt / 8;                                                // groups per block
+    const long slots = sms2 * gpb;                                          // groups resident at once
+    const int grid8 = static_cast<int>(gtrips >= slots ? slots / gpb : (gtrips + gpb - 1) / gpb);
+    const int trips = static_cast<int>((gtrips + gpb * grid8 - 1) / (gpb * grid8));
+    const int ring_bytes = nt * stages * (8 * 16 + 8);
+    B2U_REQUIRE(!use_async || 2 * (ring_bytes + 1024) <= 227 * 1024, "head ring of %d bytes does not fit twice per SM", ring_bytes);
 #define B2U_HEAD8_T(T)                                                                                              \
-  B2U_PDL_LAUNCH((head8_kernel<T>), grid8, 256, 0, st, static_cast<const T*>(x), reinterpret_cast<const float2*>(coef),  \
-                 reinterpret_cast<const uint8_t*>(mask1), w_head, out, logits, fov, acc, samples, iter_base, *d, trips)
+  do {                                                                                                              \
+    if (use_async && stages == 3) {                                                                                 \
+      B2U_SET_MAX_SMEM_ONCE((head8_async_kernel<T, 3>), 112 * 1024);                                                \
+      B2U_PDL_LAUNCH((head8_async_kernel<T, 3>), grid8, nt, ring_bytes, st, static_cast<const T*>(x),               \
+                     reinterpret_cast<const float2*>(coef), reinterpret_cast<const uint8_t*>(mask1), w_head, out,   \
+                     logits, fov, acc, samples, iter_base, *d, trips);                                              \
+    } else if (use_async && stages == 2) {                                                                          \
+      B2U_SET_MAX_SMEM_ONCE((head8_async_kernel<T, 2>), 112 * 1024);                                                \
+      B2U_PDL_LAUNCH((head8_async_kernel<T, 2>), grid8, nt, ring_bytes, st, static_cast<const T*>(x),               \
+                     reinterpret_cast<const float2*>(coef), reinterpret_cast<const uint8_t*>(mask1), w_head, out,   \
+                     logits, fov, acc, samples, iter_base, *d, trips);                                              \
+    } else if (use_async) {                                                                                         \
+      B2U_SET_MAX_SMEM_ONCE((head8_async_kernel<T, 4>), 112 * 1024);                                                \
+      B2U_PDL_LAUNCH((head8_async_kernel<T, 4>), grid8, nt, ring_bytes, st, static_cast<const T*>(x),               \
+                     reinterpret_cast<const float2*>(coef), reinterpret_cast<const uint8_t*>(mask1), w_head, out,   \
+                     logits, fov, acc, samples, iter_base, *d, trips);                                              \
+    } else {                                                                                                        \
+      B2U_PDL_LAUNCH((head8_kernel<T>), grid8, nt, 0, st, static_cast<const T*>(x),                                 \
+                     reinterpret_cast<const float2*>(coef), reinterpret_cast<const uint8_t*>(mask1), w_head, out,   \
+                     logits, fov, acc, samples, iter_base, *d, trips);                                              \
+    }                                                                                                               \
+  } while (0)
     if (d->dtype == B2U_F16) B2U_HEAD8_T(__half);
     else B2U_HEAD8_T(__nv_bfloat16);
 #undef B2U_HEAD8_T
