@@ -180,6 +180,10 @@ typedef struct {
 int b2u_head_fwd(const void* x, const float* coef, const uint32_t* mask1, const float* w_head, float* out,
                  float* logits, const float* fov, double* acc, float* samples, const long long* iter_base,
                  const b2u_head_desc* d, void* stream);
+/* Launch shape b2u_head_fwd uses for the c = 64, 16-bit head of an h0 x w0 output on a device with num_sms SMs (host
+ * only, no device work): plan[0] = 1 cp.async ring kernel / 0 register kernel, [1] threads per block, [2] blocks,
+ * [3] trips per block (a trip = 8 pixels per 8-lane group), [4] ring stages, [5] dynamic shared memory per block. */
+int b2u_head_plan(int h0, int w0, int num_sms, int* plan);
 /* mean = S1/T, std = sqrt(max((S2 - S1*S1/T)/(T-1), 0)) (unbiased, torch.std default) */
 int b2u_mc_finalize(const double* acc, float* mean, float* std, long long npix, long long t, void* stream);
 /* acc[0] += v, acc[1] += v*v for v = x[i] * fov (rotation ensemble accumulation of already-final samples) */

@@ -18,7 +18,7 @@ import traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SECTIONS = ["info", "conv", "convv1", "convv2", "wgrad", "bwdk", "convt", "first", "gn", "pool", "head", "dropblock", "rotate", "forward", "mc", "rot_ens", "tf32", "train", "traingraph", "precision", "ichan"]
+SECTIONS = ["info", "conv", "convv1", "convv2", "wgrad", "bwdk", "convt", "first", "gn", "pool", "head", "head_variants", "dropblock", "rotate", "forward", "mc", "rot_ens", "tf32", "train", "traingraph", "precision", "ichan"]
 
 
 def rel(a, b):
@@ -574,6 +574,65 @@ def sec_pool():
         print(f"  apply_pool c{c}: skip rel {r1:.3e} pooled rel {r2:.3e} argmax match {argmatch:.6f} stats_rel {sr:.3e} first-half-untouched {float(cat[..., :c].abs().max()):.1f}")
         res.append({"skip": r1, "pooled": r2, "argmax": argmatch, "stats_rel": sr, "untouched": float(cat[..., :c].abs().max())})
     return res
+
+
+def sec_head_variants():
+    """The c = 64 head: cp.async ring kernel (default) vs the register kernel (B2U_HEAD_ASYNC=0) vs torch, with and without the
+    DropBlock mask, shared and per-image fov, one and several trips per block, fp16 and bf16.  Returns (all bit-identical
+    between the kernels, worst rel against torch)."""
+    import torch
+    from unet_research_b200 import _lib
+    from unet_research_b200._lib import HeadDesc, call, ptr, stream_ptr
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(23)
+    same_all, worst = True, 0.0
+    saved = {k: os.environ.pop(k, None) for k in ("B2U_HEAD_ASYNC", "B2U_HEAD_THREADS", "B2U_HEAD_STAGES")}
+    try:
+        for (n, h, w, h0, w0, dt, use_mask, per_image) in [(3, 32, 48, 29, 45, torch.bfloat16, False, False),
+                                                          (4, 64, 64, 59, 61, torch.float16, True, True),
+                                                          (2, 304, 288, 292, 283, torch.float16, True, False),
+                                                          (1, 592, 576, 584, 565, torch.bfloat16, True, True)]:
+            c = 64
+            x = torch.randn(n, h, w, c, generator=g).to(dev).to(dt)
+            coef = torch.stack([1 + 0.1 * torch.randn(n, c, generator=g), 0.1 * torch.randn(n, c, generator=g)], -1).to(dev).contiguous()
+            wh = (torch.randn(c, generator=g) / 8).to(dev)
+            fov = (torch.rand(n if per_image else 1, h0, w0, generator=g) > 0.3).float().to(dev)
+            mask = (torch.rand(n, h, w, 8, generator=g) * 256).to(torch.uint8).to(dev) if use_mask else None
+            hd = HeadDesc()
+            hd.n, hd.h, hd.w, hd.c, hd.h0, hd.w0 = n, h, w, c, h0, w0
+            hd.dtype, hd.return_num, hd.fov_per_image = (_lib.BF16 if dt == torch.bfloat16 else _lib.F16), 2, int(per_image)
+            res = []
+            for variant in ("1", "0"):
+                os.environ["B2U_HEAD_ASYNC"] = variant
+                out = torch.zeros(n, 1, h0, w0, device=dev)
+                logits = torch.zeros(n, 1, h0, w0, device=dev)
+                acc = torch.full((2, h0, w0), 0.25, dtype=torch.float64, device=dev)      # accumulates ONTO what is there
+                samples = torch.zeros(2, h0, w0, device=dev)
+                it = torch.ones(1, dtype=torch.int64, device=dev)                         # iteration 1: only image 0 is a saved sample
+                call("b2u_head_fwd", ptr(x), ptr(coef), ptr(mask) if use_mask else None, ptr(wh), ptr(out), ptr(logits), ptr(fov),
+                     ptr(acc), ptr(samples), ptr(it), C.byref(hd), stream_ptr())
+                torch.cuda.synchronize()
+                res.append((out, logits, acc, samples))
+            same = all(torch.equal(a, b) for a, b in zip(*res))
+            same_all &= same
+            z = x.float() * coef[:, None, None, :, 0] + coef[:, None, None, :, 1]
+            if use_mask:
+                bits = ((mask[..., :, None].int() >> torch.arange(8, device=dev)) & 1).reshape(n, h, w, c).bool()
+                z = torch.where(bits, z, torch.zeros_like(z))
+            lg = (torch.relu(z) * wh).sum(-1)[:, :h0, :w0]
+            y = torch.sigmoid(lg)
+            v = y * (fov if per_image else fov[0])
+            out, logits, acc, samples = res[0]
+            r = max(rel(logits[:, 0], lg)[0], rel(out[:, 0], y)[0], rel(acc[0] - 0.25, v.double().sum(0))[0],
+                    rel(acc[1] - 0.25, (v.double() ** 2).sum(0))[0], rel(samples[1], v[0])[0], float(samples[0].abs().max()))
+            worst = max(worst, r)
+            print(f"  head variants {n}x{h}x{w} -> {h0}x{w0} mask={use_mask} fov_per_image={per_image}: kernels {'bit-identical' if same else 'DIFFER'}, vs torch rel {r:.3e}")
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+    return same_all, worst
 
 
 def sec_head():

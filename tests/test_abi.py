@@ -218,3 +218,37 @@ def test_pack_batched_plan_without_gpu():
     ents[1].cin, ents[1].kind = 128, 7
     with pytest.raises(_lib.B2uError, match="kind"):
         _lib.call("b2u_pack_batched_plan", C.byref(ents), 3, C.byref(blocks))
+
+
+def test_head_plan_without_gpu(monkeypatch):
+    """b2u_head_plan is host-only: the launch shape of the c = 64 head covers every pixel octet, the block size is the one
+    that fills the last trip better, the cp.async ring fits twice per SM, and the diagnostic overrides are validated."""
+    for k in ("B2U_HEAD_ASYNC", "B2U_HEAD_THREADS", "B2U_HEAD_STAGES"):
+        monkeypatch.delenv(k, raising=False)
+    plan = (C.c_int * 6)()
+    for h0, w0 in [(584, 565), (146, 141), (292, 283), (128, 128), (256, 256), (584, 584), (1, 1), (7, 3), (2048, 2048)]:
+        _lib.call("b2u_head_plan", h0, w0, 148, plan)
+        variant, nt, grid, trips, stages, ring = list(plan)
+        gtrips = (h0 * w0 + 7) // 8
+        assert variant == 1 and nt in (224, 192) and stages == 2
+        assert ring == nt * stages * (8 * 16 + 8) and 2 * (ring + 1024) <= 227 * 1024
+        assert 1 <= grid <= 2 * 148 and grid * (nt // 8) * trips >= gtrips          # every octet has an owner
+        assert grid * (nt // 8) * (trips - 1) < gtrips                              # ... and no trip is all empty
+        fill = {c: gtrips / (-(-gtrips // (296 * c // 8)) * (296 * c // 8)) for c in (224, 192)}
+        if gtrips >= 296 * 224 // 8:
+            assert fill[nt] >= max(fill.values()) - 1e-9
+    _lib.call("b2u_head_plan", 584, 565, 148, plan)
+    assert list(plan)[:4] == [1, 224, 296, 5]                                       # 41245 octets over 8288 resident groups: 99.5 % full
+    monkeypatch.setenv("B2U_HEAD_ASYNC", "0")
+    _lib.call("b2u_head_plan", 584, 565, 148, plan)
+    assert list(plan) == [0, 256, 296, 5, 2, 0]                                     # register kernel: 9472 groups, fifth trip 35 % full
+    monkeypatch.setenv("B2U_HEAD_ASYNC", "1")
+    monkeypatch.setenv("B2U_HEAD_THREADS", "224")
+    monkeypatch.setenv("B2U_HEAD_STAGES", "4")
+    with pytest.raises(_lib.B2uError, match="does not fit twice"):
+        _lib.call("b2u_head_plan", 584, 565, 148, plan)
+    monkeypatch.setenv("B2U_HEAD_THREADS", "100")
+    with pytest.raises(_lib.B2uError, match="multiple of 32"):
+        _lib.call("b2u_head_plan", 584, 565, 148, plan)
+    with pytest.raises(_lib.B2uError, match="bad arguments"):
+        _lib.call("b2u_head_plan", 0, 565, 148, plan)

@@ -152,6 +152,13 @@ def test_head_and_mc_accumulate():
     assert D.sec_head() < 1e-6
 
 
+def test_head_ring_kernel_bit_identical_to_register_kernel():
+    """Default head (cp.async ring) == the register kernel bit for bit (outputs, logits, fp64 accumulators, samples), both
+    within fp32 rounding of torch: masks on / off, shared and per-image fov, one and several trips per block."""
+    same, worst = D.sec_head_variants()
+    assert same and worst < 2e-6
+
+
 @pytest.mark.parametrize("dilate", ["v2", "v1"])
 def test_dropblock_masks_bit_exact_vs_torch_rand(dilate, monkeypatch):
     """v2 = sparse NHWC scatter + word-parallel 7x7 OR (default for block size 7), v1 = 32x32 bit-transpose kernel."""

@@ -102,6 +102,7 @@ SIGNATURES = {
     "b2u_pool_stat_layout": (_I, [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I)]),
     "b2u_gn_apply_pool": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, C.POINTER(ApplyDesc), _P]),
     "b2u_head_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(HeadDesc), _P]),
+    "b2u_head_plan": (_I, [_I, _I, _I, C.POINTER(_I)]),
     "b2u_mc_finalize": (_I, [_P, _P, _P, _LL, _LL, _P]),
     "b2u_mc_accumulate": (_I, [_P, _P, _P, _P, _P, _I, _LL, _I, _P]),
     "b2u_advance_counter": (_I, [_P, _LL, _P]),

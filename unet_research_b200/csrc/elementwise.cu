@@ -1248,6 +1248,48 @@ extern "C" int b2u_gn_apply_pool(const void* x, const float* coef, const uint32_
   return B2U_OK;
 }
 
+// Launch shape of the c = 64, 16-bit head (host only; CPU-tested through the ABI).  plan[0] = variant (1: cp.async ring
+// kernel, 0: register kernel), [1] = threads per block, [2] = blocks, [3] = trips per block, [4] = ring stages,
+// [5] = dynamic shared memory per block.  Default: the ring kernel with 2 stages and 224 or 192 threads per block,
+// whichever fills the last trip better (tests/exp_head.py, profiles/r02i_exp_head.log: at 10 x 584 x 565 the register
+// kernel at 256 threads takes 104 us, the ring kernel 95 us with 2 stages x 224 threads, 101 us with 3 stages, 110 us
+// with 4 -- the larger the ring the smaller L1 -- and 110-126 us at 256 threads, whose 9472 resident groups leave the
+// fifth trip 35 % full).  Diagnostic overrides, read per call: B2U_HEAD_ASYNC=0 (register kernel, 256 threads),
+// B2U_HEAD_THREADS, B2U_HEAD_STAGES.
+extern "C" int b2u_head_plan(int h0, int w0, int num_sms, int* plan) {
+  B2U_REQUIRE(plan && h0 > 0 && w0 > 0 && num_sms > 0, "bad arguments");
+  // 8 pixels per 8-lane group and trip; grid = at most the resident slots (2 blocks per SM), every block walks ceil(trips)
+  // of them -- the last trip is partly empty.  (An integral trip count made 258 blocks of 5 trips at 584x565: 110 SMs
+  // with two blocks, 38 with one -- the busiest SM did 10 trips where 9 suffice.)
+  const long gtrips = (static_cast<long>(h0) * w0 + 7) / 8;
+  int nt = 0, use_async = 1, stages = 2;
+  if (const char* e = getenv("B2U_HEAD_ASYNC")) use_async = atoi(e) != 0;
+  if (const char* e = getenv("B2U_HEAD_THREADS")) nt = atoi(e);
+  if (const char* e = getenv("B2U_HEAD_STAGES")) stages = atoi(e);
+  const long sms2 = static_cast<long>(num_sms) * 2;                       // blocks resident at once
+  if (nt == 0 && !use_async) nt = 256;
+  if (nt == 0) {
+    double best = -1.0;
+    for (int cand = 224; cand >= 192; cand -= 32) {
+      const long resident = sms2 * (cand / 8);
+      const long tr = (gtrips + resident - 1) / resident;
+      const double fill = gtrips >= resident ? static_cast<double>(gtrips) / static_cast<double>(tr * resident) : 1.0;
+      if (fill > best + 1e-9) { best = fill; nt = cand; }
+    }
+  }
+  B2U_REQUIRE(nt >= 64 && nt <= 256 && nt % 32 == 0, "B2U_HEAD_THREADS must be 64..256, a multiple of 32");
+  B2U_REQUIRE(stages >= 2 && stages <= 4, "B2U_HEAD_STAGES must be 2, 3 or 4");
+  const long gpb = nt / 8;                                                // groups per block
+  const long slots = sms2 * gpb;                                          // groups resident at once
+  const long grid8 = gtrips >= slots ? sms2 : (gtrips + gpb - 1) / gpb;
+  const long trips = (gtrips + gpb * grid8 - 1) / (gpb * grid8);
+  const int ring_bytes = use_async ? nt * stages * (8 * 16 + 8) : 0;
+  B2U_REQUIRE(2 * (ring_bytes + 1024) <= 227 * 1024, "head ring of %d bytes does not fit twice per SM", ring_bytes);
+  plan[0] = use_async; plan[1] = nt; plan[2] = static_cast<int>(grid8); plan[3] = static_cast<int>(trips);
+  plan[4] = stages; plan[5] = ring_bytes;
+  return B2U_OK;
+}
+
 extern "C" int b2u_head_fwd(const void* x, const float* coef, const uint32_t* mask1, const float* w_head, float* out,
                             float* logits, const float* fov, double* acc, float* samples, const long long* iter_base,
                             const b2u_head_desc* d, void* stream) {
@@ -1260,39 +1302,10 @@ extern "C" int b2u_head_fwd(const void* x, const float* coef, const uint32_t* ma
   const int grid = grid_for((groups + kHeadPix - 1) / kHeadPix * (d->c / 8), 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (d->c == 64 && d->dtype != B2U_F32 && static_cast<long>(d->h) * d->w < (1l << 31)) {
-    // 8 pixels per 8-lane group and trip; grid = exactly the resident slots (2 blocks per SM), every block walks
-    // ceil(trips) of them -- the last trip is partly empty.  (An integral trip count made 258 blocks of 5 trips at
-    // 584x565: 110 SMs with two blocks, 38 with one -- the busiest SM did 10 trips where 9 suffice.)
-    const long gtrips = (groups + 7) / 8;
-    // Variant and shape of the launch.  Default: the cp.async ring kernel with 2 stages and 224 or 192 threads per block,
-    // whichever fills the last trip better (tests/exp_head.py, profiles/r02i_exp_head.log: at 10 x 584 x 565 the register
-    // kernel at 256 threads takes 104 us, the ring kernel 95 us with 2 stages x 224 threads, 101 us with 3 stages, 110 us
-    // with 4 -- the larger the ring the smaller L1 -- and 110-126 us at 256 threads, whose 9472 resident groups leave
-    // the fifth trip 35 % full).  Diagnostic overrides, read per call: B2U_HEAD_ASYNC=0 (register kernel, 256 threads),
-    // B2U_HEAD_THREADS, B2U_HEAD_STAGES.
-    int nt = 0, use_async = 1, stages = 2;
-    if (const char* e = getenv("B2U_HEAD_ASYNC")) use_async = atoi(e);
-    if (const char* e = getenv("B2U_HEAD_THREADS")) nt = atoi(e);
-    if (const char* e = getenv("B2U_HEAD_STAGES")) stages = atoi(e);
-    const long sms2 = static_cast<long>(b2u_num_sms()) * 2;                 // blocks resident at once
-    if (nt == 0 && !use_async) nt = 256;
-    if (nt == 0) {
-      double best = -1.0;
-      for (int cand = 224; cand >= 192; cand -= 32) {
-        const long g = cand / 8, resident = sms2 * g;
-        const long tr = gtrips >= resident ? (gtrips + resident - 1) / resident : 1;
-        const double fill = gtrips >= resident ? static_cast<double>(gtrips) / static_cast<double>(tr * resident) : 1.0;
-        if (fill > best + 1e-9) { best = fill; nt = cand; }
-      }
-    }
-    B2U_REQUIRE(nt >= 64 && nt <= 256 && nt % 32 == 0, "B2U_HEAD_THREADS must be 64..256, a multiple of 32");
-    B2U_REQUIRE(stages >= 2 && stages <= 4, "B2U_HEAD_STAGES must be 2, 3 or 4");
-    const long gpb = nt / 8;                                                // groups per block
-    const long slots = sms2 * gpb;                                          // groups resident at once
-    const int grid8 = static_cast<int>(gtrips >= slots ? slots / gpb : (gtrips + gpb - 1) / gpb);
-    const int trips = static_cast<int>((gtrips + gpb * grid8 - 1) / (gpb * grid8));
-    const int ring_bytes = nt * stages * (8 * 16 + 8);
-    B2U_REQUIRE(!use_async || 2 * (ring_bytes + 1024) <= 227 * 1024, "head ring of %d bytes does not fit twice per SM", ring_bytes);
+    int hp[6];
+    const int prc = b2u_head_plan(d->h0, d->w0, b2u_num_sms(), hp);
+    if (prc) return prc;
+    const int use_async = hp[0], nt = hp[1], grid8 = hp[2], trips = hp[3], stages = hp[4], ring_bytes = hp[5];
 #define B2U_HEAD8_T(T)                                                                                              \
   do {                                                                                                              \
     if (use_async && stages == 3) {                                                                                 \
